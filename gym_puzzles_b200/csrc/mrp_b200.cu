@@ -1,0 +1,574 @@
+// mrp_b200.cu — sm_100a kernels + the C-ABI of include/mrp_b200.h.
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared ...
+// -fmad=false is load-bearing: Box2D on x86-64 never fuses mul+add, and contact / done
+// flags must be bit-exact (BASELINE.json north_star).
+//
+// The same translation unit also builds as plain C++ with -DMRP_HOST_EMU (g++ -x c++) into
+// tests/emu/libmrp_emu.so: a host execution of the *kernel source* used only to debug
+// kernel logic in the GPU-less build container.  The Python package never loads it.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "mrp_env.cuh"
+#include "mrp_variant.hpp"
+
+#ifndef MRP_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+using namespace mrp;
+
+// ------------------------------------------------------------------------------------
+// kernels (device) / loops (host emulation)
+// ------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kCtPad = (CT_WORDS + 31) & ~31;
+
+MRP_HD void stat_add(double* stats, int slot, double v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(stats + slot, v);
+#else
+    stats[slot] += v;
+#endif
+}
+
+// one env.step incl. TimeLimit; done envs are queued for the reset pass
+MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+    Env e(K, sm, ct, env);
+    e.load();
+    float a[3 * MRP_MAX_AGENTS];
+    const float* arow = K.act + env * K.act_dim;
+    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+    double r;
+    bool d = e.env_step(a, K.obs + env * K.obs_dim, &r, false);
+    uint32_t elapsed = e.g(W_ELAPSED) + 1u;
+    e.g(W_ELAPSED) = elapsed;
+    bool limit = (int)elapsed >= K.max_steps;
+    bool done = d || limit;
+    K.rew[env] = (float)r;
+    K.done[env] = done ? 1 : 0;
+    K.trunc[env] = (limit && !d) ? 1 : 0;
+    double ret = e.gd(W_EPRET) + r;
+    uint32_t len = e.g(W_EPLEN) + 1u;
+    e.gsd(W_EPRET, ret);
+    e.g(W_EPLEN) = len;
+    e.store();
+    if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
+    if (done) {
+        stat_add(K.stats, MRP_STAT_EPISODES, 1.0);
+        if (d) stat_add(K.stats, MRP_STAT_DONE_BY_ENV, 1.0);
+        if (limit && !d) stat_add(K.stats, MRP_STAT_TRUNCATED, 1.0);
+        stat_add(K.stats, MRP_STAT_SUM_RETURN, ret);
+        stat_add(K.stats, MRP_STAT_SUM_RETURN_SQ, ret * ret);
+        stat_add(K.stats, MRP_STAT_SUM_LENGTH, (double)len);
+        if (K.auto_reset) {
+#if defined(__CUDA_ARCH__)
+            int slot = atomicAdd(K.reset_count, 1);
+#else
+            int slot = (*K.reset_count)++;
+#endif
+            K.reset_list[slot] = (int32_t)env;
+        }
+    }
+}
+
+MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+    Env e(K, sm, ct, env);
+    e.reset_env(K.obs + env * K.obs_dim);
+    if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
+}
+
+MRP_HD void sample_actions_lane(const SimConst& K, float* dst, uint64_t step_index, int64_t env) {
+    uint64_t gid = K.env_id_base + (uint64_t)env;
+    for (int k = 0; k < K.act_dim; ++k)
+        dst[env * K.act_dim + k] = (float)(-1.0 + 2.0 * uniform53(K.seed, kStreamAction, gid, (uint32_t)step_index, (uint32_t)k));
+}
+
+MRP_HD void fix_rot_lane(const SimConst& K, int64_t env) {  // q = Rot(a) after a state upload
+    for (int b = 0; b < K.nb; ++b) {
+        uint32_t* G = K.S + env;
+        union { uint32_t u; float f; } c;
+        c.u = G[(int64_t)(K.w_body + 8 * b + 2) * K.N];
+        Rot q = rot_set(c.f);
+        c.f = q.s; G[(int64_t)(K.w_body + 8 * b + 6) * K.N] = c.u;
+        c.f = q.c; G[(int64_t)(K.w_body + 8 * b + 7) * K.N] = c.u;
+    }
+}
+
+#ifndef MRP_HOST_EMU
+__device__ __forceinline__ const float* load_ctab(const SimConst& K, float* smem) {
+    for (int i = threadIdx.x; i < CT_WORDS; i += blockDim.x) smem[i] = K.ctab[i];
+    __syncthreads();
+    return smem;
+}
+
+__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
+    step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+}
+
+// reset pass over the queue the step kernel filled (auto-reset)
+__global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    int count = *K.reset_count;
+    if ((int64_t)blockIdx.x * kBlock >= count) return;
+    const float* ct = load_ctab(K, smem);
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= count) return;
+    reset_lane(K, smem + kCtPad + threadIdx.x, ct, K.reset_list[i]);
+}
+
+__global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
+    if (K.reset_mask && !K.reset_mask[env]) return;
+    reset_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+}
+
+__global__ void k_clear_count(int32_t* p) { *p = 0; }
+
+__global__ void k_sample_actions(const __grid_constant__ SimConst K, float* dst, uint64_t step_index) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < K.N) sample_actions_lane(K, dst, step_index, env);
+}
+
+__global__ void k_fix_rot(const __grid_constant__ SimConst K, int64_t begin, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) fix_rot_lane(K, begin + i);
+}
+#endif
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------
+struct mrp_handle {
+    SimConst K;
+    mrp_layout L;
+    int device;
+    float* ctab_dev;
+    float* act_dev;
+    int64_t launches;
+    size_t smem_bytes;
+#ifdef MRP_HOST_EMU
+    float* emu_sm;
+#endif
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#ifdef MRP_HOST_EMU
+#define DEV_ALLOC(ptr, bytes) ((*(void**)&(ptr) = calloc(1, (bytes))) ? 0 : -1)
+#define DEV_FREE(ptr) free(ptr)
+#define H2D(dst, src, bytes) (memcpy((dst), (src), (bytes)), 0)
+#define D2H(dst, src, bytes) (memcpy((dst), (src), (bytes)), 0)
+#define DEV_ZERO(ptr, bytes) (memset((ptr), 0, (bytes)), 0)
+static const char* dev_err() { return "host allocation failed"; }
+#else
+#define DEV_ALLOC(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess ? (cudaMemset((ptr), 0, (bytes)), 0) : -1)
+#define DEV_FREE(ptr) cudaFree(ptr)
+#define H2D(dst, src, bytes) (cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1)
+#define D2H(dst, src, bytes) (cudaMemcpy((dst), (src), (bytes), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1)
+#define DEV_ZERO(ptr, bytes) (cudaMemset((ptr), 0, (bytes)) == cudaSuccess ? 0 : -1)
+static const char* dev_err() { return cudaGetErrorString(cudaGetLastError()); }
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return -10;
+    }
+    return 0;
+}
+#endif
+
+extern "C" {
+
+const char* mrp_last_error(void) { return g_err; }
+
+const char* mrp_backend(void) {
+#ifdef MRP_HOST_EMU
+    return "host-emu (test only)";
+#else
+    return "cuda-sm_100a";
+#endif
+}
+
+int mrp_destroy(mrp_handle* h) {
+    if (!h) return 0;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+#else
+    free(h->emu_sm);
+#endif
+    DEV_FREE(h->K.S);
+    DEV_FREE(h->ctab_dev);
+    DEV_FREE(h->act_dev);
+    DEV_FREE(h->K.obs);
+    DEV_FREE(h->K.rew);
+    DEV_FREE(h->K.done);
+    DEV_FREE(h->K.trunc);
+    DEV_FREE(h->K.stats);
+    DEV_FREE(h->K.reset_list);
+    DEV_FREE(h->K.reset_count);
+    delete h;
+    return 0;
+}
+
+int mrp_create(const mrp_config* cfg, mrp_handle** out) {
+    if (!cfg || !out) return fail(-1, "mrp_create: null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return fail(-2, "mrp_create: num_envs must be > 0");
+#ifndef MRP_HOST_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(-3, "mrp_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(cudaGetLastError()));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(-4, "mrp_create: bad device ordinal");
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(-4, "mrp_create: cudaSetDevice failed: %s", dev_err());
+#endif
+    mrp_handle* h = new (std::nothrow) mrp_handle();
+    if (!h) return fail(-5, "mrp_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    float ctab[CT_WORDS];
+    if (build_variant(cfg->variant, cfg->n_agents, &h->K, ctab, &h->L) != 0) {
+        delete h;
+        return fail(-6, "mrp_create: bad variant / n_agents (v2 variants support num_agents <= 2 in this build)");
+    }
+    SimConst& K = h->K;
+    if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
+    K.auto_reset = cfg->auto_reset ? 1 : 0;
+    K.seed = cfg->seed;
+    K.env_id_base = cfg->env_id_base;
+    K.N = cfg->num_envs;
+    h->device = cfg->device;
+    const size_t N = (size_t)cfg->num_envs;
+    int rc = 0;
+    rc |= DEV_ALLOC(K.S, sizeof(uint32_t) * N * K.w_total);
+    rc |= DEV_ALLOC(h->ctab_dev, sizeof(float) * CT_WORDS);
+    rc |= DEV_ALLOC(h->act_dev, sizeof(float) * N * K.act_dim);
+    rc |= DEV_ALLOC(K.obs, sizeof(float) * N * K.obs_dim);
+    rc |= DEV_ALLOC(K.rew, sizeof(float) * N);
+    rc |= DEV_ALLOC(K.done, N);
+    rc |= DEV_ALLOC(K.trunc, N);
+    rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
+    rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.reset_count, sizeof(int32_t));
+    if (rc) {
+        fail(-7, "mrp_create: device allocation failed: %s", dev_err());
+        mrp_destroy(h);
+        return -7;
+    }
+    K.ctab = h->ctab_dev;
+    K.act = h->act_dev;
+    H2D(h->ctab_dev, ctab, sizeof(ctab));
+    // episode counter starts at -1 so the first reset spawns episode 0; v0 goal is fixed
+    {
+        uint32_t* row = (uint32_t*)malloc(sizeof(uint32_t) * N);
+        for (size_t i = 0; i < N; ++i) row[i] = 0xffffffffu;
+        H2D(K.S + (size_t)W_EPISODE * N, row, sizeof(uint32_t) * N);
+        union { double d; uint32_t u[2]; } gx, gy;
+        gx.d = K.goal_x0; gy.d = K.goal_y0;
+        const uint32_t vals[4] = {gx.u[0], gx.u[1], gy.u[0], gy.u[1]};
+        for (int w = 0; w < 4; ++w) {
+            for (size_t i = 0; i < N; ++i) row[i] = vals[w];
+            H2D(K.S + (size_t)(W_GOAL + w) * N, row, sizeof(uint32_t) * N);
+        }
+        free(row);
+    }
+    h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
+#ifndef MRP_HOST_EMU
+    cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_reset_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_reset_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (check_launch("mrp_create")) { mrp_destroy(h); return -10; }
+#else
+    h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
+    memcpy(h->ctab_dev, ctab, sizeof(ctab));
+#endif
+    *out = h;
+    return 0;
+}
+
+int mrp_get_layout(mrp_handle* h, mrp_layout* out) {
+    if (!h || !out) return fail(-1, "mrp_get_layout: null argument");
+    *out = h->L;
+    return 0;
+}
+
+int mrp_get_buffers(mrp_handle* h, mrp_buffers* out) {
+    if (!h || !out) return fail(-1, "mrp_get_buffers: null argument");
+    out->action_dev = h->act_dev;
+    out->obs_dev = h->K.obs;
+    out->reward_dev = h->K.rew;
+    out->done_dev = h->K.done;
+    out->trunc_dev = h->K.trunc;
+    out->stats_dev = h->K.stats;
+    out->num_envs = (int32_t)h->K.N;
+    out->obs_dim = h->K.obs_dim;
+    out->act_dim = h->K.act_dim;
+    out->reserved = 0;
+    return 0;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+int mrp_reset(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
+    if (!h) return fail(-1, "mrp_reset: null handle");
+    SimConst K = h->K;
+    K.reset_mask = mask_dev;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    k_reset_mask<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, (cudaStream_t)stream>>>(K);
+    h->launches += 1;
+    return check_launch("mrp_reset");
+#else
+    (void)stream;
+    for (int64_t e = 0; e < K.N; ++e)
+        if (!mask_dev || mask_dev[e]) reset_lane(K, h->emu_sm, h->ctab_dev, e);
+    return 0;
+#endif
+}
+
+int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
+    if (!h) return fail(-1, "mrp_step: null handle");
+    SimConst K = h->K;
+    if (actions_dev) K.act = actions_dev;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K.auto_reset) k_clear_count<<<1, 1, 0, st>>>(K.reset_count);
+    k_step<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
+    h->launches += 1;
+    if (K.auto_reset) {
+        k_reset_list<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 2;
+    }
+    return check_launch("mrp_step");
+#else
+    (void)stream;
+    *K.reset_count = 0;
+    for (int64_t e = 0; e < K.N; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
+    for (int i = 0; i < *K.reset_count; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+    return 0;
+#endif
+}
+
+int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                  uint8_t* trunc_host) {
+    if (!h || !actions_host) return fail(-1, "mrp_step_host: null argument");
+    const size_t N = (size_t)h->K.N;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    cudaStream_t st = 0;
+    if (cudaMemcpyAsync(h->act_dev, actions_host, sizeof(float) * N * h->K.act_dim, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
+    int rc = mrp_step(h, nullptr, st);
+    if (rc) return rc;
+    if (obs_host) cudaMemcpyAsync(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim, cudaMemcpyDeviceToHost, st);
+    if (reward_host) cudaMemcpyAsync(reward_host, h->K.rew, sizeof(float) * N, cudaMemcpyDeviceToHost, st);
+    if (done_host) cudaMemcpyAsync(done_host, h->K.done, N, cudaMemcpyDeviceToHost, st);
+    if (trunc_host) cudaMemcpyAsync(trunc_host, h->K.trunc, N, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(-9, "mrp_step_host: %s", dev_err());
+    return 0;
+#else
+    memcpy(h->act_dev, actions_host, sizeof(float) * N * h->K.act_dim);
+    int rc = mrp_step(h, nullptr, nullptr);
+    if (rc) return rc;
+    if (obs_host) memcpy(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim);
+    if (reward_host) memcpy(reward_host, h->K.rew, sizeof(float) * N);
+    if (done_host) memcpy(done_host, h->K.done, N);
+    if (trunc_host) memcpy(trunc_host, h->K.trunc, N);
+    return 0;
+#endif
+}
+
+int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host) {
+    if (!h) return fail(-1, "mrp_reset_host: null handle");
+    const size_t N = (size_t)h->K.N;
+    uint8_t* mask_dev = nullptr;
+    if (mask_host) {
+        // done_dev doubles as the staging buffer for the mask; it is rewritten by the next step
+        mask_dev = h->K.done;
+        if (H2D(mask_dev, mask_host, N)) return fail(-8, "mrp_reset_host: H2D failed: %s", dev_err());
+    }
+    int rc = mrp_reset(h, mask_dev, nullptr);
+    if (rc) return rc;
+    if (obs_host && D2H(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim)) return fail(-9, "mrp_reset_host: D2H failed: %s", dev_err());
+#ifndef MRP_HOST_EMU
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(-9, "mrp_reset_host: %s", dev_err());
+#endif
+    return 0;
+}
+
+int mrp_sample_actions(mrp_handle* h, uint64_t step_index, float* dst_dev, void* stream) {
+    if (!h) return fail(-1, "mrp_sample_actions: null handle");
+    float* dst = dst_dev ? dst_dev : h->act_dev;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    k_sample_actions<<<grid_for(h->K.N, 256), 256, 0, (cudaStream_t)stream>>>(h->K, dst, step_index);
+    h->launches += 1;
+    return check_launch("mrp_sample_actions");
+#else
+    (void)stream;
+    for (int64_t e = 0; e < h->K.N; ++e) sample_actions_lane(h->K, dst, step_index, e);
+    return 0;
+#endif
+}
+
+// ---- canonical state records <-> internal [word][env] layout (host side) --------------
+static int fetch_internal(mrp_handle* h, int64_t begin, int64_t count, uint32_t* buf) {
+    const SimConst& K = h->K;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy2D(buf, sizeof(uint32_t) * count, K.S + begin, sizeof(uint32_t) * K.N, sizeof(uint32_t) * count, K.w_total,
+                     cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+#else
+    for (int w = 0; w < K.w_total; ++w) memcpy(buf + (size_t)w * count, K.S + (size_t)w * K.N + begin, sizeof(uint32_t) * count);
+#endif
+    return 0;
+}
+static int push_internal(mrp_handle* h, int64_t begin, int64_t count, const uint32_t* buf) {
+    const SimConst& K = h->K;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (cudaMemcpy2D(K.S + begin, sizeof(uint32_t) * K.N, buf, sizeof(uint32_t) * count, sizeof(uint32_t) * count, K.w_total,
+                     cudaMemcpyHostToDevice) != cudaSuccess)
+        return -1;
+    k_fix_rot<<<grid_for(count, 128), 128>>>(K, begin, count);
+    h->launches += 1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+#else
+    for (int w = 0; w < K.w_total; ++w) memcpy(K.S + (size_t)w * K.N + begin, buf + (size_t)w * count, sizeof(uint32_t) * count);
+    for (int64_t e = 0; e < count; ++e) fix_rot_lane(K, begin + e);
+#endif
+    return 0;
+}
+
+int mrp_get_state(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t* words) {
+    if (!h || !words) return fail(-1, "mrp_get_state: null argument");
+    if (env_begin < 0 || env_count < 0 || (int64_t)env_begin + env_count > h->K.N) return fail(-2, "mrp_get_state: bad env range");
+    const SimConst& K = h->K;
+    const mrp_layout& L = h->L;
+    const size_t C = (size_t)env_count;
+    uint32_t* buf = (uint32_t*)malloc(sizeof(uint32_t) * C * K.w_total);
+    if (!buf) return fail(-5, "mrp_get_state: out of host memory");
+    if (fetch_internal(h, env_begin, env_count, buf)) { free(buf); return fail(-9, "mrp_get_state: copy failed: %s", dev_err()); }
+    auto I = [&](int w, size_t e) -> uint32_t { return buf[(size_t)w * C + e]; };
+    memset(words, 0, sizeof(uint32_t) * C * L.state_words);
+    for (size_t e = 0; e < C; ++e) {
+        uint32_t* o = words + e * L.state_words;
+        o[0] = I(W_ELAPSED, e); o[1] = I(W_EPISODE, e); o[2] = I(W_INPLACE, e);
+        int nc = (int)I(W_NC, e);
+        o[3] = (uint32_t)nc;
+        uint32_t gc = I(W_GOALC, e);
+        for (int i = 0; i < K.n; ++i) o[L.off_goal_contact + i] = (gc >> i) & 1u;
+        for (int b = 0; b < K.nb; ++b)
+            for (int f = 0; f < 6; ++f) o[L.off_bodies + 6 * b + f] = I(K.w_body + 8 * b + f, e);
+        for (int i = 0; i < 2 * (K.n + 1); ++i) o[L.off_dists + i] = I(W_DIST + i, e);
+        for (int i = 0; i < 4; ++i) o[L.off_goal + i] = I(W_GOAL + i, e);
+        o[L.off_episode_acc] = I(W_EPRET, e); o[L.off_episode_acc + 1] = I(W_EPRET + 1, e);
+        o[L.off_episode_acc + 2] = I(W_EPLEN, e);
+        for (int i = 0; i < 4 * K.ndynfix; ++i) o[L.off_aabb + i] = I(K.w_aabb + i, e);
+        // internal slots are oldest-first; the record is world-list order (newest first)
+        for (int r = 0; r < nc; ++r) {
+            int k = nc - 1 - r;
+            uint32_t* cwp = o + L.off_contacts + MRP_CONTACT_WORDS * r;
+            uint32_t m = I(K.w_con + MRP_CONTACT_WORDS * k, e);
+            int pc = (m >> 18) & 3;
+            cwp[0] = m & 0x000fffffu;
+            if (pc == 0) continue;  // stale manifold words are not part of the state
+            uint32_t keys = I(K.w_con + MRP_CONTACT_WORDS * k + 1, e);
+            cwp[1] = pc == 1 ? (keys & 0xffffu) : keys;
+            for (int j = 2; j < 6 + 4 * pc; ++j) cwp[j] = I(K.w_con + MRP_CONTACT_WORDS * k + j, e);
+        }
+    }
+    free(buf);
+    return 0;
+}
+
+int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uint32_t* words) {
+    if (!h || !words) return fail(-1, "mrp_set_state: null argument");
+    if (env_begin < 0 || env_count < 0 || (int64_t)env_begin + env_count > h->K.N) return fail(-2, "mrp_set_state: bad env range");
+    const SimConst& K = h->K;
+    const mrp_layout& L = h->L;
+    const size_t C = (size_t)env_count;
+    uint32_t* buf = (uint32_t*)calloc(C * K.w_total, sizeof(uint32_t));
+    if (!buf) return fail(-5, "mrp_set_state: out of host memory");
+    auto I = [&](int w, size_t e) -> uint32_t& { return buf[(size_t)w * C + e]; };
+    for (size_t e = 0; e < C; ++e) {
+        const uint32_t* o = words + e * L.state_words;
+        I(W_ELAPSED, e) = o[0]; I(W_EPISODE, e) = o[1]; I(W_INPLACE, e) = o[2];
+        int nc = (int)o[3];
+        if (nc > K.maxc) { free(buf); return fail(-2, "mrp_set_state: n_contacts exceeds capacity"); }
+        I(W_NC, e) = (uint32_t)nc;
+        uint32_t gc = 0;
+        for (int i = 0; i < K.n; ++i) gc |= (o[L.off_goal_contact + i] ? 1u : 0u) << i;
+        I(W_GOALC, e) = gc;
+        for (int b = 0; b < K.nb; ++b)
+            for (int f = 0; f < 6; ++f) I(K.w_body + 8 * b + f, e) = o[L.off_bodies + 6 * b + f];
+        for (int i = 0; i < 2 * (K.n + 1); ++i) I(W_DIST + i, e) = o[L.off_dists + i];
+        for (int i = 0; i < 4; ++i) I(W_GOAL + i, e) = o[L.off_goal + i];
+        I(W_EPRET, e) = o[L.off_episode_acc]; I(W_EPRET + 1, e) = o[L.off_episode_acc + 1];
+        I(W_EPLEN, e) = o[L.off_episode_acc + 2];
+        for (int i = 0; i < 4 * K.ndynfix; ++i) I(K.w_aabb + i, e) = o[L.off_aabb + i];
+        for (int r = 0; r < nc; ++r) {
+            int k = nc - 1 - r;
+            const uint32_t* cwp = o + L.off_contacts + MRP_CONTACT_WORDS * r;
+            uint32_t m = cwp[0] & 0x000fffffu;
+            int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            if (fa >= K.nfix || fb >= K.nfix) { free(buf); return fail(-2, "mrp_set_state: bad fixture index"); }
+            // body ids of the two fixtures (fixture order: stem, bar, agents..., walls)
+            auto body_of = [&](int f) { return f < 2 ? 0 : (f < K.ndynfix ? 1 + (f - 2) / K.per_agent : K.nb + (f - K.ndynfix)); };
+            m |= ((uint32_t)body_of(fa) << 20) | ((uint32_t)body_of(fb) << 24);
+            I(K.w_con + MRP_CONTACT_WORDS * k, e) = m;
+            for (int j = 1; j < MRP_CONTACT_WORDS; ++j) I(K.w_con + MRP_CONTACT_WORDS * k + j, e) = cwp[j];
+        }
+    }
+    int rc = push_internal(h, env_begin, env_count, buf);
+    free(buf);
+    if (rc) return fail(-9, "mrp_set_state: copy failed: %s", dev_err());
+    return 0;
+}
+
+int mrp_set_params(mrp_handle* h, const mrp_params* p) {
+    if (!h || !p) return fail(-1, "mrp_set_params: null argument");
+    h->K.rp = *p;
+    return 0;
+}
+int mrp_get_params(mrp_handle* h, mrp_params* p) {
+    if (!h || !p) return fail(-1, "mrp_get_params: null argument");
+    *p = h->K.rp;
+    return 0;
+}
+
+int mrp_get_stats(mrp_handle* h, double* out_host, int32_t reset_after) {
+    if (!h || !out_host) return fail(-1, "mrp_get_stats: null argument");
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(-9, "mrp_get_stats: %s", dev_err());
+#endif
+    if (D2H(out_host, h->K.stats, sizeof(double) * MRP_N_STATS)) return fail(-9, "mrp_get_stats: D2H failed: %s", dev_err());
+    if (reset_after) DEV_ZERO(h->K.stats, sizeof(double) * MRP_N_STATS);
+    return 0;
+}
+
+int64_t mrp_launch_count(mrp_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// mrp_env.cuh — the env-level half of the hot path, per lane: control laws, observation,
+// reward, termination, TimeLimit, Philox spawn.  Mirrors
+//   reference gym_puzzles/envs/multi_robot_puzzle_00.py:413-521 (v0 / Heavy-v0 step),
+//   reference gym_puzzles/envs/multi_robot_puzzle_02.py:444-584 (v2 / Heavy-v2 step),
+//   reset + _generate_* (mrp00:299-411, mrp02:303-442).
+// Python float arithmetic is float64 and pybox2d b2Vec2 arithmetic is float32; every
+// expression keeps the width it has in the reference.
+#pragma once
+#include "mrp_sim.cuh"
+
+namespace mrp {
+
+MRP_HD double py_mod(double a, double b) {  // Python float %
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+MRP_HD double py_distance(double ax, double ay, double bx, double by) {  // mrp00:130-132
+    double x = (ax - bx) * (ax - bx), y = (ay - by) * (ay - by);
+    return sqrt(x + y);
+}
+constexpr double kTwoPiD = 2.0 * 3.141592653589793;
+constexpr double kPiD = 3.141592653589793;
+
+struct Env : Sim {
+    MRP_HD Env(const SimConst& k, float* sm_, const float* ct_, int64_t env) : Sim(k, sm_, ct_, env) {}
+
+    // b2Island::Solve's velocity integration + damping (A.8) for body b with accumulated force/torque.
+    // Nothing between the control block and the island solve reads velocities, so doing it here is
+    // bit-identical to doing it inside Solve.
+    MRP_HD void integrate_velocity(int b, V2 force, float torque) {
+        V2 v = mk(B(b, 3), B(b, 4));
+        float w = B(b, 5);
+        float im = invMass(b), ii = invI(b);
+        v = v + K.h * (im * force);
+        w += K.h * ii * torque;
+        v = K.lin_k * v;
+        w *= K.ang_k;
+        B(b, 3) = v.x; B(b, 4) = v.y; B(b, 5) = w;
+    }
+
+    // soft attraction force of agent b on the block (mrp00:421-424 / mrp02:470-474)
+    MRP_HD V2 soft_force(int b, double force) {
+        double Ax = (double)B(b, 0), Ay = (double)B(b, 1), Bx = (double)B(0, 0), By = (double)B(0, 1);
+        double dx = fabs(Bx - Ax), dy = fabs(By - Ay);
+        double denom = dx > dy ? dx : dy;  // max(abs, abs)
+        return mk((float)(force * ((Bx - Ax) / denom)), (float)(force * ((By - Ay) / denom)));
+    }
+
+    MRP_HD void control_v0(const float* a) {  // mrp00:415-424
+        V2 bf = mk(0.0f, 0.0f);
+        float btorque = 0.0f;
+        V2 bc = mk(B(0, 0), B(0, 1));
+        for (int i = 0; i < K.n; ++i) {
+            int b = 1 + i;
+            float x = a[3 * i], y = a[3 * i + 1], turn = a[3 * i + 2];
+            B(b, 3) = (float)((double)x * K.SPEED);
+            B(b, 4) = (float)((double)y * K.SPEED);
+            B(b, 5) = turn;
+            double force = pow(1.1, -gd(W_DIST + 2 * i));
+            V2 f = soft_force(b, force);
+            bf = bf + f;
+            btorque += cross(bc - bc, f);
+        }
+        for (int i = 0; i < K.n; ++i) integrate_velocity(1 + i, mk(0.0f, 0.0f), 0.0f);
+        integrate_velocity(0, bf, btorque);
+    }
+
+    MRP_HD void control_v2(const float* a) {  // mrp02:446-474
+        V2 bf = mk(0.0f, 0.0f);
+        float btorque = 0.0f;
+        V2 bc = mk(B(0, 0), B(0, 1));
+        for (int i = 0; i < K.n; ++i) {
+            int b = 1 + i;
+            float turn = a[2 * i], vel = a[2 * i + 1];
+            Xf xf = body_xf(b);
+            V2 c = mk(B(b, 0), B(b, 1));
+            V2 f = rmul(xf.q, mk(0.0f, 1.0f));   // GetWorldVector((0,1))
+            V2 p = xmul(xf, mk(0.0f, 2.0f));     // GetWorldPoint((0,2))
+            V2 ff = mk((float)((double)f.x * (double)vel * 0.75), (float)((double)f.y * (double)vel * 0.75));
+            V2 force = ff;
+            float torque = cross(p - c, ff);
+            // updateFriction (mrp02:116-122)
+            V2 rn = rmul(xf.q, mk(1.0f, 0.0f));
+            V2 v = mk(B(b, 3), B(b, 4));
+            float w = B(b, 5);
+            float dn = dot(rn, v);
+            V2 lat = dn * rn;
+            V2 imp = K.ag_mass * (-lat);
+            v = v + K.ag_invMass * imp;
+            w += K.ag_invI * cross(c - c, imp);
+            // ApplyAngularImpulse(0.1 * inertia * angularVelocity)
+            w += K.ag_invI * (float)(0.1 * (double)K.ag_inertia * (double)w);
+            B(b, 3) = v.x; B(b, 4) = v.y; B(b, 5) = w;
+            double tq = (double)fabsf(turn) * 0.0005;
+            float tturn = turn;
+            if ((double)fabsf(vel) < 0.1) tturn = 0.0f;
+            if (tturn < 0.0f) torque += (float)tq;
+            else if (tturn > 0.0f) torque += (float)(-tq);
+            else torque += 0.0f;
+            double sf = pow(10.0, -gd(W_DIST + 2 * i));
+            sf /= 50;
+            V2 s = soft_force(b, sf);
+            bf = bf + s;
+            btorque += cross(bc - bc, s);
+            integrate_velocity(b, force, torque);
+        }
+        integrate_velocity(0, bf, btorque);
+    }
+
+    // distances, observation, reward, done after world.Step; returns env "done"
+    MRP_HD bool post_step(float* obs, double* reward_out) {
+        const int n = K.n;
+        double prev_ad[MRP_MAX_AGENTS];
+        for (int i = 0; i < n; ++i) prev_ad[i] = gd(W_DIST + 2 * i);
+        double prev_bd = gd(W_DIST + 2 * n);
+        double gx = gd(W_GOAL), gy = gd(W_GOAL + 2);
+        double ad[MRP_MAX_AGENTS], bd;
+        V2 bc = mk(B(0, 0), B(0, 1));
+        if (!K.v2) {  // _calculate_distance / _calculate_agent_distance with b2Vec2*SCALE in float32
+            float s = (float)K.SCALE;
+            bd = py_distance((double)(bc.x * s), (double)(bc.y * s), gx, gy);
+            for (int i = 0; i < n; ++i)
+                ad[i] = py_distance((double)(B(1 + i, 0) * s), (double)(B(1 + i, 1) * s), (double)(bc.x * s), (double)(bc.y * s));
+        } else {
+            bd = py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, gx, gy);
+            for (int i = 0; i < n; ++i)
+                ad[i] = py_distance((double)B(1 + i, 0) * K.ratio, (double)B(1 + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio);
+        }
+        for (int i = 0; i < n; ++i) gsd(W_DIST + 2 * i, ad[i]);
+        gsd(W_DIST + 2 * n, bd);
+
+        Xf bxf = body_xf(0);
+        int o = 0;
+        double reward = 0.0;
+        bool in_place;
+        int blks = (int)g(W_INPLACE);
+        if (!K.v2) {
+            for (int i = 0; i < n; ++i) {
+                obs[o++] = (float)((double)B(1 + i, 0) * K.SCALE - (double)bc.x * K.SCALE);
+                obs[o++] = (float)((double)B(1 + i, 1) * K.SCALE - (double)bc.y * K.SCALE);
+                obs[o++] = (float)ad[i];
+                obs[o++] = ((goalc >> i) & 1) ? 1.0f : 0.0f;
+            }
+            double x = (double)bc.x * K.SCALE, y = (double)bc.y * K.SCALE;
+            double angle = py_mod((double)B(0, 2), kTwoPiD);
+            double a_diff = 0.0 - angle;
+            in_place = !(fabs(gx - x) > 25.0) && !(fabs(gy - y) > 25.0);
+            obs[o++] = (float)(x - gx);
+            obs[o++] = (float)(y - gy);
+            obs[o++] = (float)a_diff;
+            obs[o++] = (float)py_distance(x, y, gx, gy);
+            for (int k = 0; k < 8; ++k) {
+                V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
+                obs[o++] = (float)((double)p.x * K.SCALE);
+                obs[o++] = (float)((double)p.y * K.SCALE);
+            }
+            reward += (prev_bd - bd) * K.rp.blockDelta * 1.0 / 4.;
+            reward -= K.rp.blockDistance * bd * 1.0 / 4.;
+            for (int i = 0; i < n; ++i) {
+                reward += (prev_ad[i] - ad[i]) * K.rp.agentDelta * 1.0 / 4.;
+                reward -= K.rp.agentDistance * ad[i] * 1.0 / 4.;
+                if ((goalc >> i) & 1) reward += 0.25;
+            }
+            int now = in_place ? 1 : 0;
+            reward += (double)((now - blks) * 10);
+            g(W_INPLACE) = (uint32_t)now;
+            bool done = false;
+            if (now == 1) { done = true; reward += 10000.0; }
+            *reward_out = reward;
+            return done;
+        }
+        for (int i = 0; i < n; ++i) {
+            int b = 1 + i;
+            double aX = (double)B(b, 0) * K.ratio, aY = (double)B(b, 1) * K.ratio;
+            double theta = py_mod((double)B(b, 2), kTwoPiD);
+            double nt = theta <= kPiD ? -theta / kPiD : (kTwoPiD - theta) / kPiD;
+            obs[o++] = (float)aX;
+            obs[o++] = (float)aY;
+            obs[o++] = (float)nt;
+            double bX = (double)bc.x * K.ratio, bY = (double)bc.y * K.ratio;
+            obs[o++] = (float)(aX - bX);
+            obs[o++] = (float)(aY - bY);
+            obs[o++] = B(b, 3);
+            obs[o++] = B(b, 4);
+            obs[o++] = B(b, 5);
+            obs[o++] = (float)ad[i];
+        }
+        {
+            double x = (double)bc.x * K.ratio, y = (double)bc.y * K.ratio;
+            double angle = py_mod((double)B(0, 2), kTwoPiD);
+            double a_diff = (0.0 - angle) / kPiD;
+            in_place = !(fabs(gx - x) > K.rp.scaled_epsilon) && !(fabs(gy - y) > K.rp.scaled_epsilon);
+            obs[o++] = (float)(x - gx);
+            obs[o++] = (float)(y - gy);
+            obs[o++] = (float)a_diff;
+            obs[o++] = (float)py_distance(x, y, gx, gy);
+            for (int k = 0; k < 8; ++k) {
+                V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
+                obs[o++] = (float)((double)p.x * K.ratio);
+                obs[o++] = (float)((double)p.y * K.ratio);
+            }
+        }
+        obs[o++] = (float)K.rp.scaled_epsilon;
+        reward += (prev_bd - bd) * K.rp.blockDelta;
+        reward -= K.rp.blockDistance * bd;
+        for (int i = 0; i < n; ++i) {
+            reward += (prev_ad[i] - ad[i]) * K.rp.agentDelta;
+            reward -= K.rp.agentDistance * ad[i];
+        }
+        const double BOUNDS = 0.1;
+        bool agt_oob = false;
+        for (int i = 0; i < n && !agt_oob; ++i) {
+            double x = (double)B(1 + i, 0), y = (double)B(1 + i, 1);
+            if (x < BOUNDS || x > (K.W - BOUNDS)) agt_oob = true;
+            else if (y < BOUNDS || y > (K.H - BOUNDS)) agt_oob = true;
+        }
+        if (agt_oob) {
+            reward -= K.rp.outOfBounds * K.rp.decay_pow;
+            *reward_out = reward;
+            return true;
+        }
+        {
+            double x = (double)bc.x, y = (double)bc.y;
+            bool oob = (x < BOUNDS || x > (K.W - BOUNDS)) || (y < BOUNDS || y > (K.H - BOUNDS));
+            if (oob) {
+                reward -= K.rp.blkOutOfBounds * K.rp.decay_pow;
+                *reward_out = reward;
+                return true;
+            }
+        }
+        int now = in_place ? 1 : 0;
+        g(W_INPLACE) = (uint32_t)now;
+        int num_in_contact = 0;
+        for (int i = 0; i < n; ++i) num_in_contact += (goalc >> i) & 1;
+        bool done = false;
+        if (now == 1) {
+            done = true;
+            reward += K.rp.puzzleComp * K.rp.decay_pow * ((double)num_in_contact / (double)n);
+        }
+        *reward_out = reward;
+        return done;
+    }
+
+    // one env.step body: control -> world.Step -> post
+    MRP_HD bool env_step(const float* a, float* obs, double* reward, bool new_fixtures) {
+        if (K.v2) control_v2(a); else control_v0(a);
+        world_step(new_fixtures);
+        return post_step(obs, reward);
+    }
+
+    // respawn (mrp00:392-409 / mrp02:421-440) with counter-based Philox (north star)
+    MRP_HD void spawn(uint32_t episode) {
+        uint32_t d = 0;
+        const double W = K.W, H = K.H;
+        double bx, by, ba;
+        double ag[2 * MRP_MAX_AGENTS];
+        if (!K.v2) {
+            bx = 1.0 + ((W - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            by = 1.0 + ((H - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            ba = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            for (int i = 0; i < K.n; ++i) {
+                ag[2 * i] = 1.0 + ((W - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+                ag[2 * i + 1] = 1.0 + ((H - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            }
+        } else {
+            bx = W / 2; by = H / 2;
+            ba = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            for (int i = 0; i < K.n; ++i) {
+                ag[2 * i] = 0.3 + ((W / 3 - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+                ag[2 * i + 1] = 0.3 + ((H - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            }
+        }
+        // bodies: xf.p = position, sweep.c = Mul(xf, localCenter) (b2Body ctor + ResetMassData)
+        for (int b = 0; b < K.nb; ++b) {
+            float px = (float)(b == 0 ? bx : ag[2 * (b - 1)]);
+            float py = (float)(b == 0 ? by : ag[2 * (b - 1) + 1]);
+            float ang = b == 0 ? (float)ba : (K.v2 ? (float)(3.0 / 2 * kPiD) : 0.0f);
+            Xf xf;
+            xf.p = mk(px, py);
+            xf.q = rot_set(ang);
+            V2 c = xmul(xf, localCenter(b));
+            B(b, 0) = c.x; B(b, 1) = c.y; B(b, 2) = ang;
+            B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
+            BX(b, 9) = xf.q.s; BX(b, 10) = xf.q.c; BX(b, 11) = px; BX(b, 12) = py;
+            // proxies: fat AABB = tight AABB at creation +- 0.1 (b2DynamicTree::CreateProxy)
+            int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
+            int f1 = b == 0 ? 2 : f0 + K.per_agent;
+            for (int f = f0; f < f1; ++f) {
+                Box t = shape_aabb(fix_shape(f), xf);
+                FA(f, 0) = t.lx - kAabbExtension; FA(f, 1) = t.ly - kAabbExtension;
+                FA(f, 2) = t.hx + kAabbExtension; FA(f, 3) = t.hy + kAabbExtension;
+            }
+        }
+        for (int k = 0; k < 4; ++k) {
+            int b = K.nb + k;
+            B(b, 0) = ct[CT_WALLPOS + 2 * k];
+            B(b, 1) = ct[CT_WALLPOS + 2 * k + 1];
+            B(b, 2) = 0.0f; B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
+        }
+        nc = 0;
+        goalc = 0;
+        double gx = K.goal_x0, gy = K.goal_y0;
+        if (K.v2) {  // _set_random_goal (mrp02:303-311)
+            double x = (W * 2 / 3 + 0.4) + ((W - 0.4) - (W * 2 / 3 + 0.4)) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            double y = 0.4 + ((H - 0.4) - 0.4) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            gx = x * K.ratio;
+            gy = y * K.ratio;
+        }
+        gsd(W_GOAL, gx);
+        gsd(W_GOAL + 2, gy);
+        // _calculate_distance / _calculate_agent_distance
+        V2 bc = mk(B(0, 0), B(0, 1));
+        if (!K.v2) {
+            float s = (float)K.SCALE;
+            gsd(W_DIST + 2 * K.n, py_distance((double)(bc.x * s), (double)(bc.y * s), gx, gy));
+            for (int i = 0; i < K.n; ++i)
+                gsd(W_DIST + 2 * i, py_distance((double)(B(1 + i, 0) * s), (double)(B(1 + i, 1) * s), (double)(bc.x * s), (double)(bc.y * s)));
+        } else {
+            gsd(W_DIST + 2 * K.n, py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, gx, gy));
+            for (int i = 0; i < K.n; ++i)
+                gsd(W_DIST + 2 * i, py_distance((double)B(1 + i, 0) * K.ratio, (double)B(1 + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio));
+        }
+    }
+
+    // env.reset(): respawn + hidden step with a sampled action (mrp00:411 / mrp02:442)
+    MRP_HD void reset_env(float* obs) {
+        uint32_t episode = g(W_EPISODE) + 1u;
+        g(W_EPISODE) = episode;
+        g(W_ELAPSED) = 0;
+        g(W_EPLEN) = 0;
+        gsd(W_EPRET, 0.0);
+        spawn(episode);
+        float a[3 * MRP_MAX_AGENTS];
+        for (int i = 0; i < K.act_dim; ++i)
+            a[i] = (float)(-1.0 + 2.0 * uniform53(K.seed, kStreamResetAction, gid, episode, (uint32_t)i));
+        double r;
+        env_step(a, obs, &r, true);
+        store();
+    }
+};
+
+}  // namespace mrp

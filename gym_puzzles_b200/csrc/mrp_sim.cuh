@@ -1,0 +1,930 @@
+// mrp_sim.cuh — one lane = one environment: the whole MultiRobotPuzzle step
+// (reference mrp00:413-521 / mrp02:444-584 incl. b2World::Step(1/50, 180, 60)) for the
+// sm_100a kernels.  A warp advances a tile of 32 envs; every per-env array that is
+// indexed dynamically (bodies, fat AABBs) sits in shared memory in a lane-major layout
+// (word k of lane t at smem[k*blockDim + t]) so any divergent index is bank-conflict
+// free; the contact cache stays in HBM in a coalesced [word][env] layout.
+//
+// Box2D semantics followed: SURVEY.md Appendix A (Collide / Solve / SolveTOI ordering,
+// contact list = reverse creation order sorted by proxy-id pair, DFS islands over
+// newest-first edges, warm starting, block solver, position solver, TOI sub-steps).
+#pragma once
+#include "../../include/mrp_b200.h"
+#include "mrp_collide.cuh"
+
+namespace mrp {
+
+#if defined(__CUDA_ARCH__)
+#define MRP_SS 128  // lanes per CTA == shared-memory lane stride
+#else
+#define MRP_SS 1
+#endif
+constexpr int kBlock = 128;
+constexpr int kMaxC = 32;  // contact slots per env (mrp_layout.max_contacts <= 32)
+
+// ---- per-CTA constant table (floats; small ints stored as floats) -----------------
+constexpr int CT_FIXBODY = 0;     // [32] body index of fixture
+constexpr int CT_FIXSHAPE = 32;   // [32] shape index of fixture
+constexpr int CT_FIXFRIC = 64;    // [32] friction of fixture
+constexpr int CT_WALLFAT = 96;    // [4][4] fat AABB of wall fixtures
+constexpr int CT_WALLPOS = 112;   // [4][2] wall body positions
+constexpr int CT_SHAPES = 120;    // [8][33]
+constexpr int CT_WORDS = CT_SHAPES + 8 * kShapeWords;
+
+// ---- internal per-env state words in HBM: S[word * N + env] ------------------------
+constexpr int W_ELAPSED = 0, W_EPISODE = 1, W_INPLACE = 2, W_NC = 3, W_GOALC = 4, W_EPLEN = 5;
+constexpr int W_EPRET = 6;   // f64
+constexpr int W_GOAL = 8;    // 2 x f64
+constexpr int W_DIST = 12;   // (n+1) x f64: agent_dist[0..n-1], block_dist
+// then bodies[nb][8] = {cx, cy, a, vx, vy, w, q.s, q.c}; fat[ndynfix][4]; contacts[maxc][14]
+
+struct SimConst {
+    // variant
+    int32_t variant, v2, n, nb, nfix, ndynfix, per_agent, maxc, obs_dim, act_dim, max_steps, auto_reset;
+    int32_t w_body, w_aabb, w_con, w_total;  // word offsets of the internal state
+    int32_t smem_words;                      // per-lane shared-memory words
+    int32_t pad0;
+    // body classes
+    float blk_mass, blk_invMass, blk_invI, blk_lcx, blk_lcy;
+    float ag_mass, ag_invMass, ag_invI, ag_lcx, ag_lcy, ag_inertia;
+    float lin_k, ang_k;  // 1/(1+h*damping)
+    float h;
+    float blkv[8][2];  // observation vertex list (bar verts, then stem verts)
+    // env constants (float64, as the reference's Python arithmetic)
+    double SCALE, W, H, ratio, SPEED;
+    double goal_x0, goal_y0;
+    mrp_params rp;
+    uint64_t seed, env_id_base;
+    // memory
+    uint32_t* S;
+    int64_t N;
+    const float* ctab;
+    const float* act;
+    float* obs;
+    float* rew;
+    uint8_t* done;
+    uint8_t* trunc;
+    double* stats;
+    int32_t* reset_list;
+    int32_t* reset_count;
+    const uint8_t* reset_mask;
+};
+
+// ---- solver constraint record (per touching contact, in island order) --------------
+constexpr int VC_META = 0;   // bA | bB<<4 | vpc<<8 | ppc<<10 | type<<12 | island<<16 | slot<<24
+constexpr int VC_FRIC = 1, VC_NX = 2, VC_NY = 3;
+constexpr int VC_PT = 4;     // [2][8]: rAx rAy rBx rBy nMass tMass nI tI
+constexpr int VC_K11 = 20, VC_K12 = 21, VC_K22 = 22, VC_M11 = 23, VC_M12 = 24, VC_M22 = 25;
+constexpr int VC_LNX = 26, VC_LNY = 27, VC_LPX = 28, VC_LPY = 29, VC_LP0X = 30, VC_LP0Y = 31, VC_LP1X = 32, VC_LP1Y = 33;
+constexpr int VC_WORDS = 34;
+
+struct Sim {
+    const SimConst& K;
+    float* sm;          // this lane's shared-memory column
+    const float* ct;    // CTA constant table (shared memory)
+    uint32_t* G;        // &S[env]
+    int64_t N;
+    uint64_t gid;
+    // per-lane scratch (local memory where dynamically indexed)
+    uint32_t meta[kMaxC];  // fa | fb<<8 | touching<<16 | type<<17 | pc<<18 | bA<<20 | bB<<24
+    float vc[kMaxC * VC_WORDS];
+    uint8_t order[kMaxC];
+    float toi[kMaxC];
+    uint8_t toiCount[kMaxC];
+    float wallAlpha0[4];
+    int nc;
+    uint32_t goalc;
+    uint32_t overflow;
+
+    MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env)
+        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), nc(0), goalc(0), overflow(0) {}
+
+    // ------------------------------------------------------------ memory helpers
+    MRP_HD uint32_t& g(int w) { return G[(int64_t)w * N]; }
+    MRP_HD float gf(int w) { return __uint_as_float_(g(w)); }
+    MRP_HD void gsf(int w, float v) { g(w) = __float_as_uint_(v); }
+    MRP_HD double gd(int w) {
+        uint64_t lo = g(w), hi = g(w + 1);
+        return __ull_as_double_(lo | (hi << 32));
+    }
+    MRP_HD void gsd(int w, double v) {
+        uint64_t u = __double_as_ull_(v);
+        g(w) = (uint32_t)u;
+        g(w + 1) = (uint32_t)(u >> 32);
+    }
+    static MRP_HD float __uint_as_float_(uint32_t u) { union { uint32_t u; float f; } c; c.u = u; return c.f; }
+    static MRP_HD uint32_t __float_as_uint_(float f) { union { uint32_t u; float f; } c; c.f = f; return c.u; }
+    static MRP_HD double __ull_as_double_(uint64_t u) { union { uint64_t u; double f; } c; c.u = u; return c.f; }
+    static MRP_HD uint64_t __double_as_ull_(double f) { union { uint64_t u; double f; } c; c.f = f; return c.u; }
+    MRP_HD int cw(int k, int j) const { return K.w_con + k * MRP_CONTACT_WORDS + j; }
+
+    // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 c0x 7 c0y 8 a0 9 qs 10 qc 11 px 12 py 13 alpha0 (dynamic)
+    MRP_HD float& B(int b, int f) { return sm[(f * (K.nb + 4) + b) * MRP_SS]; }
+    MRP_HD float& BX(int b, int f) { return sm[(6 * (K.nb + 4) + (f - 6) * K.nb + b) * MRP_SS]; }
+    MRP_HD float& FA(int fx, int j) { return sm[(6 * (K.nb + 4) + 8 * K.nb + fx * 4 + j) * MRP_SS]; }
+
+    MRP_HD bool is_dyn(int b) const { return b < K.nb; }
+    MRP_HD float invMass(int b) const { return b == 0 ? K.blk_invMass : (b < K.nb ? K.ag_invMass : 0.0f); }
+    MRP_HD float invI(int b) const { return b == 0 ? K.blk_invI : (b < K.nb ? K.ag_invI : 0.0f); }
+    MRP_HD V2 localCenter(int b) const {
+        return b == 0 ? mk(K.blk_lcx, K.blk_lcy) : (b < K.nb ? mk(K.ag_lcx, K.ag_lcy) : mk(0.0f, 0.0f));
+    }
+    MRP_HD Xf body_xf(int b) {
+        Xf x;
+        if (b < K.nb) {
+            x.p = mk(BX(b, 11), BX(b, 12));
+            x.q.s = BX(b, 9);
+            x.q.c = BX(b, 10);
+        } else {
+            x.p = mk(B(b, 0), B(b, 1));
+            x.q.s = 0.0f;
+            x.q.c = 1.0f;
+        }
+        return x;
+    }
+    MRP_HD void sync_transform(int b) {  // b2Body::SynchronizeTransform
+        Rot q = rot_set(B(b, 2));
+        V2 r = rmul(q, localCenter(b));
+        BX(b, 9) = q.s;
+        BX(b, 10) = q.c;
+        BX(b, 11) = B(b, 0) - r.x;
+        BX(b, 12) = B(b, 1) - r.y;
+    }
+    MRP_HD int fix_body(int f) const { return (int)ct[CT_FIXBODY + f]; }
+    MRP_HD const float* fix_shape(int f) const { return ct + CT_SHAPES + kShapeWords * (int)ct[CT_FIXSHAPE + f]; }
+    MRP_HD Box fat(int f) {
+        Box b;
+        if (f < K.ndynfix) {
+            b.lx = FA(f, 0); b.ly = FA(f, 1); b.hx = FA(f, 2); b.hy = FA(f, 3);
+        } else {
+            const float* w = ct + CT_WALLFAT + 4 * (f - K.ndynfix);
+            b.lx = w[0]; b.ly = w[1]; b.hx = w[2]; b.hy = w[3];
+        }
+        return b;
+    }
+    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, 13) : wallAlpha0[b - K.nb]; }
+
+    // ------------------------------------------------------------ state load / store
+    MRP_HD void load() {
+        nc = (int)g(W_NC);
+        goalc = g(W_GOALC);
+        for (int b = 0; b < K.nb; ++b) {
+            int w = K.w_body + 8 * b;
+            for (int f = 0; f < 6; ++f) B(b, f) = gf(w + f);
+            BX(b, 9) = gf(w + 6);
+            BX(b, 10) = gf(w + 7);
+            V2 r = rmul(Rot{BX(b, 9), BX(b, 10)}, localCenter(b));
+            BX(b, 11) = B(b, 0) - r.x;
+            BX(b, 12) = B(b, 1) - r.y;
+        }
+        for (int k = 0; k < 4; ++k) {
+            int b = K.nb + k;
+            B(b, 0) = ct[CT_WALLPOS + 2 * k];
+            B(b, 1) = ct[CT_WALLPOS + 2 * k + 1];
+            B(b, 2) = 0.0f; B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
+        }
+        for (int f = 0; f < K.ndynfix; ++f)
+            for (int j = 0; j < 4; ++j) FA(f, j) = gf(K.w_aabb + 4 * f + j);
+        for (int k = 0; k < nc; ++k) meta[k] = g(cw(k, 0));
+    }
+    MRP_HD void store() {
+        g(W_NC) = (uint32_t)nc;
+        g(W_GOALC) = goalc;
+        for (int b = 0; b < K.nb; ++b) {
+            int w = K.w_body + 8 * b;
+            for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
+            gsf(w + 6, BX(b, 9));
+            gsf(w + 7, BX(b, 10));
+        }
+        for (int f = 0; f < K.ndynfix; ++f)
+            for (int j = 0; j < 4; ++j) gsf(K.w_aabb + 4 * f + j, FA(f, j));
+        for (int k = 0; k < nc; ++k) g(cw(k, 0)) = meta[k];
+    }
+
+    // ------------------------------------------------------------ contact events (ContactDetector, mrp00:92-111)
+    MRP_HD void contact_event(uint32_t m, bool begin) {
+        int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+        int ag = bA == 0 ? bB : (bB == 0 ? bA : -1);
+        if (ag >= 1 && ag < K.nb) {
+            uint32_t bit = 1u << (ag - 1);
+            goalc = begin ? (goalc | bit) : (goalc & ~bit);
+        }
+    }
+
+    // b2Contact::Update for slot k (A.4): narrowphase at the bodies' current transforms, impulse
+    // matching by feature id, touching flag, Begin/End events.
+    MRP_HDN void update_contact(int k) {
+        uint32_t m = meta[k];
+        int fa = m & 0xff, fb = (m >> 8) & 0xff;
+        int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+        bool was = (m >> 16) & 1;
+        int oldpc = (m >> 18) & 3;
+        Manifold man;
+        collide_polygons(&man, fix_shape(fa), body_xf(bA), fix_shape(fb), body_xf(bB));
+        bool touching = man.pc > 0;
+        if (touching) {
+            uint32_t okeys = oldpc ? g(cw(k, 1)) : 0u;
+            float nI[2] = {0.0f, 0.0f}, tI[2] = {0.0f, 0.0f};
+            for (int i = 0; i < man.pc; ++i) {
+                for (int j = 0; j < oldpc; ++j) {
+                    if (((okeys >> (16 * j)) & 0xffffu) == man.key[i]) {
+                        nI[i] = gf(cw(k, 8 + 4 * j));
+                        tI[i] = gf(cw(k, 9 + 4 * j));
+                        break;
+                    }
+                }
+            }
+            g(cw(k, 1)) = man.key[0] | ((man.pc > 1 ? man.key[1] : 0u) << 16);
+            gsf(cw(k, 2), man.ln.x); gsf(cw(k, 3), man.ln.y);
+            gsf(cw(k, 4), man.lp.x); gsf(cw(k, 5), man.lp.y);
+            for (int i = 0; i < man.pc; ++i) {
+                gsf(cw(k, 6 + 4 * i), man.pt[i].x);
+                gsf(cw(k, 7 + 4 * i), man.pt[i].y);
+                gsf(cw(k, 8 + 4 * i), nI[i]);
+                gsf(cw(k, 9 + 4 * i), tI[i]);
+            }
+        }
+        m = (m & 0xfff0ffffu) | ((touching ? 1u : 0u) << 16) | (((uint32_t)man.type & 1u) << 17) | ((uint32_t)man.pc << 18);
+        if (!touching) m &= ~(1u << 17);
+        meta[k] = m;
+        if (!was && touching) contact_event(m, true);
+        if (was && !touching) contact_event(m, false);
+    }
+
+    // b2ContactManager::Collide (A.3): world-list order = newest slot first
+    MRP_HD void collide() {
+        uint32_t dead = 0;
+        for (int k = nc - 1; k >= 0; --k) {
+            uint32_t m = meta[k];
+            int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            if (!overlap(fat(fa), fat(fb))) {
+                if ((m >> 16) & 1) contact_event(m, false);
+                dead |= 1u << k;
+                continue;
+            }
+            update_contact(k);
+        }
+        if (dead) {  // rare: compact, preserving order
+            int dst = 0;
+            for (int k = 0; k < nc; ++k) {
+                if ((dead >> k) & 1) continue;
+                if (dst != k) {
+                    meta[dst] = meta[k];
+                    for (int j = 1; j < MRP_CONTACT_WORDS; ++j) g(cw(dst, j)) = g(cw(k, j));
+                }
+                ++dst;
+            }
+            nc = dst;
+        }
+    }
+
+    // ------------------------------------------------------------ broadphase (A.3)
+    MRP_HD Box shape_aabb(const float* sh, Xf xf) {  // b2PolygonShape::ComputeAABB
+        V2 lo = xmul(xf, sh_v(sh, 0)), hi = lo;
+        int cnt = sh_count(sh);
+        for (int i = 1; i < cnt; ++i) {
+            V2 p = xmul(xf, sh_v(sh, i));
+            lo = mk(fmin2(lo.x, p.x), fmin2(lo.y, p.y));
+            hi = mk(fmax2(hi.x, p.x), fmax2(hi.y, p.y));
+        }
+        Box b;
+        b.lx = lo.x - kPolygonRadius; b.ly = lo.y - kPolygonRadius;
+        b.hx = hi.x + kPolygonRadius; b.hy = hi.y + kPolygonRadius;
+        return b;
+    }
+    // b2Body::SynchronizeFixtures + b2DynamicTree::MoveProxy; returns the moved-proxy mask
+    MRP_HD uint32_t synchronize_fixtures(int b, Xf xf1) {
+        uint32_t moved = 0;
+        Xf xf2 = body_xf(b);
+        V2 disp = xf2.p - xf1.p;
+        int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
+        int f1 = b == 0 ? 2 : f0 + K.per_agent;
+        for (int f = f0; f < f1; ++f) {
+            const float* sh = fix_shape(f);
+            Box a1 = shape_aabb(sh, xf1), a2 = shape_aabb(sh, xf2);
+            Box a;
+            a.lx = fmin2(a1.lx, a2.lx); a.ly = fmin2(a1.ly, a2.ly);
+            a.hx = fmax2(a1.hx, a2.hx); a.hy = fmax2(a1.hy, a2.hy);
+            if (contains(fat(f), a)) continue;
+            a.lx = a.lx - kAabbExtension; a.ly = a.ly - kAabbExtension;
+            a.hx = a.hx + kAabbExtension; a.hy = a.hy + kAabbExtension;
+            V2 d = kAabbMultiplier * disp;
+            if (d.x < 0.0f) a.lx += d.x; else a.hx += d.x;
+            if (d.y < 0.0f) a.ly += d.y; else a.hy += d.y;
+            FA(f, 0) = a.lx; FA(f, 1) = a.ly; FA(f, 2) = a.hx; FA(f, 3) = a.hy;
+            moved |= 1u << f;
+        }
+        return moved;
+    }
+    MRP_HD bool contact_exists(int fa, int fb) {
+        uint32_t key = (uint32_t)fa | ((uint32_t)fb << 8);
+        for (int k = 0; k < nc; ++k)
+            if ((meta[k] & 0xffffu) == key) return true;
+        return false;
+    }
+    // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair: pairs visited in lexicographic
+    // (proxyA < proxyB) order == the sorted pair buffer; each new contact goes to the list head.
+    MRP_HD void find_new_contacts(uint32_t moved) {
+        if (!moved) return;
+        int nf = K.nfix;
+        for (int i = 0; i < nf; ++i) {
+            bool mi = (moved >> i) & 1;
+            uint32_t cand = mi ? (0xffffffffu << (i + 1)) : (moved & (0xffffffffu << (i + 1)));
+            if (i + 1 >= 32) cand = 0;
+            cand &= (nf >= 32) ? 0xffffffffu : ((1u << nf) - 1u);
+            if (!cand) continue;
+            int bi = fix_body(i);
+            Box ai = fat(i);
+            while (cand) {
+                int j = ctz32(cand);
+                cand &= cand - 1;
+                int bj = fix_body(j);
+                if (bi == bj) continue;
+                if (!is_dyn(bi) && !is_dyn(bj)) continue;
+                if (!overlap(ai, fat(j))) continue;
+                if (contact_exists(i, j)) continue;
+                if (nc >= K.maxc) { overflow = 1; continue; }
+                meta[nc] = (uint32_t)i | ((uint32_t)j << 8) | ((uint32_t)bi << 20) | ((uint32_t)bj << 24);
+                ++nc;
+            }
+        }
+    }
+    static MRP_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+        return __ffs((int)x) - 1;
+#else
+        return __builtin_ctz(x);
+#endif
+    }
+
+    // ------------------------------------------------------------ contact solver (A.8)
+    MRP_HD float& V(int t, int w) { return vc[t * VC_WORDS + w]; }
+    MRP_HD uint32_t vmeta(int t) { return __float_as_uint_(vc[t * VC_WORDS + VC_META]); }
+
+    // b2ContactSolver ctor + InitializeVelocityConstraints for constraints [0, T)
+    MRP_HD void init_constraints(int T, const uint8_t* island_of, bool warm) {
+        for (int t = 0; t < T; ++t) {
+            int k = order[t];
+            uint32_t m = meta[k];
+            int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+            int pc = (m >> 18) & 3, type = (m >> 17) & 1;
+            int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            V(t, VC_FRIC) = sqrtf(ct[CT_FIXFRIC + fa] * ct[CT_FIXFRIC + fb]);
+            V2 ln = mk(gf(cw(k, 2)), gf(cw(k, 3))), lp = mk(gf(cw(k, 4)), gf(cw(k, 5)));
+            V(t, VC_LNX) = ln.x; V(t, VC_LNY) = ln.y; V(t, VC_LPX) = lp.x; V(t, VC_LPY) = lp.y;
+            V2 lpt[2];
+            float nI[2], tI[2];
+            for (int j = 0; j < 2; ++j) {
+                if (j < pc) {
+                    lpt[j] = mk(gf(cw(k, 6 + 4 * j)), gf(cw(k, 7 + 4 * j)));
+                    nI[j] = warm ? gf(cw(k, 8 + 4 * j)) : 0.0f;
+                    tI[j] = warm ? gf(cw(k, 9 + 4 * j)) : 0.0f;
+                } else {
+                    lpt[j] = mk(0.0f, 0.0f); nI[j] = 0.0f; tI[j] = 0.0f;
+                }
+                V(t, VC_LP0X + 2 * j) = lpt[j].x;
+                V(t, VC_LP0X + 2 * j + 1) = lpt[j].y;
+            }
+            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
+            V2 cA = mk(B(bA, 0), B(bA, 1)), cB = mk(B(bB, 0), B(bB, 1));
+            V2 vA = mk(B(bA, 3), B(bA, 4)), vB = mk(B(bB, 3), B(bB, 4));
+            float wA = B(bA, 5), wB = B(bB, 5);
+            Xf xfA, xfB;
+            xfA.q = is_dyn(bA) ? rot_set(B(bA, 2)) : Rot{0.0f, 1.0f};
+            xfB.q = is_dyn(bB) ? rot_set(B(bB, 2)) : Rot{0.0f, 1.0f};
+            xfA.p = cA - rmul(xfA.q, localCenter(bA));
+            xfB.p = cB - rmul(xfB.q, localCenter(bB));
+            // b2WorldManifold::Initialize
+            V2 normal, wpt[2];
+            if (type == 0) {
+                normal = rmul(xfA.q, ln);
+                V2 planePoint = xmul(xfA, lp);
+                for (int j = 0; j < pc; ++j) {
+                    V2 clip = xmul(xfB, lpt[j]);
+                    V2 pA = clip + (kPolygonRadius - dot(clip - planePoint, normal)) * normal;
+                    V2 pB = clip - kPolygonRadius * normal;
+                    wpt[j] = 0.5f * (pA + pB);
+                }
+            } else {
+                normal = rmul(xfB.q, ln);
+                V2 planePoint = xmul(xfB, lp);
+                for (int j = 0; j < pc; ++j) {
+                    V2 clip = xmul(xfA, lpt[j]);
+                    V2 pB = clip + (kPolygonRadius - dot(clip - planePoint, normal)) * normal;
+                    V2 pA = clip - kPolygonRadius * normal;
+                    wpt[j] = 0.5f * (pA + pB);
+                }
+                normal = -normal;
+            }
+            V(t, VC_NX) = normal.x; V(t, VC_NY) = normal.y;
+            int vpc = pc;
+            V2 tangent = crossVS(normal, 1.0f);
+            V2 rAj[2], rBj[2];
+            for (int j = 0; j < 2; ++j) {
+                float* P = &V(t, VC_PT + 8 * j);
+                if (j >= pc) { for (int q = 0; q < 8; ++q) P[q] = 0.0f; continue; }
+                V2 rA = wpt[j] - cA, rB = wpt[j] - cB;
+                rAj[j] = rA; rBj[j] = rB;
+                float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                float rtA = cross(rA, tangent), rtB = cross(rB, tangent);
+                float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+                P[0] = rA.x; P[1] = rA.y; P[2] = rB.x; P[3] = rB.y;
+                P[4] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+                P[5] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+                P[6] = nI[j]; P[7] = tI[j];
+                // restitution is 0 for every fixture here => velocityBias = -0 * vRel (no effect)
+            }
+            V(t, VC_K11) = 0.0f; V(t, VC_K12) = 0.0f; V(t, VC_K22) = 0.0f;
+            V(t, VC_M11) = 0.0f; V(t, VC_M12) = 0.0f; V(t, VC_M22) = 0.0f;
+            if (pc == 2) {
+                float rn1A = cross(rAj[0], normal), rn1B = cross(rBj[0], normal);
+                float rn2A = cross(rAj[1], normal), rn2B = cross(rBj[1], normal);
+                float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+                float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+                float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+                const float k_maxConditionNumber = 1000.0f;
+                if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+                    V(t, VC_K11) = k11; V(t, VC_K12) = k12; V(t, VC_K22) = k22;
+                    float det = k11 * k22 - k12 * k12;
+                    if (det != 0.0f) det = 1.0f / det;
+                    V(t, VC_M11) = det * k22; V(t, VC_M12) = -det * k12; V(t, VC_M22) = det * k11;
+                } else {
+                    vpc = 1;
+                }
+            }
+            (void)vA; (void)vB; (void)wA; (void)wB;
+            uint32_t vm = (uint32_t)bA | ((uint32_t)bB << 4) | ((uint32_t)vpc << 8) | ((uint32_t)pc << 10) | ((uint32_t)type << 12) |
+                          ((uint32_t)(island_of ? island_of[t] : 0) << 16) | ((uint32_t)k << 24);
+            V(t, VC_META) = __uint_as_float_(vm);
+        }
+    }
+
+    MRP_HD void warm_start(int T) {
+        for (int t = 0; t < T; ++t) {
+            uint32_t vm = vmeta(t);
+            int bA = vm & 15, bB = (vm >> 4) & 15, vpc = (vm >> 8) & 3;
+            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
+            V2 vA = mk(B(bA, 3), B(bA, 4)), vB = mk(B(bB, 3), B(bB, 4));
+            float wA = B(bA, 5), wB = B(bB, 5);
+            V2 normal = mk(V(t, VC_NX), V(t, VC_NY));
+            V2 tangent = crossVS(normal, 1.0f);
+            for (int j = 0; j < vpc; ++j) {
+                const float* P = &V(t, VC_PT + 8 * j);
+                V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
+                V2 Pi = P[6] * normal + P[7] * tangent;
+                wA -= iA * cross(rA, Pi);
+                vA = vA - mA * Pi;
+                wB += iB * cross(rB, Pi);
+                vB = vB + mB * Pi;
+            }
+            B(bA, 3) = vA.x; B(bA, 4) = vA.y; B(bA, 5) = wA;
+            B(bB, 3) = vB.x; B(bB, 4) = vB.y; B(bB, 5) = wB;
+        }
+    }
+
+    // one b2ContactSolver::SolveVelocityConstraints sweep; returns true if anything changed
+    MRP_HD bool solve_velocity_sweep(int T) {
+        bool changed = false;
+        for (int t = 0; t < T; ++t) {
+            uint32_t vm = vmeta(t);
+            int bA = vm & 15, bB = (vm >> 4) & 15, vpc = (vm >> 8) & 3;
+            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
+            V2 vA = mk(B(bA, 3), B(bA, 4)), vB = mk(B(bB, 3), B(bB, 4));
+            float wA = B(bA, 5), wB = B(bB, 5);
+            V2 normal = mk(V(t, VC_NX), V(t, VC_NY));
+            V2 tangent = crossVS(normal, 1.0f);
+            float friction = V(t, VC_FRIC);
+            for (int j = 0; j < vpc; ++j) {
+                float* P = &V(t, VC_PT + 8 * j);
+                V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
+                V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
+                float vt = dot(dv, tangent) - 0.0f;
+                float lambda = P[5] * (-vt);
+                float maxFriction = friction * P[6];
+                float newImpulse = clampf(P[7] + lambda, -maxFriction, maxFriction);
+                lambda = newImpulse - P[7];
+                P[7] = newImpulse;
+                changed = changed || (lambda != 0.0f);
+                V2 Pi = lambda * tangent;
+                vA = vA - mA * Pi;
+                wA -= iA * cross(rA, Pi);
+                vB = vB + mB * Pi;
+                wB += iB * cross(rB, Pi);
+            }
+            if (vpc == 1) {
+                float* P = &V(t, VC_PT);
+                V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
+                V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
+                float vn = dot(dv, normal);
+                float lambda = -P[4] * (vn - 0.0f);
+                float newImpulse = fmax2(P[6] + lambda, 0.0f);
+                lambda = newImpulse - P[6];
+                P[6] = newImpulse;
+                changed = changed || (lambda != 0.0f);
+                V2 Pi = lambda * normal;
+                vA = vA - mA * Pi;
+                wA -= iA * cross(rA, Pi);
+                vB = vB + mB * Pi;
+                wB += iB * cross(rB, Pi);
+            } else if (vpc == 2) {
+                float* P1 = &V(t, VC_PT);
+                float* P2 = &V(t, VC_PT + 8);
+                V2 rA1 = mk(P1[0], P1[1]), rB1 = mk(P1[2], P1[3]);
+                V2 rA2 = mk(P2[0], P2[1]), rB2 = mk(P2[2], P2[3]);
+                float ax = P1[6], ay = P2[6];
+                V2 dv1 = vB + crossSV(wB, rB1) - vA - crossSV(wA, rA1);
+                V2 dv2 = vB + crossSV(wB, rB2) - vA - crossSV(wA, rA2);
+                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                float k11 = V(t, VC_K11), k12 = V(t, VC_K12), k22 = V(t, VC_K22);
+                float bx = vn1 - 0.0f, by = vn2 - 0.0f;
+                bx -= k11 * ax + k12 * ay;
+                by -= k12 * ax + k22 * ay;
+                float xx, xy;
+                bool ok = false;
+                // case 1
+                xx = -(V(t, VC_M11) * bx + V(t, VC_M12) * by);
+                xy = -(V(t, VC_M12) * bx + V(t, VC_M22) * by);
+                if (xx >= 0.0f && xy >= 0.0f) ok = true;
+                if (!ok) {  // case 2
+                    xx = -P1[4] * bx; xy = 0.0f;
+                    vn2 = k12 * xx + by;
+                    if (xx >= 0.0f && vn2 >= 0.0f) ok = true;
+                }
+                if (!ok) {  // case 3
+                    xx = 0.0f; xy = -P2[4] * by;
+                    vn1 = k12 * xy + bx;
+                    if (xy >= 0.0f && vn1 >= 0.0f) ok = true;
+                }
+                if (!ok) {  // case 4
+                    xx = 0.0f; xy = 0.0f;
+                    if (bx >= 0.0f && by >= 0.0f) ok = true;
+                }
+                if (ok) {
+                    float dx = xx - ax, dy = xy - ay;
+                    V2 Pa = dx * normal, Pb = dy * normal;
+                    vA = vA - mA * (Pa + Pb);
+                    wA -= iA * (cross(rA1, Pa) + cross(rA2, Pb));
+                    vB = vB + mB * (Pa + Pb);
+                    wB += iB * (cross(rB1, Pa) + cross(rB2, Pb));
+                    P1[6] = xx; P2[6] = xy;
+                    changed = changed || (dx != 0.0f) || (dy != 0.0f);
+                }
+            }
+            B(bA, 3) = vA.x; B(bA, 4) = vA.y; B(bA, 5) = wA;
+            B(bB, 3) = vB.x; B(bB, 4) = vB.y; B(bB, 5) = wB;
+        }
+        return changed;
+    }
+    // 180 sweeps; stops early once a whole sweep changes nothing (every later sweep would be the
+    // identical no-op, so the result equals the full 180 bit for bit)
+    MRP_HD void solve_velocity(int T, int iters) {
+        if (T == 0) return;
+        for (int it = 0; it < iters; ++it)
+            if (!solve_velocity_sweep(T)) break;
+    }
+    MRP_HD void store_impulses(int T) {
+        for (int t = 0; t < T; ++t) {
+            uint32_t vm = vmeta(t);
+            int vpc = (vm >> 8) & 3, k = (vm >> 24) & 0xff;
+            for (int j = 0; j < vpc; ++j) {
+                gsf(cw(k, 8 + 4 * j), V(t, VC_PT + 8 * j + 6));
+                gsf(cw(k, 9 + 4 * j), V(t, VC_PT + 8 * j + 7));
+            }
+        }
+    }
+    MRP_HD void integrate_position(int b, float h) {
+        V2 v = mk(B(b, 3), B(b, 4));
+        float w = B(b, 5);
+        V2 tr = h * v;
+        if (dot(tr, tr) > kMaxTranslationSquared) {
+            float ratio = kMaxTranslation / length(tr);
+            v = ratio * v;
+        }
+        float rotation = h * w;
+        if (rotation * rotation > kMaxRotationSquared) {
+            float ratio = kMaxRotation / fabsf(rotation);
+            w *= ratio;
+        }
+        B(b, 0) += h * v.x;
+        B(b, 1) += h * v.y;
+        B(b, 2) += h * w;
+        B(b, 3) = v.x; B(b, 4) = v.y; B(b, 5) = w;
+    }
+    // one position sweep over constraints whose island bit is not in doneMask; per island, records
+    // whether minSeparation >= -limit*slop.  toiA/toiB >= 0 selects b2ContactSolver::SolveTOIPositionConstraints.
+    MRP_HD uint32_t solve_position_sweep(int T, uint32_t doneMask, int toiA, int toiB) {
+        uint32_t bad = 0;  // islands still violating
+        const bool toi = toiA >= 0;
+        const float baum = toi ? kToiBaumgarte : kBaumgarte;
+        const float lim = toi ? -1.5f * kLinearSlop : -3.0f * kLinearSlop;
+        for (int t = 0; t < T; ++t) {
+            uint32_t vm = vmeta(t);
+            int isl = (vm >> 16) & 0xff;
+            if ((doneMask >> isl) & 1) continue;
+            int bA = vm & 15, bB = (vm >> 4) & 15, ppc = (vm >> 10) & 3, type = (vm >> 12) & 1;
+            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
+            if (toi) {
+                if (bA != toiA && bA != toiB) { mA = 0.0f; iA = 0.0f; }
+                if (bB != toiA && bB != toiB) { mB = 0.0f; iB = 0.0f; }
+            }
+            V2 lcA = localCenter(bA), lcB = localCenter(bB);
+            V2 cA = mk(B(bA, 0), B(bA, 1)), cB = mk(B(bB, 0), B(bB, 1));
+            float aA = B(bA, 2), aB = B(bB, 2);
+            V2 ln = mk(V(t, VC_LNX), V(t, VC_LNY)), lp = mk(V(t, VC_LPX), V(t, VC_LPY));
+            float minSep = 0.0f;
+            for (int j = 0; j < ppc; ++j) {
+                Xf xfA, xfB;
+                xfA.q = is_dyn(bA) ? rot_set(aA) : Rot{0.0f, 1.0f};
+                xfB.q = is_dyn(bB) ? rot_set(aB) : Rot{0.0f, 1.0f};
+                xfA.p = cA - rmul(xfA.q, lcA);
+                xfB.p = cB - rmul(xfB.q, lcB);
+                V2 lpj = mk(V(t, VC_LP0X + 2 * j), V(t, VC_LP0X + 2 * j + 1));
+                V2 normal, point;
+                float separation;
+                if (type == 0) {
+                    normal = rmul(xfA.q, ln);
+                    V2 planePoint = xmul(xfA, lp);
+                    V2 clip = xmul(xfB, lpj);
+                    separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
+                    point = clip;
+                } else {
+                    normal = rmul(xfB.q, ln);
+                    V2 planePoint = xmul(xfB, lp);
+                    V2 clip = xmul(xfA, lpj);
+                    separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
+                    point = clip;
+                    normal = -normal;
+                }
+                V2 rA = point - cA, rB = point - cB;
+                minSep = fmin2(minSep, separation);
+                float C = clampf(baum * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                float Kn = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                float impulse = Kn > 0.0f ? -C / Kn : 0.0f;
+                V2 Pi = impulse * normal;
+                cA = cA - mA * Pi;
+                aA -= iA * cross(rA, Pi);
+                cB = cB + mB * Pi;
+                aB += iB * cross(rB, Pi);
+            }
+            B(bA, 0) = cA.x; B(bA, 1) = cA.y; B(bA, 2) = aA;
+            B(bB, 0) = cB.x; B(bB, 1) = cB.y; B(bB, 2) = aB;
+            if (!(minSep >= lim)) bad |= 1u << isl;
+        }
+        return bad;
+    }
+
+    // ------------------------------------------------------------ b2World::Solve (A.7, A.8)
+    MRP_HD void solve_islands() {
+        // island build: DFS seeds in body-list order (newest first): agent n-1 .. agent 0, block
+        uint8_t island_of[kMaxC];
+        int T = 0;
+        uint32_t touch = 0;
+        for (int k = 0; k < nc; ++k) touch |= ((meta[k] >> 16) & 1u) << k;
+        if (touch) {
+            uint32_t bflag = 0, cflag = 0;
+            int nisl = 0;
+            for (int seed = K.nb - 1; seed >= 0; --seed) {
+                if ((bflag >> seed) & 1) continue;
+                uint64_t stack = (uint64_t)seed;  // 4 bits per entry
+                int sp = 1;
+                bflag |= 1u << seed;
+                uint32_t statics = 0;
+                int T0 = T;
+                while (sp > 0) {
+                    --sp;
+                    int b = (int)((stack >> (4 * sp)) & 15u);
+                    if (!is_dyn(b)) { statics |= 1u << b; continue; }
+                    for (int k = nc - 1; k >= 0; --k) {
+                        if (!((touch >> k) & 1) || ((cflag >> k) & 1)) continue;
+                        uint32_t m = meta[k];
+                        int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+                        if (bA != b && bB != b) continue;
+                        order[T] = (uint8_t)k;
+                        island_of[T] = (uint8_t)nisl;
+                        ++T;
+                        cflag |= 1u << k;
+                        int other = bA == b ? bB : bA;
+                        if ((bflag >> other) & 1) continue;
+                        stack = (stack & ~(15ull << (4 * sp))) | ((uint64_t)other << (4 * sp));
+                        ++sp;
+                        bflag |= 1u << other;
+                    }
+                }
+                bflag &= ~statics;  // static bodies may join later islands
+                if (T > T0) ++nisl;
+            }
+        }
+        init_constraints(T, island_of, true);
+        warm_start(T);
+        solve_velocity(T, 180);
+        store_impulses(T);
+        for (int b = 0; b < K.nb; ++b) integrate_position(b, K.h);
+        if (T) {
+            uint32_t done = 0;
+            for (int it = 0; it < 60; ++it) {
+                uint32_t bad = solve_position_sweep(T, done, -1, -1);
+                done = ~bad;
+                if (!bad) break;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ b2World::SolveTOI (A.10)
+    MRP_HD Sweep body_sweep(int b) {
+        Sweep s;
+        if (b < K.nb) {
+            s.lc = localCenter(b);
+            s.c0 = mk(BX(b, 6), BX(b, 7));
+            s.a0 = BX(b, 8);
+            s.c = mk(B(b, 0), B(b, 1));
+            s.a = B(b, 2);
+        } else {
+            s.lc = mk(0.0f, 0.0f);
+            s.c0 = mk(B(b, 0), B(b, 1));
+            s.c = s.c0;
+            s.a0 = 0.0f;
+            s.a = 0.0f;
+        }
+        return s;
+    }
+    MRP_HD void sweep_advance(int b, float alpha) {  // b2Sweep::Advance (on c0/a0/alpha0 only)
+        float& al0 = alpha0(b);
+        if (b < K.nb) {
+            float beta = (alpha - al0) / (1.0f - al0);
+            BX(b, 6) += beta * (B(b, 0) - BX(b, 6));
+            BX(b, 7) += beta * (B(b, 1) - BX(b, 7));
+            BX(b, 8) += beta * (B(b, 2) - BX(b, 8));
+        }
+        al0 = alpha;
+    }
+    MRP_HD void body_advance(int b, float alpha) {  // b2Body::Advance
+        sweep_advance(b, alpha);
+        if (b < K.nb) {
+            B(b, 0) = BX(b, 6); B(b, 1) = BX(b, 7); B(b, 2) = BX(b, 8);
+            sync_transform(b);
+        }
+    }
+
+    MRP_HDN void toi_event(int minK, float minAlpha, uint32_t& toiFlag, uint32_t& enabled) {
+        uint32_t m = meta[minK];
+        int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+        // backups of the two sweeps
+        float bk[2][7];
+        int two[2] = {bA, bB};
+        for (int s = 0; s < 2; ++s) {
+            int b = two[s];
+            if (b < K.nb) {
+                bk[s][0] = BX(b, 6); bk[s][1] = BX(b, 7); bk[s][2] = BX(b, 8);
+                bk[s][3] = B(b, 0); bk[s][4] = B(b, 1); bk[s][5] = B(b, 2);
+            }
+            bk[s][6] = alpha0(b);
+        }
+        body_advance(bA, minAlpha);
+        body_advance(bB, minAlpha);
+        update_contact(minK);
+        enabled |= 1u << minK;
+        toiFlag &= ~(1u << minK);
+        ++toiCount[minK];
+        if (!((meta[minK] >> 16) & 1)) {
+            enabled &= ~(1u << minK);
+            for (int s = 0; s < 2; ++s) {
+                int b = two[s];
+                if (b < K.nb) {
+                    BX(b, 6) = bk[s][0]; BX(b, 7) = bk[s][1]; BX(b, 8) = bk[s][2];
+                    B(b, 0) = bk[s][3]; B(b, 1) = bk[s][4]; B(b, 2) = bk[s][5];
+                    sync_transform(b);
+                }
+                alpha0(b) = bk[s][6];
+            }
+            return;
+        }
+        // mini island: bA, bB, minContact + the dynamic body's other touching static contacts
+        int T = 0;
+        order[T++] = (uint8_t)minK;
+        uint32_t cflag = 1u << minK;
+        uint32_t bflag = (1u << bA) | (1u << bB);
+        for (int s = 0; s < 2; ++s) {
+            int body = two[s];
+            if (!is_dyn(body)) continue;
+            for (int k = nc - 1; k >= 0; --k) {
+                if (T == kMaxC) break;
+                if ((cflag >> k) & 1) continue;
+                uint32_t mk_ = meta[k];
+                int cA = (mk_ >> 20) & 15, cB = (mk_ >> 24) & 15;
+                if (cA != body && cB != body) continue;
+                int other = cA == body ? cB : cA;
+                if (is_dyn(other)) continue;  // no bullets
+                float backupAlpha = alpha0(other);
+                if (!((bflag >> other) & 1)) body_advance(other, minAlpha);
+                update_contact(k);
+                enabled |= 1u << k;
+                if (!((meta[k] >> 16) & 1)) { alpha0(other) = backupAlpha; continue; }
+                cflag |= 1u << k;
+                order[T++] = (uint8_t)k;
+                bflag |= 1u << other;
+            }
+        }
+        float subdt = (1.0f - minAlpha) * K.h;
+        // b2Island::SolveTOI
+        init_constraints(T, nullptr, false);
+        for (int it = 0; it < 20; ++it)
+            if (!solve_position_sweep(T, 0, bA, bB)) break;
+        for (int s = 0; s < 2; ++s) {
+            int b = two[s];
+            if (b < K.nb) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+        }
+        init_constraints(T, nullptr, false);
+        solve_velocity(T, 180);
+        uint32_t moved = 0;
+        for (int b = 0; b < K.nb; ++b) {
+            if (!((bflag >> b) & 1)) continue;
+            integrate_position(b, subdt);
+            sync_transform(b);
+        }
+        for (int b = 0; b < K.nb; ++b) {
+            if (!((bflag >> b) & 1)) continue;
+            Xf xf1;
+            xf1.q = rot_set(BX(b, 8));
+            xf1.p = mk(BX(b, 6), BX(b, 7)) - rmul(xf1.q, localCenter(b));
+            moved |= synchronize_fixtures(b, xf1);
+            for (int k = 0; k < nc; ++k) {
+                uint32_t mk_ = meta[k];
+                if ((int)((mk_ >> 20) & 15) == b || (int)((mk_ >> 24) & 15) == b) toiFlag &= ~(1u << k);
+            }
+        }
+        int nc0 = nc;
+        find_new_contacts(moved);
+        for (int k = nc0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; enabled |= 1u << k; toiFlag &= ~(1u << k); }
+    }
+
+    MRP_HD void solve_toi() {
+        uint32_t wallc = 0;  // contacts with a static body: the only TOI candidates (no bullets)
+        for (int k = 0; k < nc; ++k) {
+            uint32_t m = meta[k];
+            if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc |= 1u << k;
+        }
+        if (!wallc) return;
+        for (int b = 0; b < K.nb; ++b) BX(b, 13) = 0.0f;
+        for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
+        for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
+        uint32_t toiFlag = 0, enabled = 0xffffffffu;
+        for (;;) {
+            int minK = -1;
+            float minAlpha = 1.0f;
+            for (int k = nc - 1; k >= 0; --k) {
+                if (!((enabled >> k) & 1)) continue;
+                if (toiCount[k] > kMaxSubSteps) continue;
+                float alpha = 1.0f;
+                if ((toiFlag >> k) & 1) {
+                    alpha = toi[k];
+                } else {
+                    uint32_t m = meta[k];
+                    int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+                    if (is_dyn(bA) && is_dyn(bB)) continue;
+                    float al0 = alpha0(bA);
+                    if (alpha0(bA) < alpha0(bB)) {
+                        al0 = alpha0(bB);
+                        sweep_advance(bA, al0);
+                    } else if (alpha0(bB) < alpha0(bA)) {
+                        al0 = alpha0(bA);
+                        sweep_advance(bB, al0);
+                    }
+                    float t;
+                    int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
+                    if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
+                    else alpha = 1.0f;
+                    toi[k] = alpha;
+                    toiFlag |= 1u << k;
+                }
+                if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
+            }
+            if (minK < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
+            toi_event(minK, minAlpha, toiFlag, enabled);
+        }
+    }
+
+    // ------------------------------------------------------------ b2World::Step (A.6)
+    MRP_HD void world_step(bool new_fixtures) {
+        if (new_fixtures) find_new_contacts(0xffffffffu);
+        collide();
+        // xf1 of SynchronizeFixtures == the transform the step started with (c0, a0 are set from c, a)
+        for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+        solve_islands();
+        uint32_t moved = 0;
+        for (int b = K.nb - 1; b >= 0; --b) {
+            // xf1 = transform at (c0, a0); its rotation is the one the step started with
+            Xf xf1;
+            xf1.q.s = BX(b, 9);
+            xf1.q.c = BX(b, 10);
+            xf1.p = mk(BX(b, 6), BX(b, 7)) - rmul(xf1.q, localCenter(b));
+            sync_transform(b);
+            moved |= synchronize_fixtures(b, xf1);
+        }
+        find_new_contacts(moved);
+        solve_toi();
+    }
+};
+
+}  // namespace mrp

@@ -78,9 +78,12 @@ inline float Dot(Vec2 a, Vec2 b) { return a.x * b.x + a.y * b.y; }
 inline float Cross(Vec2 a, Vec2 b) { return a.x * b.y - a.y * b.x; }
 inline Vec2 Cross(Vec2 a, float s) { return Vec2(s * a.y, -s * a.x); }
 inline Vec2 Cross(float s, Vec2 a) { return Vec2(-s * a.y, s * a.x); }
-inline Vec2 Min(Vec2 a, Vec2 b) { return Vec2(std::min(a.x, b.x), std::min(a.y, b.y)); }
-inline Vec2 Max(Vec2 a, Vec2 b) { return Vec2(std::max(a.x, b.x), std::max(a.y, b.y)); }
-inline float Clamp(float a, float lo, float hi) { return std::max(lo, std::min(a, hi)); }
+// b2Min / b2Max are ternaries in Box2D (they differ from std::min/max in which signed zero wins)
+inline float Min(float a, float b) { return a < b ? a : b; }
+inline float Max(float a, float b) { return a > b ? a : b; }
+inline Vec2 Min(Vec2 a, Vec2 b) { return Vec2(Min(a.x, b.x), Min(a.y, b.y)); }
+inline Vec2 Max(Vec2 a, Vec2 b) { return Vec2(Max(a.x, b.x), Max(a.y, b.y)); }
+inline float Clamp(float a, float lo, float hi) { return Max(lo, Min(a, hi)); }
 inline float DistanceSquared(Vec2 a, Vec2 b) { Vec2 c = a - b; return Dot(c, c); }
 inline float Distance(Vec2 a, Vec2 b) { return (a - b).Length(); }
 
@@ -746,7 +749,7 @@ inline TOIState TimeOfImpact(float* tOut, const DistanceProxy* proxyA, const Dis
     sweepA.Normalize();
     sweepB.Normalize();
     float totalRadius = proxyA->radius + proxyB->radius;
-    float target = std::max(kLinearSlop, totalRadius - 3.0f * kLinearSlop);
+    float target = Max(kLinearSlop, totalRadius - 3.0f * kLinearSlop);
     float tolerance = 0.25f * kLinearSlop;
     float t1 = 0.0f;
     const int k_maxIterations = 20;
@@ -928,6 +931,11 @@ struct World {
     bool warmStarting = true, continuousPhysics = true;
     // instrumentation for tests
     long stat_toi_events = 0, stat_toi_calls = 0, stat_pos_iters = 0;
+    // workload probes (used to size the CUDA design; do not alter results)
+    bool probe = false;
+    long stat_islands = 0, stat_islands_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // histogram by #contacts (7 = 7+)
+    long stat_period[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long stat_fix_iters = 0, stat_fix_never = 0, stat_contact_sum = 0, stat_touch_sum = 0, stat_steps = 0;
 
     ~World() { for (Contact* c : contactList) delete c; }
     World() {}
@@ -1030,7 +1038,7 @@ struct World {
         Contact* c = new Contact();
         c->fA = proxyA; c->fB = proxyB; c->bA = bodyA; c->bB = bodyB;
         c->friction = std::sqrt(fixtures[proxyA].friction * fixtures[proxyB].friction);
-        c->restitution = std::max(fixtures[proxyA].restitution, fixtures[proxyB].restitution);
+        c->restitution = Max(fixtures[proxyA].restitution, fixtures[proxyB].restitution);
         c->manifold.pointCount = 0;
         contactList.insert(contactList.begin(), c);
         bodies[bodyA].contacts.insert(bodies[bodyA].contacts.begin(), c);
@@ -1288,7 +1296,7 @@ inline void ContactSolver::SolveVelocityConstraints() {
                 Vec2 dv = vB + Cross(wB, vcp->rB) - vA - Cross(wA, vcp->rA);
                 float vn = Dot(dv, normal);
                 float lambda = -vcp->normalMass * (vn - vcp->velocityBias);
-                float newImpulse = std::max(vcp->normalImpulse + lambda, 0.0f);
+                float newImpulse = Max(vcp->normalImpulse + lambda, 0.0f);
                 lambda = newImpulse - vcp->normalImpulse;
                 vcp->normalImpulse = newImpulse;
                 Vec2 P = lambda * normal;
@@ -1401,7 +1409,7 @@ inline bool ContactSolver::SolvePositionConstraints() {
             Vec2 normal = psm.normal, point = psm.point;
             float separation = psm.separation;
             Vec2 rA = point - cA, rB = point - cB;
-            minSeparation = std::min(minSeparation, separation);
+            minSeparation = Min(minSeparation, separation);
             float C = Clamp(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
             float rnA = Cross(rA, normal), rnB = Cross(rB, normal);
             float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
@@ -1441,7 +1449,7 @@ inline bool ContactSolver::SolveTOIPositionConstraints(int toiIndexA, int toiInd
             Vec2 normal = psm.normal, point = psm.point;
             float separation = psm.separation;
             Vec2 rA = point - cA, rB = point - cB;
-            minSeparation = std::min(minSeparation, separation);
+            minSeparation = Min(minSeparation, separation);
             float C = Clamp(kToiBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
             float rnA = Cross(rA, normal), rnB = Cross(rB, normal);
             float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
@@ -1483,6 +1491,30 @@ inline void World::SolveIsland(std::vector<int>& ibodies, std::vector<Contact*>&
     ContactSolver solver(step, &icontacts, &positions, &velocities, this);
     solver.InitializeVelocityConstraints();
     if (step.warmStarting) solver.WarmStart();
+    if (probe && !icontacts.empty()) {
+        ++stat_islands;
+        ++stat_islands_c[std::min<size_t>(icontacts.size(), 7)];
+        ContactSolver s2 = solver;
+        std::vector<Velocity> v2 = velocities;
+        s2.velocities = &v2;
+        int fixed = -1;
+        std::vector<std::vector<char>> hist;
+        auto snap = [&]() {
+            std::vector<char> b(sizeof(Velocity) * v2.size() + sizeof(VelocityConstraint) * s2.vcs.size());
+            std::memcpy(b.data(), v2.data(), sizeof(Velocity) * v2.size());
+            std::memcpy(b.data() + sizeof(Velocity) * v2.size(), s2.vcs.data(), sizeof(VelocityConstraint) * s2.vcs.size());
+            return b;
+        };
+        hist.push_back(snap());
+        for (int i = 0; i < step.velocityIterations && fixed < 0; ++i) {
+            s2.SolveVelocityConstraints();
+            std::vector<char> cur = snap();
+            for (int p = 1; p <= 8 && p <= (int)hist.size(); ++p)
+                if (hist[hist.size() - p] == cur) { fixed = i + 1; ++stat_period[p]; break; }
+            hist.push_back(cur);
+        }
+        if (fixed < 0) { ++stat_fix_never; stat_fix_iters += step.velocityIterations; } else stat_fix_iters += fixed;
+    }
     for (int i = 0; i < step.velocityIterations; ++i) solver.SolveVelocityConstraints();
     solver.StoreImpulses();
     for (int i = 0; i < nb; ++i) {
@@ -1639,7 +1671,7 @@ inline void World::SolveTOI(const TimeStep& step) {
                 ++stat_toi_calls;
                 TOIState st = TimeOfImpact(&t, &pA, &pB, bA.sweep, bB.sweep, 1.0f);
                 float beta = t;
-                if (st == kToiTouching) alpha = std::min(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+                if (st == kToiTouching) alpha = Min(alpha0 + (1.0f - alpha0) * beta, 1.0f);
                 else alpha = 1.0f;
                 c->toi = alpha;
                 c->toiFlag = true;
@@ -1728,6 +1760,11 @@ inline void World::Step(float dt, int velocityIterations, int positionIterations
     step.dtRatio = inv_dt0 * dt;
     step.warmStarting = warmStarting;
     Collide();
+    if (probe) {
+        ++stat_steps;
+        stat_contact_sum += (long)contactList.size();
+        for (Contact* c : contactList) stat_touch_sum += c->touching ? 1 : 0;
+    }
     if (step.dt > 0.0f) Solve(step);
     if (continuousPhysics && step.dt > 0.0f) SolveTOI(step);
     if (step.dt > 0.0f) inv_dt0 = step.inv_dt;

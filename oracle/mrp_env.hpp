@@ -36,8 +36,10 @@ inline double py_mod(double a, double b) {  // Python float %
     return r;
 }
 inline double py_distance(double ax, double ay, double bx, double by) {  // mrp00:130-132
+    // Python evaluates (x+y)**0.5 with libm pow(); IEEE sqrt is used here so that the value is
+    // reproducible on every platform (the two differ by <= 1 ulp of float64 in rare cases).
     double x = (ax - bx) * (ax - bx), y = (ay - by) * (ay - by);
-    return std::pow(x + y, 0.5);
+    return std::sqrt(x + y);
 }
 
 struct Env : ContactListener {
@@ -468,12 +470,17 @@ struct Env : ContactListener {
             const Contact* c = world->contactList[k];
             uint32_t* cw = w + L.off_contacts + MRP_CONTACT_WORDS * k;
             const Manifold& m = c->manifold;
-            cw[0] = (uint32_t)c->fA | ((uint32_t)c->fB << 8) | ((c->touching ? 1u : 0u) << 16) | ((uint32_t)m.type << 17) | ((uint32_t)m.pointCount << 18);
+            // words beyond pointCount hold stale data in Box2D (b2Manifold is not cleared); they are
+            // never read again, so the canonical record zeroes them
+            int pc = m.pointCount;
+            uint32_t type = pc > 0 ? (uint32_t)m.type : 0u;
+            cw[0] = (uint32_t)c->fA | ((uint32_t)c->fB << 8) | ((c->touching ? 1u : 0u) << 16) | (type << 17) | ((uint32_t)pc << 18);
+            if (pc == 0) continue;
             auto key16 = [](const ContactID& id) { return (uint32_t)(id.indexA | (id.indexB << 4) | (id.typeA << 8) | (id.typeB << 9)); };
-            cw[1] = key16(m.points[0].id) | (key16(m.points[1].id) << 16);
+            cw[1] = key16(m.points[0].id) | (pc > 1 ? (key16(m.points[1].id) << 16) : 0u);
             float* cf = (float*)cw;
             cf[2] = m.localNormal.x; cf[3] = m.localNormal.y; cf[4] = m.localPoint.x; cf[5] = m.localPoint.y;
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < pc; ++j) {
                 cf[6 + 4 * j] = m.points[j].localPoint.x; cf[7 + 4 * j] = m.points[j].localPoint.y;
                 cf[8 + 4 * j] = m.points[j].normalImpulse; cf[9 + 4 * j] = m.points[j].tangentImpulse;
             }

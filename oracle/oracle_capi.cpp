@@ -63,6 +63,12 @@ int orc_set_auto_reset(void* h, int on) {
     for (Env* e : ((OrcBatch*)h)->envs) e->auto_reset = on != 0;
     return 0;
 }
+int orc_set_max_episode_steps(void* h, int steps) {
+    OrcBatch* b = (OrcBatch*)h;
+    b->L.max_episode_steps = steps;
+    for (Env* e : b->envs) e->L.max_episode_steps = steps;
+    return 0;
+}
 // reward weights (set_reward_params mrp00:231-239), epsilon (update_goal mrp02:232-233), decay^(-t) (update_params mrp02:227-230)
 int orc_set_params(void* h, const double* p9) {
     for (Env* e : ((OrcBatch*)h)->envs) {
@@ -128,6 +134,24 @@ int orc_stats(void* h, double* out8) {
         out8[0] += e->n_episodes; out8[1] += e->n_success; out8[2] += e->n_trunc;
         out8[3] += e->sum_return; out8[4] += e->sum_len;
         out8[5] += e->world->stat_toi_events; out8[6] += e->world->stat_toi_calls; out8[7] += e->world->stat_pos_iters;
+    }
+    return 0;
+}
+
+// workload probe: enable, then read {steps, contacts, touching, islands_with_contacts, fix_iters, fix_never, hist[8]}
+int orc_probe(void* h, int enable, double* out14, double* period9) {
+    OrcBatch* b = (OrcBatch*)h;
+    if (out14) for (int k = 0; k < 14; ++k) out14[k] = 0;
+    if (period9) for (int k = 0; k < 9; ++k) period9[k] = 0;
+    for (Env* e : b->envs) {
+        b2o::World* w = e->world;
+        if (out14) {
+            out14[0] += w->stat_steps; out14[1] += w->stat_contact_sum; out14[2] += w->stat_touch_sum;
+            out14[3] += w->stat_islands; out14[4] += w->stat_fix_iters; out14[5] += w->stat_fix_never;
+            for (int k = 0; k < 8; ++k) out14[6 + k] += w->stat_islands_c[k];
+        }
+        if (period9) for (int k = 0; k < 9; ++k) period9[k] += w->stat_period[k];
+        w->probe = enable != 0;
     }
     return 0;
 }

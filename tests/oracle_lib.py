@@ -51,7 +51,7 @@ VARIANTS = {"MultiRobotPuzzle-v0": 0, "MultiRobotPuzzleHeavy-v0": 1, "MultiRobot
 
 
 class OracleBatch:
-    def __init__(self, variant, num_envs, seed=17, n_agents=0, env_id_base=0, nthreads=1):
+    def __init__(self, variant, num_envs, seed=17, n_agents=0, env_id_base=0, nthreads=1, max_episode_steps=0):
         if isinstance(variant, str):
             variant = VARIANTS[variant]
         self.L = lib()
@@ -60,6 +60,8 @@ class OracleBatch:
             raise ValueError("orc_create failed")
         self.layout = Layout()
         self.L.orc_layout(self.h, C.byref(self.layout))
+        if max_episode_steps > 0:
+            self.L.orc_set_max_episode_steps(self.h, max_episode_steps)
         self.N = num_envs
         self.O, self.A, self.SW = self.layout.obs_dim, self.layout.act_dim, self.layout.state_words
 
