@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the MultiRobotPuzzle hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # native arm (sm_100a kernels through the C-ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement on the host cores
+
+Workload (config.workload): MultiRobotPuzzleHeavy-v0 (5 robots, 2x block), 1,048,576 envs per GPU, random actions
+U(-1,1) from the Philox ACTION stream, auto-reset on (BASELINE.json configs[2]; the registered TimeLimit of 3000
+steps applies).  One "step" = one env.step of every env of the batch.
+
+  value     whole-job env-steps/s with actions already resident in HBM (pre-generated ring of action buffers),
+            K steps bracketed by barrier + synchronize, CUDA-event timed, max over ranks.
+  e2e       the same through mrp_step_host(): pinned HOST action buffer -> H2D, step, obs/reward/done/trunc D2H,
+            every step, copies inside the timed region.
+  roofline  dominant kernel k_step: algorithmic bytes (513 B per env-step, SURVEY.md §8d / DESIGN.md) over its mean
+            launch time measured with CUDA events recorded around that launch inside the library (mrp_set_timing).
+  cpu_baseline  the oracle ("port": pybox2d is not installable here) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ENV_ID = "MultiRobotPuzzleHeavy-v0"
+ALGO_BYTES_PER_ENV_STEP = 513  # 4*(A+O+1)+1 + 2*24*(n+1) with A=15, O=40, n=5
+METRIC = "env-steps/sec MultiRobotPuzzleHeavy-v0"
+UNIT = "env-steps/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_run(n_envs, steps, warmup, nthreads):
+    """Oracle (CPU restatement of the reference path) on the host cores; returns env-steps/s."""
+    from oracle_lib import OracleBatch
+
+    o = OracleBatch(ENV_ID, n_envs, seed=17, nthreads=nthreads)
+    o.reset()
+    acts = [o.sample_actions(t) for t in range(4)]
+    for t in range(warmup):
+        o.step(acts[t % 4])
+    t0 = time.perf_counter()
+    for t in range(steps):
+        o.step(acts[t % 4])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.ref_envs
+    v, dt = cpu_baseline_run(n_envs, args.steps, max(args.warmup, 1), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID}, random actions U(-1,1), auto-reset; each step = one env.step of a bounded sample of "
+                               f"{n_envs} envs on the host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_envs} envs x {args.steps} steps, {cores} threads (pybox2d not installable: oracle/ C++ restatement, "
+                                   "no Python/SWIG overhead => upper bound on the reference)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    import gym_puzzles_b200 as gp
+
+    N = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+    env = gp.VectorEnv(ENV_ID, N, device=dev, seed=17, env_id_base=rank * N)
+    h = env.handle
+    A, O = h.act_dim, h.obs_dim
+    env.reset()
+    R = 4  # ring of pre-generated action buffers: inputs are resident in HBM before the timed region
+    acts = torch.empty((R, N, A), dtype=torch.float32, device=dev)
+    for r in range(R):
+        env.sample_actions(step_index=r, out=acts[r])
+    for t in range(W):
+        env.step(acts[t % R])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = None
+    if rank == 0:
+        try:
+            gpu_sel = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", "")
+        except Exception:
+            gpu_sel = str(local_rank)
+        sampler = ClockSampler(gpu_sel)
+    # ---------------- device-resident throughput
+    h.set_timing(True)
+    h.get_timing(reset_after=True)
+    launches0 = h.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for t in range(K):
+        env.step(acts[t % R])
+    e1.record()
+    barrier()
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    launches = h.launch_count - launches0
+    k_ms, k_cnt = h.get_timing(reset_after=True)
+    h.set_timing(False)
+    value = world * N * K / (elapsed_ms / 1e3)
+
+    # ---------------- end to end through the host-buffer C-ABI call (pinned host memory)
+    Ke = max(2, min(K, args.e2e_steps))
+    host_act = acts[0].cpu().pin_memory()
+    host_obs = torch.empty((N, O), dtype=torch.float32).pin_memory()
+    host_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
+    host_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    host_trunc = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    np_args = [x.numpy() for x in (host_act, host_obs, host_rew, host_done, host_trunc)]
+    h.step_host(np_args[0], *np_args[1:])  # warm
+    barrier()
+    e0.record()
+    for t in range(Ke):
+        h.step_host(np_args[0], *np_args[1:])
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / (float(e2e_ms.item()) / 1e3)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # the one collective of this path: episode statistics, 8 doubles summed over ranks (NCCL)
+    stats = env.episode_stats(reduce_across_ranks=True, reset=False)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        k_mean_ms = k_ms / max(k_cnt, 1)
+        achieved = ALGO_BYTES_PER_ENV_STEP * N / (k_mean_ms / 1e3) / 1e9 if k_mean_ms > 0 else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID}, {N} envs per GPU ({world * N} total), random actions U(-1,1) (Philox), auto-reset, "
+                                   "TimeLimit 3000", "envs_per_gpu": N, "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "l2": "per-step working set (state 2.3 GB + obs/actions 0.23 GB per GPU) >> 126 MB L2, no flush needed"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * A * 4, "d2h_bytes_per_step": N * (O * 4 + 4 + 1 + 1),
+                    "steps": Ke, "ms_per_step": float(e2e_ms.item()) / Ke},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_step", "kernel_ms": k_mean_ms, "kernel_share_of_step": (k_ms / elapsed_ms) if elapsed_ms else None,
+                         "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
+            "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, dt = cpu_baseline_run(args.ref_envs, args.cpu_steps, 2, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_envs} envs x {args.cpu_steps} steps of the same workload, {cores} threads, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs", type=int, default=1048576, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--ref-envs", type=int, default=32768, help="bounded sample of the workload for the CPU arm")
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

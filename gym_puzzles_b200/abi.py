@@ -24,7 +24,7 @@ STAT_NAMES = ("episodes", "done_by_env", "truncated", "sum_return", "sum_return_
 EXPORTS = (
     "mrp_last_error", "mrp_backend", "mrp_create", "mrp_destroy", "mrp_get_layout", "mrp_get_buffers", "mrp_reset",
     "mrp_step", "mrp_step_host", "mrp_reset_host", "mrp_sample_actions", "mrp_get_state", "mrp_set_state",
-    "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_launch_count",
+    "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_set_timing", "mrp_get_timing", "mrp_launch_count",
 )
 
 
@@ -83,6 +83,8 @@ class MrpLib:
         L.mrp_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.mrp_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.mrp_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.mrp_set_timing.argtypes = [C.c_void_p, C.c_int32]
+        L.mrp_get_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
         L.mrp_launch_count.argtypes = [C.c_void_p]
         L.mrp_launch_count.restype = C.c_int64
 
@@ -200,6 +202,15 @@ class Handle:
         s = np.zeros(N_STATS, dtype=np.float64)
         self.lib.check(self.lib.lib.mrp_get_stats(self.h, _ptr(s), 1 if reset_after else 0), "mrp_get_stats")
         return dict(zip(STAT_NAMES, s.tolist()))
+
+    def set_timing(self, enable):
+        self.lib.check(self.lib.lib.mrp_set_timing(self.h, 1 if enable else 0), "mrp_set_timing")
+
+    def get_timing(self, reset_after=True):
+        """-> (total milliseconds spent in the step kernel, number of step-kernel launches)"""
+        ms, n = C.c_double(), C.c_int64()
+        self.lib.check(self.lib.lib.mrp_get_timing(self.h, C.byref(ms), C.byref(n), 1 if reset_after else 0), "mrp_get_timing")
+        return ms.value, n.value
 
     @property
     def launch_count(self):

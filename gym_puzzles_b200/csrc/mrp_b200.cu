@@ -162,6 +162,14 @@ struct mrp_handle {
     float* act_dev;
     int64_t launches;
     size_t smem_bytes;
+    // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
+    int timing;
+    int ev_n;          // pairs recorded and not yet accumulated
+    double k_ms;       // accumulated k_step milliseconds
+    int64_t k_count;   // accumulated k_step launches
+#ifndef MRP_HOST_EMU
+    cudaEvent_t ev0[64], ev1[64];
+#endif
 #ifdef MRP_HOST_EMU
     float* emu_sm;
 #endif
@@ -209,10 +217,13 @@ const char* mrp_backend(void) {
 #endif
 }
 
+int mrp_set_timing(mrp_handle* h, int32_t enable);
+
 int mrp_destroy(mrp_handle* h) {
     if (!h) return 0;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
+    if (h->timing) mrp_set_timing(h, 0);
 #else
     free(h->emu_sm);
 #endif
@@ -344,6 +355,44 @@ int mrp_reset(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
 #endif
 }
 
+#ifndef MRP_HOST_EMU
+static void drain_timing(mrp_handle* h) {
+    for (int i = 0; i < h->ev_n; ++i) {
+        float ms = 0.0f;
+        cudaEventSynchronize(h->ev1[i]);
+        if (cudaEventElapsedTime(&ms, h->ev0[i], h->ev1[i]) == cudaSuccess) { h->k_ms += ms; h->k_count += 1; }
+    }
+    h->ev_n = 0;
+}
+#endif
+
+int mrp_set_timing(mrp_handle* h, int32_t enable) {
+    if (!h) return fail(-1, "mrp_set_timing: null handle");
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (enable && !h->timing)
+        for (int i = 0; i < 64; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); }
+    if (!enable && h->timing) {
+        drain_timing(h);
+        for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
+    }
+#endif
+    h->timing = enable ? 1 : 0;
+    return 0;
+}
+
+int mrp_get_timing(mrp_handle* h, double* total_ms, int64_t* count, int32_t reset_after) {
+    if (!h || !total_ms || !count) return fail(-1, "mrp_get_timing: null argument");
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (h->timing) drain_timing(h);
+#endif
+    *total_ms = h->k_ms;
+    *count = h->k_count;
+    if (reset_after) { h->k_ms = 0.0; h->k_count = 0; }
+    return 0;
+}
+
 int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
     if (!h) return fail(-1, "mrp_step: null handle");
     SimConst K = h->K;
@@ -352,7 +401,12 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (K.auto_reset) k_clear_count<<<1, 1, 0, st>>>(K.reset_count);
+    if (h->timing) {
+        if (h->ev_n == 64) drain_timing(h);
+        cudaEventRecord(h->ev0[h->ev_n], st);
+    }
     k_step<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
+    if (h->timing) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     h->launches += 1;
     if (K.auto_reset) {
         k_reset_list<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);

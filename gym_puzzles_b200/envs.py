@@ -1,0 +1,129 @@
+"""Single-environment classes with the reference's gym surface (reset / step / seed / spaces / knobs).
+
+Drop-in for `gym.make('MultiRobotPuzzle-v0')` etc. (reference gym_puzzles/__init__.py:3-29,
+gym_puzzles/envs/__init__.py:1-2): each instance is a 1-env C-ABI handle on the GPU; `step` takes / returns numpy
+like the reference (obs float32 instead of the reference's float64 array — SURVEY.md C.8).  TimeLimit is folded in
+(`info['TimeLimit.truncated']`).  Rendering is out of scope (host-side viewer code stays with the reference).
+For throughput use `VectorEnv`; this class pays one kernel launch + two PCIe copies per step by construction.
+"""
+import numpy as np
+
+from . import abi, spaces
+
+
+class MultiRobotPuzzle:
+    env_id = "MultiRobotPuzzle-v0"
+    metadata = {"render.modes": [], "video.frames_per_second": 50}
+    reward_range = (-float("inf"), float("inf"))
+    spec = None
+
+    def __init__(self, obs_depth=3, frameskip=4, num_agents=0, seed=17, device=0, _lib=None):
+        # obs_depth / frameskip are accepted for signature compatibility (reference mrp00:152-162: the low-dim
+        # env forces frameskip to 1); v2's ctor is (frameskip=1, num_agents=2) (reference mrp02:139)
+        self._seed_value = seed
+        self._device = device
+        self._lib = _lib
+        self._num_agents = num_agents
+        self._episode_base = 0
+        self._make_handle()
+        self.observation_space = spaces.observation_space(self.env_id, self.num_agents)
+        self.action_space = spaces.action_space(self.env_id, self.num_agents)
+        self.done_status = None
+        self._last_done = False
+
+    def _make_handle(self):
+        self._h = abi.Handle(self.env_id, 1, device=self._device, seed=self._seed_value, n_agents=self._num_agents,
+                             auto_reset=False, lib=self._lib)
+        self.num_agents = self._h.layout.n_agents
+
+    # ---- gym API
+    def seed(self, seed=None):
+        """reference mrp00:211-216.  Here the seed keys the Philox spawn stream, so (unlike the reference, whose
+        spawns use numpy's global RNG — SURVEY.md C.2) it does make resets reproducible."""
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+        self._seed_value = int(seed)
+        self._h.close()
+        self._make_handle()
+        return [self._seed_value]
+
+    def reset(self):
+        self.done_status = None
+        self._last_done = False
+        return self._h.reset_host()[0].copy()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(1, -1)
+        if a.shape[1] != self._h.act_dim:
+            raise ValueError(f"action must have {self._h.act_dim} entries, got {a.shape[1]}")
+        obs, rew, done, trunc = self._h.step_host(a)
+        info = {}
+        if done[0]:
+            if trunc[0]:
+                info["TimeLimit.truncated"] = True
+            else:
+                self.done_status = "puzzle complete!!" if self.env_id.endswith("-v0") else "episode finished"
+        self._last_done = bool(done[0])
+        return obs[0].copy(), float(rew[0]), bool(done[0]), info
+
+    def render(self, mode="human", close=False):
+        raise NotImplementedError("rendering is out of scope of the B200 hot path; use the reference viewer on get_state()")
+
+    def close(self):
+        self._h.close()
+
+    # ---- knobs (reference mrp00:231-258 / mrp02:216-245)
+    def set_reward_params(self, agentDelta=None, agentDistance=None, blockDelta=None, blockDistance=None, puzzleComp=10000,
+                          outOfBounds=1000, blkOutOfBounds=100):
+        cur = self._h.get_params()
+        kw = dict(puzzleComp=puzzleComp, outOfBounds=outOfBounds, blkOutOfBounds=blkOutOfBounds)
+        for k, v in (("agentDelta", agentDelta), ("agentDistance", agentDistance), ("blockDelta", blockDelta), ("blockDistance", blockDistance)):
+            kw[k] = cur[k] if v is None else v
+        self._h.set_params(**kw)
+
+    def update_params(self, timestep, decay):
+        self._h.set_params(decay_pow=float(decay) ** (-float(timestep)))
+
+    def update_goal(self, epoch, nb_epochs):
+        self._h.set_params(scaled_epsilon=0.1 * (2 - epoch / nb_epochs))
+
+    def get_deltaAgent(self):
+        return self._h.get_params()["agentDelta"]
+
+    def get_agentDist(self):
+        return self._h.get_params()["agentDistance"]
+
+    def get_deltaBlk(self):
+        return self._h.get_params()["blockDelta"]
+
+    def get_blkDist(self):
+        return self._h.get_params()["blockDistance"]
+
+    def _return_status(self):
+        return self.done_status if self.done_status else "Stayed in bounds"
+
+    # ---- state (new: the reference cannot serialise an env)
+    def get_state(self):
+        return self._h.get_state()[0]
+
+    def set_state(self, words):
+        self._h.set_state(np.asarray(words, dtype=np.uint32).reshape(1, -1))
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class MultiRobotPuzzleHeavy(MultiRobotPuzzle):
+    env_id = "MultiRobotPuzzleHeavy-v0"   # heavy = True, number_agents = 5 (reference mrp00:606-610)
+
+
+class MultiRobotPuzzle2(MultiRobotPuzzle):
+    env_id = "MultiRobotPuzzle-v2"
+
+    def __init__(self, frameskip=1, num_agents=2, seed=17, device=0, _lib=None):
+        super().__init__(frameskip=frameskip, num_agents=num_agents, seed=seed, device=device, _lib=_lib)
+
+
+class MultiRobotPuzzleHeavy2(MultiRobotPuzzle2):
+    env_id = "MultiRobotPuzzleHeavy-v2"   # heavy = True: block density 20 (reference mrp02:162-163,711-712)

@@ -1,0 +1,118 @@
+"""CPU-side parity of the *kernel source* against the oracle.
+
+tests/emu/libmrp_emu.so is gym_puzzles_b200/csrc/mrp_b200.cu compiled for the host (-DMRP_HOST_EMU): the same
+lane-per-env step code the GPU runs, executed in a loop.  It lets the GPU-less container check the kernel logic
+bit for bit; the `-m gpu` tests repeat this on the real device through the product library."""
+import numpy as np
+import pytest
+
+from emu_lib import emu_lib
+from gym_puzzles_b200 import abi
+from oracle_lib import OracleBatch
+from parity_util import rollout_compare, single_step_compare
+
+
+def _exact(rep):
+    assert rep["flag_mismatch"] == 0 and rep["done_mismatch"] == 0, rep
+    assert rep["state_bit_bad"] == 0 and rep["obs_not_exact"] == 0 and rep["rew_not_close"] == 0, rep
+
+
+@pytest.mark.parametrize("variant,n_agents", [(0, 0), (1, 0), (2, 0), (3, 0), (0, 3), (0, 8), (2, 1)])
+def test_rollout_bit_exact(variant, n_agents):
+    N, T, cap = 96, 130, 40
+    h = abi.Handle(variant, N, seed=11 + variant, max_episode_steps=cap, n_agents=n_agents, lib=emu_lib())
+    rep = rollout_compare(h, variant, N, T, seed=11 + variant, max_episode_steps=cap, n_agents=n_agents, nthreads=4)
+    _exact(rep)
+    assert rep["dones"] >= 3 * N          # every env was auto-reset (hidden step included) three times
+    h.close()
+
+
+def test_toi_events_are_exercised():
+    # Heavy-v0 robots hit walls often: make sure the run above style covers TOI sub-steps
+    N = 256
+    h = abi.Handle(1, N, seed=3, lib=emu_lib())
+    rep = rollout_compare(h, 1, N, 60, seed=3, nthreads=4)
+    _exact(rep)
+    assert rep["oracle_stats"]["toi_events"] > 20
+    h.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_one_step_from_identical_states(variant):
+    N = 512
+    o = OracleBatch(variant, N, seed=17, nthreads=4)
+    o.reset()
+    for t in range(30):
+        o.step(o.sample_actions(t))
+    h = abi.Handle(variant, N, seed=17, lib=emu_lib())
+    rep = single_step_compare(h, o, o.get_state(), o.sample_actions(999))
+    assert rep["flag_mismatch"] == 0 and rep["done_mismatch"] == 0 and rep["state_bit_bad"] == 0 and rep["obs_not_exact"] == 0, rep
+
+
+def test_state_roundtrip_through_abi():
+    h = abi.Handle(1, 32, seed=2, lib=emu_lib())
+    h.reset_host()
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        h.step_host(rng.uniform(-1, 1, (32, 15)).astype(np.float32))
+    w = h.get_state()
+    g = abi.Handle(1, 32, seed=2, lib=emu_lib())
+    g.set_state(w)
+    assert np.array_equal(g.get_state(), w)
+    a = rng.uniform(-1, 1, (32, 15)).astype(np.float32)
+    for x, y in zip(h.step_host(a), g.step_host(a)):
+        assert np.array_equal(x, y)
+    # partial ranges
+    assert np.array_equal(h.get_state(5, 7), h.get_state()[5:12])
+
+
+def test_reset_mask_only_touches_selected_envs():
+    h = abi.Handle(0, 8, seed=9, lib=emu_lib())
+    h.reset_host()
+    before = h.get_state()
+    mask = np.array([0, 1, 0, 0, 1, 0, 0, 0], dtype=np.uint8)
+    h.reset_host(mask)
+    after = h.get_state()
+    changed = (before != after).any(axis=1)
+    assert changed.tolist() == mask.astype(bool).tolist()
+    assert after[1, 1] == before[1, 1] + 1   # episode counter
+
+
+def test_sharding_invariance_emu():
+    a = abi.Handle(1, 24, seed=5, max_episode_steps=30, lib=emu_lib())
+    b0 = abi.Handle(1, 12, seed=5, max_episode_steps=30, env_id_base=0, lib=emu_lib())
+    b1 = abi.Handle(1, 12, seed=5, max_episode_steps=30, env_id_base=12, lib=emu_lib())
+    assert np.array_equal(a.reset_host(), np.concatenate([b0.reset_host(), b1.reset_host()]))
+    rng = np.random.default_rng(1)
+    for _ in range(70):
+        act = rng.uniform(-1, 1, (24, 15)).astype(np.float32)
+        ra, r0, r1 = a.step_host(act), b0.step_host(act[:12]), b1.step_host(act[12:])
+        for x, y0, y1 in zip(ra, r0, r1):
+            assert np.array_equal(x, np.concatenate([y0, y1]))
+
+
+def test_variant_constants_match_oracle():
+    """mass data / shapes computed by the product's host code (mrp_variant.hpp) == the oracle's Box2D restatement."""
+    for variant in range(4):
+        o = OracleBatch(variant, 1)
+        h = abi.Handle(variant, 1, lib=emu_lib(), auto_reset=False)
+        # one step from the same contact-free state must agree exactly even for the v2 robot whose local centre is
+        # a rounding residue (-9.757e-10): covered by the rollout tests; here compare obs vertex layout directly
+        oo, ho = o.reset(), h.reset_host()
+        assert np.array_equal(oo.astype(np.float32), ho)
+
+
+def test_v2_agent_limit_is_reported():
+    with pytest.raises(abi.MrpError, match="num_agents <= 2"):
+        abi.Handle(2, 4, n_agents=5, lib=emu_lib())
+
+
+def test_params_change_rewards():
+    h = abi.Handle(0, 4, seed=1, lib=emu_lib())
+    g = abi.Handle(0, 4, seed=1, lib=emu_lib())
+    h.reset_host(); g.reset_host()
+    g.set_params(agentDistance=0.0, blockDistance=0.0)
+    assert g.get_params()["agentDistance"] == 0.0 and g.get_params()["blockDelta"] == 50.0
+    a = np.zeros((4, 6), dtype=np.float32)
+    r1, r2 = h.step_host(a)[1], g.step_host(a)[1]
+    assert (r2 > r1).all()    # distance penalties removed
