@@ -59,6 +59,7 @@ MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env
     e.gsd(W_EPRET, ret);
     e.g(W_EPLEN) = len;
     e.store();
+    K.work_class[env] = (uint8_t)work_to_class(e.work);
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
     if (done) {
         stat_add(K.stats, MRP_STAT_EPISODES, 1.0);
@@ -81,6 +82,7 @@ MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env
 MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
     Env e(K, sm, ct, env);
     e.reset_env(K.obs + env * K.obs_dim);
+    K.work_class[env] = (uint8_t)work_to_class(e.work);
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
 }
 
@@ -111,9 +113,51 @@ __device__ __forceinline__ const float* load_ctab(const SimConst& K, float* smem
 __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (env >= K.N) return;
+    int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (tid >= K.N) return;
+    // heavy envs first, envs of similar predicted work share a warp (see k_sort_*)
+    int64_t env = K.perm ? (int64_t)K.perm[tid] : tid;
     step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+}
+
+// ---- lane scheduling: counting sort of envs by work class, heaviest class first -------------------
+__global__ void k_sort_clear(int32_t* hist, int32_t* reset_count) {
+    if (threadIdx.x < 2 * kWorkClasses) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0 && reset_count) *reset_count = 0;
+}
+__global__ void __launch_bounds__(256) k_sort_hist(const uint8_t* __restrict__ wc, int64_t N, int32_t* hist) {
+    __shared__ int32_t h[kWorkClasses];
+    if (threadIdx.x < kWorkClasses) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[wc[i]], 1);
+    __syncthreads();
+    if (threadIdx.x < kWorkClasses && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint8_t* __restrict__ wc, int64_t N, int32_t* hist, int32_t* perm) {
+    // class c starts after all heavier classes; blocks reserve ranges per class with one atomic per class
+    __shared__ int32_t start[kWorkClasses], h[kWorkClasses], base[kWorkClasses];
+    if (threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int c = kWorkClasses - 1; c >= 0; --c) { start[c] = acc; acc += hist[c]; }
+    }
+    if (threadIdx.x < kWorkClasses) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < N ? lo + per : N;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&h[wc[i]], 1);
+    __syncthreads();
+    if (threadIdx.x < kWorkClasses) {
+        int32_t cnt = h[threadIdx.x];
+        base[threadIdx.x] = start[threadIdx.x] + (cnt ? atomicAdd(&hist[kWorkClasses + threadIdx.x], cnt) : 0);
+        h[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int c = wc[i];
+        int32_t pos = base[c] + atomicAdd(&h[c], 1);
+        perm[pos] = (int32_t)i;
+    }
 }
 
 // reset pass over the queue the step kernel filled (auto-reset)
@@ -135,8 +179,6 @@ __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ S
     if (K.reset_mask && !K.reset_mask[env]) return;
     reset_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
-
-__global__ void k_clear_count(int32_t* p) { *p = 0; }
 
 __global__ void k_sample_actions(const __grid_constant__ SimConst K, float* dst, uint64_t step_index) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,6 +202,9 @@ struct mrp_handle {
     int device;
     float* ctab_dev;
     float* act_dev;
+    int32_t* perm_dev;
+    int perm_valid;   // perm_dev holds a permutation computed after the last step/reset
+    int sort_lanes;   // 1: schedule lanes by predicted work (default)
     int64_t launches;
     size_t smem_bytes;
     // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
@@ -237,6 +282,9 @@ int mrp_destroy(mrp_handle* h) {
     DEV_FREE(h->K.stats);
     DEV_FREE(h->K.reset_list);
     DEV_FREE(h->K.reset_count);
+    DEV_FREE(h->K.work_class);
+    DEV_FREE(h->K.hist);
+    DEV_FREE(h->perm_dev);
     delete h;
     return 0;
 }
@@ -263,6 +311,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     SimConst& K = h->K;
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
+    h->sort_lanes = getenv("MRP_NO_LANE_SORT") ? 0 : 1;
     K.seed = cfg->seed;
     K.env_id_base = cfg->env_id_base;
     K.N = cfg->num_envs;
@@ -279,6 +328,9 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
     rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC(K.reset_count, sizeof(int32_t));
+    rc |= DEV_ALLOC(K.work_class, N);
+    rc |= DEV_ALLOC(K.hist, sizeof(int32_t) * 2 * kWorkClasses);
+    rc |= DEV_ALLOC(h->perm_dev, sizeof(int32_t) * N);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
         mrp_destroy(h);
@@ -346,6 +398,7 @@ int mrp_reset(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
     cudaSetDevice(h->device);
     k_reset_mask<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, (cudaStream_t)stream>>>(K);
     h->launches += 1;
+    h->perm_valid = 0;
     return check_launch("mrp_reset");
 #else
     (void)stream;
@@ -400,7 +453,9 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (K.auto_reset) k_clear_count<<<1, 1, 0, st>>>(K.reset_count);
+    K.perm = (h->sort_lanes && h->perm_valid) ? h->perm_dev : nullptr;
+    k_sort_clear<<<1, 2 * kWorkClasses, 0, st>>>(K.hist, K.reset_count);
+    h->launches += 1;
     if (h->timing) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
@@ -410,7 +465,14 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
     h->launches += 1;
     if (K.auto_reset) {
         k_reset_list<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 1;
+    }
+    if (h->sort_lanes) {
+        const unsigned sb = (unsigned)((K.N + 8191) / 8192) < 1184u ? (unsigned)((K.N + 8191) / 8192) : 1184u;
+        k_sort_hist<<<sb, 256, 0, st>>>(K.work_class, K.N, K.hist);
+        k_sort_scatter<<<sb, 256, 0, st>>>(K.work_class, K.N, K.hist, h->perm_dev);
         h->launches += 2;
+        h->perm_valid = 1;
     }
     return check_launch("mrp_step");
 #else

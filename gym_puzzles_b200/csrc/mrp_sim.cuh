@@ -68,7 +68,17 @@ struct SimConst {
     int32_t* reset_list;
     int32_t* reset_count;
     const uint8_t* reset_mask;
+    // lane scheduling: envs are processed in order of decreasing predicted work (perm), predicted from
+    // the work class each env recorded on its previous step
+    const int32_t* perm;
+    uint8_t* work_class;
+    int32_t* hist;    // [kWorkClasses] histogram, then [kWorkClasses] scatter cursors
 };
+constexpr int kWorkClasses = 64;
+MRP_HD int work_to_class(uint32_t w) {
+    int c = w < 64u ? (int)(w >> 2) : 16 + (int)((w - 64u) >> 4);
+    return c > kWorkClasses - 1 ? kWorkClasses - 1 : c;
+}
 
 // ---- solver constraint record (per touching contact, in island order) --------------
 constexpr int VC_META = 0;   // bA | bB<<4 | vpc<<8 | ppc<<10 | type<<12 | island<<16 | slot<<24
@@ -95,9 +105,10 @@ struct Sim {
     int nc;
     uint32_t goalc;
     uint32_t overflow;
+    uint32_t work;  // estimate of this env's divergent work this step (drives next step's lane scheduling)
 
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env)
-        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), nc(0), goalc(0), overflow(0) {}
+        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), nc(0), goalc(0), overflow(0), work(0) {}
 
     // ------------------------------------------------------------ memory helpers
     MRP_HD uint32_t& g(int w) { return G[(int64_t)w * N]; }
@@ -580,8 +591,10 @@ struct Sim {
     // identical no-op, so the result equals the full 180 bit for bit)
     MRP_HD void solve_velocity(int T, int iters) {
         if (T == 0) return;
-        for (int it = 0; it < iters; ++it)
+        int it = 0;
+        for (; it < iters; ++it)
             if (!solve_velocity_sweep(T)) break;
+        work += (uint32_t)((it + 1) * T);
     }
     MRP_HD void store_impulses(int T) {
         for (int t = 0; t < T; ++t) {
@@ -725,6 +738,7 @@ struct Sim {
             uint32_t done = 0;
             for (int it = 0; it < 60; ++it) {
                 uint32_t bad = solve_position_sweep(T, done, -1, -1);
+                work += 2u * (uint32_t)T;
                 done = ~bad;
                 if (!bad) break;
             }
@@ -892,6 +906,7 @@ struct Sim {
                         sweep_advance(bB, al0);
                     }
                     float t;
+                    work += 6u;
                     int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
                     if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
                     else alpha = 1.0f;
@@ -901,6 +916,7 @@ struct Sim {
                 if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
             }
             if (minK < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
+            work += 100u;
             toi_event(minK, minAlpha, toiFlag, enabled);
         }
     }
@@ -908,6 +924,7 @@ struct Sim {
     // ------------------------------------------------------------ b2World::Step (A.6)
     MRP_HD void world_step(bool new_fixtures) {
         if (new_fixtures) find_new_contacts(0xffffffffu);
+        work += 8u * (uint32_t)nc;
         collide();
         // xf1 of SynchronizeFixtures == the transform the step started with (c0, a0 are set from c, a)
         for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
