@@ -38,15 +38,8 @@ MRP_HD void stat_add(double* stats, int slot, double v) {
 #endif
 }
 
-// one env.step incl. TimeLimit; done envs are queued for the reset pass
-MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    Env e(K, sm, ct, env);
-    e.load();
-    float a[3 * MRP_MAX_AGENTS];
-    const float* arow = K.act + env * K.act_dim;
-    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
-    double r;
-    bool d = e.env_step(a, K.obs + env * K.obs_dim, &r, false);
+// TimeLimit, episode accounting, auto-reset queue: the tail of every env.step
+MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r) {
     uint32_t elapsed = e.g(W_ELAPSED) + 1u;
     e.g(W_ELAPSED) = elapsed;
     bool limit = (int)elapsed >= K.max_steps;
@@ -59,7 +52,6 @@ MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env
     e.gsd(W_EPRET, ret);
     e.g(W_EPLEN) = len;
     e.store();
-    K.work_class[env] = (uint8_t)work_to_class(e.work);
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
     if (done) {
         stat_add(K.stats, MRP_STAT_EPISODES, 1.0);
@@ -68,21 +60,100 @@ MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env
         stat_add(K.stats, MRP_STAT_SUM_RETURN, ret);
         stat_add(K.stats, MRP_STAT_SUM_RETURN_SQ, ret * ret);
         stat_add(K.stats, MRP_STAT_SUM_LENGTH, (double)len);
-        if (K.auto_reset) {
-#if defined(__CUDA_ARCH__)
-            int slot = atomicAdd(K.reset_count, 1);
-#else
-            int slot = (*K.reset_count)++;
-#endif
-            K.reset_list[slot] = (int32_t)env;
-        }
+        if (K.auto_reset) K.reset_list[atomic_add_i32(&K.cnt[CNT_RESET], 1)] = (int32_t)env;
     }
 }
 
+// phase 1 (lane per env): control + Collide + island order + constraint setup -> solver task
+MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+    Env e(K, sm, ct, env, nullptr);
+    e.load();
+    float a[3 * MRP_MAX_AGENTS];
+    const float* arow = K.act + env * K.act_dim;
+    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+    e.pre_phase(a);
+}
+
+// phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
+struct VelTask {
+    Sim::VelState st;
+    int T;
+};
+MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
+    const int64_t env = K.task_env[task];
+    vt.T = K.task_T[task];
+    s.G = K.S + env;
+    s.vcp = K.pool + K.task_off[task];
+    for (int b = 0; b < K.nb; ++b)
+        for (int f = 0; f < 6; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
+    for (int b = K.nb; b < K.nb + 4; ++b) { s.B(b, 3) = 0.0f; s.B(b, 4) = 0.0f; s.B(b, 5) = 0.0f; }
+    s.vel_begin(vt.st);
+}
+MRP_HD void vel_task_end(const SimConst& K, Sim& s, VelTask& vt) {
+    s.store_impulses(vt.T);
+    for (int b = 0; b < K.nb; ++b) {
+        s.integrate_position(b, K.h);
+        for (int f = 0; f < 6; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
+    }
+}
+// phase 2b (lane per task): up to 60 position sweeps
+struct PosTask {
+    Sim::PosState st;
+    int T;
+};
+MRP_HD void pos_task_begin(const SimConst& K, Sim& s, PosTask& pt, int task) {
+    const int64_t env = K.task_env[task];
+    pt.T = K.task_T[task];
+    s.G = K.S + env;
+    s.vcp = K.pool + K.task_off[task];
+    const float nan = s.__uint_as_float_(0x7fc00000u);
+    for (int b = 0; b < K.nb; ++b) {
+        for (int f = 0; f < 3; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
+        s.set_rot_cache(b, Rot{0.0f, 1.0f}, nan);  // no rotation known for the freshly integrated angle
+    }
+    for (int k = 0; k < 4; ++k) {
+        s.B(K.nb + k, 0) = K.ctab[CT_WALLPOS + 2 * k];
+        s.B(K.nb + k, 1) = K.ctab[CT_WALLPOS + 2 * k + 1];
+        s.B(K.nb + k, 2) = 0.0f;
+    }
+    s.pos_begin(pt.st);
+}
+MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
+    for (int b = 0; b < K.nb; ++b)
+        for (int f = 0; f < 3; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
+}
+
+// phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
+// false an env whose TOI scan finds an event is queued for the event pass and left untouched.
+MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local) {
+    Env e(K, sm, ct, env, vc_local);
+    e.load();
+    double r;
+    bool d;
+    if (!e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events)) {
+        K.toi_list[atomic_add_i32(&K.cnt[CNT_TOI], 1)] = (int32_t)env;
+        return;
+    }
+    finish_step(K, e, env, d, r);
+}
+
+// fused single-lane step (used by the host emulation's reference path and kept for debugging)
+MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+    float vc_local[kMaxC * VC_WORDS];
+    Env e(K, sm, ct, env, vc_local);
+    e.load();
+    float a[3 * MRP_MAX_AGENTS];
+    const float* arow = K.act + env * K.act_dim;
+    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+    double r;
+    bool d = e.env_step(a, K.obs + env * K.obs_dim, &r, false);
+    finish_step(K, e, env, d, r);
+}
+
 MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    Env e(K, sm, ct, env);
+    float vc_local[kMaxC * VC_WORDS];
+    Env e(K, sm, ct, env, vc_local);
     e.reset_env(K.obs + env * K.obs_dim);
-    K.work_class[env] = (uint8_t)work_to_class(e.work);
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
 }
 
@@ -96,10 +167,10 @@ MRP_HD void fix_rot_lane(const SimConst& K, int64_t env) {  // q = Rot(a) after 
     for (int b = 0; b < K.nb; ++b) {
         uint32_t* G = K.S + env;
         union { uint32_t u; float f; } c;
-        c.u = G[(int64_t)(K.w_body + 8 * b + 2) * K.N];
+        c.u = G[(int64_t)(K.w_body + kBodyWords * b + 2) * K.N];
         Rot q = rot_set(c.f);
-        c.f = q.s; G[(int64_t)(K.w_body + 8 * b + 6) * K.N] = c.u;
-        c.f = q.c; G[(int64_t)(K.w_body + 8 * b + 7) * K.N] = c.u;
+        c.f = q.s; G[(int64_t)(K.w_body + kBodyWords * b + 6) * K.N] = c.u;
+        c.f = q.c; G[(int64_t)(K.w_body + kBodyWords * b + 7) * K.N] = c.u;
     }
 }
 
@@ -110,65 +181,105 @@ __device__ __forceinline__ const float* load_ctab(const SimConst& K, float* smem
     return smem;
 }
 
+__global__ void k_clear(int32_t* cnt) {
+    if (threadIdx.x < CNT_N) cnt[threadIdx.x] = 0;
+}
+
+// fused single-kernel step (MRP_FUSED_STEP=1): kept for A/B measurements against the phase pipeline
 __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (tid >= K.N) return;
-    // heavy envs first, envs of similar predicted work share a warp (see k_sort_*)
-    int64_t env = K.perm ? (int64_t)K.perm[tid] : tid;
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
     step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
 
-// ---- lane scheduling: counting sort of envs by work class, heaviest class first -------------------
-__global__ void k_sort_clear(int32_t* hist, int32_t* reset_count) {
-    if (threadIdx.x < 2 * kWorkClasses) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0 && reset_count) *reset_count = 0;
+__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
+    pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
-__global__ void __launch_bounds__(256) k_sort_hist(const uint8_t* __restrict__ wc, int64_t N, int32_t* hist) {
-    __shared__ int32_t h[kWorkClasses];
-    if (threadIdx.x < kWorkClasses) h[threadIdx.x] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[wc[i]], 1);
-    __syncthreads();
-    if (threadIdx.x < kWorkClasses && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
-}
-__global__ void __launch_bounds__(256) k_sort_scatter(const uint8_t* __restrict__ wc, int64_t N, int32_t* hist, int32_t* perm) {
-    // class c starts after all heavier classes; blocks reserve ranges per class with one atomic per class
-    __shared__ int32_t start[kWorkClasses], h[kWorkClasses], base[kWorkClasses];
-    if (threadIdx.x == 0) {
-        int32_t acc = 0;
-        for (int c = kWorkClasses - 1; c >= 0; --c) { start[c] = acc; acc += hist[c]; }
-    }
-    if (threadIdx.x < kWorkClasses) h[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < N ? lo + per : N;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&h[wc[i]], 1);
-    __syncthreads();
-    if (threadIdx.x < kWorkClasses) {
-        int32_t cnt = h[threadIdx.x];
-        base[threadIdx.x] = start[threadIdx.x] + (cnt ? atomicAdd(&hist[kWorkClasses + threadIdx.x], cnt) : 0);
-        h[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        int c = wc[i];
-        int32_t pos = base[c] + atomicAdd(&h[c], 1);
-        perm[pos] = (int32_t)i;
+
+// Persistent solver kernels.  Every lane owns one task at a time and advances it by one point operation per loop
+// trip; a warp refills its idle lanes from the global task queue once kRefill of them are idle, so the 32 lanes
+// stay busy although islands need anywhere between 2 and ~1000 operations.
+constexpr int kRefill = 8;
+
+__global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
+    const int ntasks = K.cnt[CNT_TASKS];
+    VelTask vt;
+    bool busy = false, exhausted = false;
+    for (;;) {
+        const unsigned bm = __ballot_sync(0xffffffffu, busy);
+        if (32 - __popc(bm) >= kRefill || bm == 0u) {
+            if (!busy && !exhausted) {
+                const int task = atomicAdd(&K.cnt[CNT_HEAD_V], 1);
+                if (task < ntasks) { vel_task_begin(K, s, vt, task); busy = true; }
+                else exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        }
+        if (busy && s.vel_trip(vt.st, vt.T, 180)) {
+            vel_task_end(K, s, vt);
+            busy = false;
+        }
     }
 }
 
-// reset pass over the queue the step kernel filled (auto-reset)
-__global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K) {
+__global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
-    int count = *K.reset_count;
+    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 9);
+    const int ntasks = K.cnt[CNT_TASKS];
+    PosTask pt;
+    bool busy = false, exhausted = false;
+    for (;;) {
+        const unsigned bm = __ballot_sync(0xffffffffu, busy);
+        if (32 - __popc(bm) >= kRefill || bm == 0u) {
+            if (!busy && !exhausted) {
+                const int task = atomicAdd(&K.cnt[CNT_HEAD_P], 1);
+                if (task < ntasks) { pos_task_begin(K, s, pt, task); busy = true; }
+                else exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        }
+        if (busy && s.pos_trip(pt.st, pt.T, 60, -1, -1)) {
+            pos_task_end(K, s, pt);
+            busy = false;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_post(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
+    post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr);
+}
+
+// rare paths, grid-stride over their queues: envs with a TOI event this step; envs to auto-reset
+__global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const int count = K.cnt[CNT_TOI];
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
-    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= count) return;
-    reset_lane(K, smem + kCtPad + threadIdx.x, ct, K.reset_list[i]);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock) {
+        float vc_local[kMaxC * VC_WORDS];
+        post_lane(K, smem + kCtPad + threadIdx.x, ct, K.toi_list[i], true, vc_local);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const int count = K.cnt[CNT_RESET];
+    if ((int64_t)blockIdx.x * kBlock >= count) return;
+    const float* ct = load_ctab(K, smem);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock)
+        reset_lane(K, smem + kCtPad + threadIdx.x, ct, K.reset_list[i]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ SimConst K) {
@@ -202,9 +313,8 @@ struct mrp_handle {
     int device;
     float* ctab_dev;
     float* act_dev;
-    int32_t* perm_dev;
-    int perm_valid;   // perm_dev holds a permutation computed after the last step/reset
-    int sort_lanes;   // 1: schedule lanes by predicted work (default)
+    int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
+    size_t smem_vel, smem_pos;
     int64_t launches;
     size_t smem_bytes;
     // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
@@ -228,6 +338,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 
 #ifdef MRP_HOST_EMU
 #define DEV_ALLOC(ptr, bytes) ((*(void**)&(ptr) = calloc(1, (bytes))) ? 0 : -1)
+#define DEV_ALLOC_RAW(ptr, bytes) ((*(void**)&(ptr) = malloc((bytes))) ? 0 : -1)
 #define DEV_FREE(ptr) free(ptr)
 #define H2D(dst, src, bytes) (memcpy((dst), (src), (bytes)), 0)
 #define D2H(dst, src, bytes) (memcpy((dst), (src), (bytes)), 0)
@@ -235,6 +346,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 static const char* dev_err() { return "host allocation failed"; }
 #else
 #define DEV_ALLOC(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess ? (cudaMemset((ptr), 0, (bytes)), 0) : -1)
+#define DEV_ALLOC_RAW(ptr, bytes) (cudaMalloc((void**)&(ptr), (bytes)) == cudaSuccess ? 0 : -1)
 #define DEV_FREE(ptr) cudaFree(ptr)
 #define H2D(dst, src, bytes) (cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1)
 #define D2H(dst, src, bytes) (cudaMemcpy((dst), (src), (bytes), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1)
@@ -281,10 +393,12 @@ int mrp_destroy(mrp_handle* h) {
     DEV_FREE(h->K.trunc);
     DEV_FREE(h->K.stats);
     DEV_FREE(h->K.reset_list);
-    DEV_FREE(h->K.reset_count);
-    DEV_FREE(h->K.work_class);
-    DEV_FREE(h->K.hist);
-    DEV_FREE(h->perm_dev);
+    DEV_FREE(h->K.cnt);
+    DEV_FREE(h->K.pool);
+    DEV_FREE(h->K.task_env);
+    DEV_FREE(h->K.task_T);
+    DEV_FREE(h->K.task_off);
+    DEV_FREE(h->K.toi_list);
     delete h;
     return 0;
 }
@@ -311,7 +425,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     SimConst& K = h->K;
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
-    h->sort_lanes = getenv("MRP_NO_LANE_SORT") ? 0 : 1;
+    h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
     K.seed = cfg->seed;
     K.env_id_base = cfg->env_id_base;
     K.N = cfg->num_envs;
@@ -327,10 +441,13 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.trunc, N);
     rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
     rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.reset_count, sizeof(int32_t));
-    rc |= DEV_ALLOC(K.work_class, N);
-    rc |= DEV_ALLOC(K.hist, sizeof(int32_t) * 2 * kWorkClasses);
-    rc |= DEV_ALLOC(h->perm_dev, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * CNT_N);
+    // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
+    rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
+    rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
         mrp_destroy(h);
@@ -354,9 +471,13 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
         free(row);
     }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
+    h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
+    h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
 #ifndef MRP_HOST_EMU
-    cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-    cudaFuncSetAttribute(k_reset_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    for (auto fn : {k_step, k_pre, k_post, k_post_events, k_reset_list})
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
+    cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
     cudaFuncSetAttribute(k_reset_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (check_launch("mrp_create")) { mrp_destroy(h); return -10; }
 #else
@@ -398,7 +519,6 @@ int mrp_reset(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
     cudaSetDevice(h->device);
     k_reset_mask<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, (cudaStream_t)stream>>>(K);
     h->launches += 1;
-    h->perm_valid = 0;
     return check_launch("mrp_reset");
 #else
     (void)stream;
@@ -453,33 +573,65 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    K.perm = (h->sort_lanes && h->perm_valid) ? h->perm_dev : nullptr;
-    k_sort_clear<<<1, 2 * kWorkClasses, 0, st>>>(K.hist, K.reset_count);
-    h->launches += 1;
+    const unsigned grid = grid_for(K.N, kBlock);
+    // persistent / queue kernels: a few CTAs per SM
+    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+    k_clear<<<1, 32, 0, st>>>(K.cnt);
     if (h->timing) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
     }
-    k_step<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
-    if (h->timing) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
-    h->launches += 1;
-    if (K.auto_reset) {
-        k_reset_list<<<grid_for(K.N, kBlock), kBlock, h->smem_bytes, st>>>(K);
-        h->launches += 1;
-    }
-    if (h->sort_lanes) {
-        const unsigned sb = (unsigned)((K.N + 8191) / 8192) < 1184u ? (unsigned)((K.N + 8191) / 8192) : 1184u;
-        k_sort_hist<<<sb, 256, 0, st>>>(K.work_class, K.N, K.hist);
-        k_sort_scatter<<<sb, 256, 0, st>>>(K.work_class, K.N, K.hist, h->perm_dev);
+    if (h->fused) {
+        k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 2;
-        h->perm_valid = 1;
+    } else {
+        k_pre<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_solve_vel<<<pgrid, kBlock, h->smem_vel, st>>>(K);
+        k_solve_pos<<<pgrid, kBlock, h->smem_pos, st>>>(K);
+        k_post<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 6;
+    }
+    if (h->timing) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+    if (K.auto_reset) {
+        k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 1;
     }
     return check_launch("mrp_step");
 #else
     (void)stream;
-    *K.reset_count = 0;
-    for (int64_t e = 0; e < K.N; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
-    for (int i = 0; i < *K.reset_count; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+    for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
+    if (h->fused) {
+        for (int64_t e = 0; e < K.N; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
+    } else {
+        // the same phases the device runs as kernels, executed as loops
+        for (int64_t e = 0; e < K.N; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
+        const int ntasks = K.cnt[CNT_TASKS];
+        for (int i = 0; i < ntasks; ++i) {
+            Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
+            VelTask vt;
+            vel_task_begin(K, s, vt, i);
+            while (!s.vel_trip(vt.st, vt.T, 180)) {}
+            vel_task_end(K, s, vt);
+        }
+        for (int i = 0; i < ntasks; ++i) {
+            Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
+            PosTask pt;
+            pos_task_begin(K, s, pt, i);
+            while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
+            pos_task_end(K, s, pt);
+        }
+        for (int64_t e = 0; e < K.N; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
+        const int ntoi = K.cnt[CNT_TOI];
+        for (int i = 0; i < ntoi; ++i) {
+            float vc_local[kMaxC * VC_WORDS];
+            post_lane(K, h->emu_sm, h->ctab_dev, K.toi_list[i], true, vc_local);
+        }
+    }
+    if (K.auto_reset) {
+        const int nreset = K.cnt[CNT_RESET];
+        for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+    }
     return 0;
 #endif
 }
@@ -596,7 +748,7 @@ int mrp_get_state(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t*
         uint32_t gc = I(W_GOALC, e);
         for (int i = 0; i < K.n; ++i) o[L.off_goal_contact + i] = (gc >> i) & 1u;
         for (int b = 0; b < K.nb; ++b)
-            for (int f = 0; f < 6; ++f) o[L.off_bodies + 6 * b + f] = I(K.w_body + 8 * b + f, e);
+            for (int f = 0; f < 6; ++f) o[L.off_bodies + 6 * b + f] = I(K.w_body + kBodyWords * b + f, e);
         for (int i = 0; i < 2 * (K.n + 1); ++i) o[L.off_dists + i] = I(W_DIST + i, e);
         for (int i = 0; i < 4; ++i) o[L.off_goal + i] = I(W_GOAL + i, e);
         o[L.off_episode_acc] = I(W_EPRET, e); o[L.off_episode_acc + 1] = I(W_EPRET + 1, e);
@@ -638,7 +790,7 @@ int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uin
         for (int i = 0; i < K.n; ++i) gc |= (o[L.off_goal_contact + i] ? 1u : 0u) << i;
         I(W_GOALC, e) = gc;
         for (int b = 0; b < K.nb; ++b)
-            for (int f = 0; f < 6; ++f) I(K.w_body + 8 * b + f, e) = o[L.off_bodies + 6 * b + f];
+            for (int f = 0; f < 6; ++f) I(K.w_body + kBodyWords * b + f, e) = o[L.off_bodies + 6 * b + f];
         for (int i = 0; i < 2 * (K.n + 1); ++i) I(W_DIST + i, e) = o[L.off_dists + i];
         for (int i = 0; i < 4; ++i) I(W_GOAL + i, e) = o[L.off_goal + i];
         I(W_EPRET, e) = o[L.off_episode_acc]; I(W_EPRET + 1, e) = o[L.off_episode_acc + 1];

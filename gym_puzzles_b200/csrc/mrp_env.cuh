@@ -23,7 +23,8 @@ constexpr double kTwoPiD = 2.0 * 3.141592653589793;
 constexpr double kPiD = 3.141592653589793;
 
 struct Env : Sim {
-    MRP_HD Env(const SimConst& k, float* sm_, const float* ct_, int64_t env) : Sim(k, sm_, ct_, env) {}
+    MRP_HD Env(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
+        : Sim(k, sm_, ct_, env, vc_, fdyn_) {}
 
     // b2Island::Solve's velocity integration + damping (A.8) for body b with accumulated force/torque.
     // Nothing between the control block and the island solve reads velocities, so doing it here is
@@ -283,6 +284,7 @@ struct Env : Sim {
             B(b, 0) = c.x; B(b, 1) = c.y; B(b, 2) = ang;
             B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
             BX(b, 9) = xf.q.s; BX(b, 10) = xf.q.c; BX(b, 11) = px; BX(b, 12) = py;
+            set_rot_cache(b, xf.q, ang);
             // proxies: fat AABB = tight AABB at creation +- 0.1 (b2DynamicTree::CreateProxy)
             int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
             int f1 = b == 0 ? 2 : f0 + K.per_agent;
@@ -321,6 +323,52 @@ struct Env : Sim {
             for (int i = 0; i < K.n; ++i)
                 gsd(W_DIST + 2 * i, py_distance((double)B(1 + i, 0) * K.ratio, (double)B(1 + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio));
         }
+    }
+
+    // ---------------------------------------------------------------- phase pipeline (one env.step split at the solver)
+    // k_pre: control, Collide, island order; envs with touching contacts become solver tasks, the others
+    // integrate their positions right away.  Returns T.
+    MRP_HD int pre_phase(const float* a) {
+        if (K.v2) control_v2(a); else control_v0(a);
+        collide();
+        for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+        uint8_t island_of[kMaxC];
+        const int T = build_islands(island_of);
+        if (T > 0) {
+            const int off = atomic_add_i32(&K.cnt[CNT_POOL], T * VC_WORDS);
+            const int task = atomic_add_i32(&K.cnt[CNT_TASKS], 1);
+            K.task_env[task] = (int32_t)(G - K.S);
+            K.task_T[task] = T;
+            K.task_off[task] = off;
+            vcp = K.pool + off;
+            init_constraints(T, island_of, true);
+            warm_start(T);
+        } else {
+            for (int b = 0; b < K.nb; ++b) integrate_position(b, K.h);
+        }
+        // hand-off to the solver / post kernels: poses + velocities, pre-step pose, contact list
+        g(W_NC) = (uint32_t)nc;
+        g(W_GOALC) = goalc;
+        for (int b = 0; b < K.nb; ++b) {
+            const int w = K.w_body + kBodyWords * b;
+            for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
+            gsf(w + 8, BX(b, 6)); gsf(w + 9, BX(b, 7)); gsf(w + 10, BX(b, 8));
+        }
+        for (int k = 0; k < nc; ++k) g(cw(k, 0)) = meta[k];
+        return T;
+    }
+    // k_post: the step after the solver — transforms, broadphase, TOI, obs / reward / done.
+    // Returns false (nothing stored) when a TOI event is needed and allow_events is false.
+    MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events) {
+        // load(): q/p are still the pre-step transform; c0/a0 from the hand-off words
+        for (int b = 0; b < K.nb; ++b) {
+            const int w = K.w_body + kBodyWords * b;
+            BX(b, 6) = gf(w + 8); BX(b, 7) = gf(w + 9); BX(b, 8) = gf(w + 10);
+            set_rot_cache(b, Rot{BX(b, 9), BX(b, 10)}, BX(b, 8));
+        }
+        if (!post_solve(allow_events)) return false;
+        *done_env = post_step(obs, reward);
+        return true;
     }
 
     // env.reset(): respawn + hidden step with a sampled action (mrp00:411 / mrp02:442)

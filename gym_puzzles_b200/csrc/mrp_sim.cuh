@@ -36,7 +36,9 @@ constexpr int W_ELAPSED = 0, W_EPISODE = 1, W_INPLACE = 2, W_NC = 3, W_GOALC = 4
 constexpr int W_EPRET = 6;   // f64
 constexpr int W_GOAL = 8;    // 2 x f64
 constexpr int W_DIST = 12;   // (n+1) x f64: agent_dist[0..n-1], block_dist
-// then bodies[nb][8] = {cx, cy, a, vx, vy, w, q.s, q.c}; fat[ndynfix][4]; contacts[maxc][14]
+// then bodies[nb][11] = {cx, cy, a, vx, vy, w, q.s, q.c, c0x, c0y, a0} (c0/a0: pose at the start of the step, written by
+// k_pre for k_post's SynchronizeFixtures); fat[ndynfix][4]; contacts[maxc][14]
+constexpr int kBodyWords = 11;
 
 struct SimConst {
     // variant
@@ -66,18 +68,25 @@ struct SimConst {
     uint8_t* trunc;
     double* stats;
     int32_t* reset_list;
-    int32_t* reset_count;
     const uint8_t* reset_mask;
-    // lane scheduling: envs are processed in order of decreasing predicted work (perm), predicted from
-    // the work class each env recorded on its previous step
-    const int32_t* perm;
-    uint8_t* work_class;
-    int32_t* hist;    // [kWorkClasses] histogram, then [kWorkClasses] scatter cursors
+    // phase pipeline (DESIGN.md "kernels"): solver tasks produced by k_pre, consumed by k_solve_vel / k_solve_pos
+    float* pool;          // constraint records, VC_WORDS floats each, allocated per task with one atomic
+    int32_t* cnt;         // [CNT_*] counters, zeroed at the start of every step
+    int32_t* task_env;    // [N] env of task i
+    int32_t* task_T;      // [N] number of constraints of task i
+    int32_t* task_off;    // [N] offset of task i's records in pool (floats)
+    int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
 };
-constexpr int kWorkClasses = 64;
-MRP_HD int work_to_class(uint32_t w) {
-    int c = w < 64u ? (int)(w >> 2) : 16 + (int)((w - 64u) >> 4);
-    return c > kWorkClasses - 1 ? kWorkClasses - 1 : c;
+enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_N = 8 };
+
+MRP_HD int atomic_add_i32(int32_t* p, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    int o = *p;
+    *p = o + v;
+    return o;
+#endif
 }
 
 // ---- solver constraint record (per touching contact, in island order) --------------
@@ -86,18 +95,22 @@ constexpr int VC_FRIC = 1, VC_NX = 2, VC_NY = 3;
 constexpr int VC_PT = 4;     // [2][8]: rAx rAy rBx rBy nMass tMass nI tI
 constexpr int VC_K11 = 20, VC_K12 = 21, VC_K22 = 22, VC_M11 = 23, VC_M12 = 24, VC_M22 = 25;
 constexpr int VC_LNX = 26, VC_LNY = 27, VC_LPX = 28, VC_LPY = 29, VC_LP0X = 30, VC_LP0Y = 31, VC_LP1X = 32, VC_LP1Y = 33;
-constexpr int VC_WORDS = 34;
+constexpr int VC_MA = 34, VC_IA = 35, VC_MB = 36, VC_IB = 37;  // invMassA invIA invMassB invIB
+constexpr int VC_WORDS = 38;
+
+constexpr int kDynFields = 17;  // per-lane shared-memory words of a dynamic body in the per-env kernels
 
 struct Sim {
     const SimConst& K;
     float* sm;          // this lane's shared-memory column
     const float* ct;    // CTA constant table (shared memory)
-    uint32_t* G;        // &S[env]
+    uint32_t* G;        // &S[env] (re-pointed per task in the solver kernels)
     int64_t N;
     uint64_t gid;
     // per-lane scratch (local memory where dynamically indexed)
     uint32_t meta[kMaxC];  // fa | fb<<8 | touching<<16 | type<<17 | pc<<18 | bA<<20 | bB<<24
-    float vc[kMaxC * VC_WORDS];
+    float* vcp;            // solver constraint records: a lane-local array (fused path) or a slot of the HBM task pool
+    int fdyn;              // shared-memory words per dynamic body (17 in the per-env kernels, 6 in the solver kernels)
     uint8_t order[kMaxC];
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
@@ -105,10 +118,10 @@ struct Sim {
     int nc;
     uint32_t goalc;
     uint32_t overflow;
-    uint32_t work;  // estimate of this env's divergent work this step (drives next step's lane scheduling)
 
-    MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env)
-        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), nc(0), goalc(0), overflow(0), work(0) {}
+    MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
+        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_), nc(0), goalc(0),
+          overflow(0) {}
 
     // ------------------------------------------------------------ memory helpers
     MRP_HD uint32_t& g(int w) { return G[(int64_t)w * N]; }
@@ -129,10 +142,30 @@ struct Sim {
     static MRP_HD uint64_t __double_as_ull_(double f) { union { uint64_t u; double f; } c; c.f = f; return c.u; }
     MRP_HD int cw(int k, int j) const { return K.w_con + k * MRP_CONTACT_WORDS + j; }
 
-    // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 c0x 7 c0y 8 a0 9 qs 10 qc 11 px 12 py 13 alpha0 (dynamic)
-    MRP_HD float& B(int b, int f) { return sm[(f * (K.nb + 4) + b) * MRP_SS]; }
-    MRP_HD float& BX(int b, int f) { return sm[(6 * (K.nb + 4) + (f - 6) * K.nb + b) * MRP_SS]; }
-    MRP_HD float& FA(int fx, int j) { return sm[(6 * (K.nb + 4) + 8 * K.nb + fx * 4 + j) * MRP_SS]; }
+    // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 c0x 7 c0y 8 a0 9 qs 10 qc 11 px 12 py 13 alpha0
+    // 14 cache.s 15 cache.c 16 cache angle (dynamic bodies): last Rot evaluated for this body and the angle it belongs to
+    // body-major, lane-strided: one base computation per body, then compile-time field offsets
+    MRP_HD float* bp(int b) { return sm + (b < K.nb ? b * fdyn : K.nb * fdyn + (b - K.nb) * 6) * MRP_SS; }
+    MRP_HD float& B(int b, int f) { return bp(b)[f * MRP_SS]; }
+    MRP_HD float& BX(int b, int f) { return bp(b)[f * MRP_SS]; }
+    MRP_HD float& FA(int fx, int j) { return sm[(K.nb * kDynFields + 24 + fx * 4 + j) * MRP_SS]; }
+
+    // b2Rot::Set(angle of body b) through a one-entry cache: sin/cos are pure functions of the float angle, so
+    // reusing the last evaluation when the angle is bit-identical cannot change results (robots with invI = 0
+    // never rotate inside the position solver; the block only when an impulse acts on it)
+    MRP_HD void set_rot_cache(int b, Rot q, float angle) {
+        float* const c = bp(b) + (fdyn - 3) * MRP_SS;
+        c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
+    }
+    MRP_HD Rot body_rot(int b, float angle) {
+        Rot q;
+        if (b >= K.nb) { q.s = 0.0f; q.c = 1.0f; return q; }
+        float* const c = bp(b) + (fdyn - 3) * MRP_SS;  // the last three words of the body slot
+        if (c[2 * MRP_SS] == angle) { q.s = c[0]; q.c = c[MRP_SS]; return q; }
+        q = rot_set(angle);
+        c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
+        return q;
+    }
 
     MRP_HD bool is_dyn(int b) const { return b < K.nb; }
     MRP_HD float invMass(int b) const { return b == 0 ? K.blk_invMass : (b < K.nb ? K.ag_invMass : 0.0f); }
@@ -154,7 +187,7 @@ struct Sim {
         return x;
     }
     MRP_HD void sync_transform(int b) {  // b2Body::SynchronizeTransform
-        Rot q = rot_set(B(b, 2));
+        Rot q = body_rot(b, B(b, 2));
         V2 r = rmul(q, localCenter(b));
         BX(b, 9) = q.s;
         BX(b, 10) = q.c;
@@ -180,10 +213,11 @@ struct Sim {
         nc = (int)g(W_NC);
         goalc = g(W_GOALC);
         for (int b = 0; b < K.nb; ++b) {
-            int w = K.w_body + 8 * b;
+            int w = K.w_body + kBodyWords * b;
             for (int f = 0; f < 6; ++f) B(b, f) = gf(w + f);
             BX(b, 9) = gf(w + 6);
             BX(b, 10) = gf(w + 7);
+            set_rot_cache(b, Rot{BX(b, 9), BX(b, 10)}, B(b, 2));
             V2 r = rmul(Rot{BX(b, 9), BX(b, 10)}, localCenter(b));
             BX(b, 11) = B(b, 0) - r.x;
             BX(b, 12) = B(b, 1) - r.y;
@@ -202,7 +236,7 @@ struct Sim {
         g(W_NC) = (uint32_t)nc;
         g(W_GOALC) = goalc;
         for (int b = 0; b < K.nb; ++b) {
-            int w = K.w_body + 8 * b;
+            int w = K.w_body + kBodyWords * b;
             for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
             gsf(w + 6, BX(b, 9));
             gsf(w + 7, BX(b, 10));
@@ -369,8 +403,8 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ contact solver (A.8)
-    MRP_HD float& V(int t, int w) { return vc[t * VC_WORDS + w]; }
-    MRP_HD uint32_t vmeta(int t) { return __float_as_uint_(vc[t * VC_WORDS + VC_META]); }
+    MRP_HD float& V(int t, int w) { return vcp[t * VC_WORDS + w]; }
+    MRP_HD uint32_t vmeta(int t) { return __float_as_uint_(vcp[t * VC_WORDS + VC_META]); }
 
     // b2ContactSolver ctor + InitializeVelocityConstraints for constraints [0, T)
     MRP_HD void init_constraints(int T, const uint8_t* island_of, bool warm) {
@@ -401,8 +435,8 @@ struct Sim {
             V2 vA = mk(B(bA, 3), B(bA, 4)), vB = mk(B(bB, 3), B(bB, 4));
             float wA = B(bA, 5), wB = B(bB, 5);
             Xf xfA, xfB;
-            xfA.q = is_dyn(bA) ? rot_set(B(bA, 2)) : Rot{0.0f, 1.0f};
-            xfB.q = is_dyn(bB) ? rot_set(B(bB, 2)) : Rot{0.0f, 1.0f};
+            xfA.q = body_rot(bA, B(bA, 2));
+            xfB.q = body_rot(bB, B(bB, 2));
             xfA.p = cA - rmul(xfA.q, localCenter(bA));
             xfB.p = cB - rmul(xfB.q, localCenter(bB));
             // b2WorldManifold::Initialize
@@ -428,6 +462,7 @@ struct Sim {
                 normal = -normal;
             }
             V(t, VC_NX) = normal.x; V(t, VC_NY) = normal.y;
+            V(t, VC_MA) = mA; V(t, VC_IA) = iA; V(t, VC_MB) = mB; V(t, VC_IB) = iB;
             int vpc = pc;
             V2 tangent = crossVS(normal, 1.0f);
             V2 rAj[2], rBj[2];
@@ -494,67 +529,80 @@ struct Sim {
         }
     }
 
-    // one b2ContactSolver::SolveVelocityConstraints sweep; returns true if anything changed
-    MRP_HD bool solve_velocity_sweep(int T) {
-        bool changed = false;
-        for (int t = 0; t < T; ++t) {
-            uint32_t vm = vmeta(t);
-            int bA = vm & 15, bB = (vm >> 4) & 15, vpc = (vm >> 8) & 3;
-            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
-            V2 vA = mk(B(bA, 3), B(bA, 4)), vB = mk(B(bB, 3), B(bB, 4));
-            float wA = B(bA, 5), wB = B(bB, 5);
-            V2 normal = mk(V(t, VC_NX), V(t, VC_NY));
-            V2 tangent = crossVS(normal, 1.0f);
-            float friction = V(t, VC_FRIC);
-            for (int j = 0; j < vpc; ++j) {
-                float* P = &V(t, VC_PT + 8 * j);
-                V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
-                V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
-                float vt = dot(dv, tangent) - 0.0f;
-                float lambda = P[5] * (-vt);
-                float maxFriction = friction * P[6];
-                float newImpulse = clampf(P[7] + lambda, -maxFriction, maxFriction);
-                lambda = newImpulse - P[7];
-                P[7] = newImpulse;
+    // b2ContactSolver::SolveVelocityConstraints x iters, flattened: the (sweep, contact, point) loop nest runs as
+    // ONE per-lane loop whose trip is a single point operation — friction point j, then the normal point
+    // (1-point manifolds) or the 2-point block solve.  Lanes of a warp advance through their own islands
+    // independently, so a warp runs max_lane(total ops) trips instead of 180 x max_lane(contacts) x max(points).
+    // The operation order inside an env is exactly Box2D's.  A lane stops after the first sweep that changes
+    // nothing: every later sweep would be the identical no-op, so the result equals the full 180 bit for bit.
+    struct VelState {
+        int t, j, sweep;
+        bool changed;
+    };
+    MRP_HD void vel_begin(VelState& st) { st.t = 0; st.j = 0; st.sweep = 0; st.changed = false; }
+    MRP_HD void solve_velocity(int T, int iters) {
+        if (T == 0) return;
+        VelState st;
+        vel_begin(st);
+        while (!vel_trip(st, T, iters)) {}
+    }
+    // one point operation; returns true when the solve is finished
+    MRP_HD bool vel_trip(VelState& st, int T, int iters) {
+        int t = st.t, j = st.j;
+        bool changed = st.changed;
+        bool finished = false;
+        {
+            const uint32_t vm = vmeta(t);
+            const int bA = vm & 15, bB = (vm >> 4) & 15, vpc = (vm >> 8) & 3;
+            float* const C = &V(t, 0);
+            const float mA = C[VC_MA], mB = C[VC_MB], iA = C[VC_IA], iB = C[VC_IB];
+            float* const pA = bp(bA);
+            float* const pB = bp(bB);
+            V2 vA = mk(pA[3 * MRP_SS], pA[4 * MRP_SS]), vB = mk(pB[3 * MRP_SS], pB[4 * MRP_SS]);
+            float wA = pA[5 * MRP_SS], wB = pB[5 * MRP_SS];
+            const V2 normal = mk(C[VC_NX], C[VC_NY]);
+            if (j < vpc || vpc == 1) {
+                // 1-D op: friction (j < vpc) along the tangent, else the single normal point
+                const bool fr = j < vpc;
+                float* P = &V(t, VC_PT + 8 * (fr ? j : 0));
+                const V2 dir = fr ? crossVS(normal, 1.0f) : normal;
+                const V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
+                const V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
+                const float vd = dot(dv, dir);
+                const float acc = fr ? P[7] : P[6];
+                float lambda = (fr ? P[5] : P[4]) * (-vd);  // tangentMass*(-vt)  ==  -normalMass*vn (exact sign symmetry)
+                float newImpulse;
+                if (fr) {
+                    const float maxFriction = V(t, VC_FRIC) * P[6];
+                    newImpulse = clampf(acc + lambda, -maxFriction, maxFriction);
+                } else {
+                    newImpulse = fmax2(acc + lambda, 0.0f);
+                }
+                lambda = newImpulse - acc;
+                if (fr) P[7] = newImpulse; else P[6] = newImpulse;
                 changed = changed || (lambda != 0.0f);
-                V2 Pi = lambda * tangent;
+                const V2 Pi = lambda * dir;
                 vA = vA - mA * Pi;
                 wA -= iA * cross(rA, Pi);
                 vB = vB + mB * Pi;
                 wB += iB * cross(rB, Pi);
-            }
-            if (vpc == 1) {
-                float* P = &V(t, VC_PT);
-                V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
-                V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
-                float vn = dot(dv, normal);
-                float lambda = -P[4] * (vn - 0.0f);
-                float newImpulse = fmax2(P[6] + lambda, 0.0f);
-                lambda = newImpulse - P[6];
-                P[6] = newImpulse;
-                changed = changed || (lambda != 0.0f);
-                V2 Pi = lambda * normal;
-                vA = vA - mA * Pi;
-                wA -= iA * cross(rA, Pi);
-                vB = vB + mB * Pi;
-                wB += iB * cross(rB, Pi);
-            } else if (vpc == 2) {
+            } else {
+                // block solver (2 points)
                 float* P1 = &V(t, VC_PT);
                 float* P2 = &V(t, VC_PT + 8);
-                V2 rA1 = mk(P1[0], P1[1]), rB1 = mk(P1[2], P1[3]);
-                V2 rA2 = mk(P2[0], P2[1]), rB2 = mk(P2[2], P2[3]);
-                float ax = P1[6], ay = P2[6];
-                V2 dv1 = vB + crossSV(wB, rB1) - vA - crossSV(wA, rA1);
-                V2 dv2 = vB + crossSV(wB, rB2) - vA - crossSV(wA, rA2);
+                const V2 rA1 = mk(P1[0], P1[1]), rB1 = mk(P1[2], P1[3]);
+                const V2 rA2 = mk(P2[0], P2[1]), rB2 = mk(P2[2], P2[3]);
+                const float ax = P1[6], ay = P2[6];
+                const V2 dv1 = vB + crossSV(wB, rB1) - vA - crossSV(wA, rA1);
+                const V2 dv2 = vB + crossSV(wB, rB2) - vA - crossSV(wA, rA2);
                 float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-                float k11 = V(t, VC_K11), k12 = V(t, VC_K12), k22 = V(t, VC_K22);
-                float bx = vn1 - 0.0f, by = vn2 - 0.0f;
+                const float k11 = V(t, VC_K11), k12 = V(t, VC_K12), k22 = V(t, VC_K22);
+                float bx = vn1, by = vn2;
                 bx -= k11 * ax + k12 * ay;
                 by -= k12 * ax + k22 * ay;
                 float xx, xy;
                 bool ok = false;
-                // case 1
-                xx = -(V(t, VC_M11) * bx + V(t, VC_M12) * by);
+                xx = -(V(t, VC_M11) * bx + V(t, VC_M12) * by);  // case 1
                 xy = -(V(t, VC_M12) * bx + V(t, VC_M22) * by);
                 if (xx >= 0.0f && xy >= 0.0f) ok = true;
                 if (!ok) {  // case 2
@@ -572,8 +620,8 @@ struct Sim {
                     if (bx >= 0.0f && by >= 0.0f) ok = true;
                 }
                 if (ok) {
-                    float dx = xx - ax, dy = xy - ay;
-                    V2 Pa = dx * normal, Pb = dy * normal;
+                    const float dx = xx - ax, dy = xy - ay;
+                    const V2 Pa = dx * normal, Pb = dy * normal;
                     vA = vA - mA * (Pa + Pb);
                     wA -= iA * (cross(rA1, Pa) + cross(rA2, Pb));
                     vB = vB + mB * (Pa + Pb);
@@ -582,19 +630,21 @@ struct Sim {
                     changed = changed || (dx != 0.0f) || (dy != 0.0f);
                 }
             }
-            B(bA, 3) = vA.x; B(bA, 4) = vA.y; B(bA, 5) = wA;
-            B(bB, 3) = vB.x; B(bB, 4) = vB.y; B(bB, 5) = wB;
+            pA[3 * MRP_SS] = vA.x; pA[4 * MRP_SS] = vA.y; pA[5 * MRP_SS] = wA;
+            pB[3 * MRP_SS] = vB.x; pB[4 * MRP_SS] = vB.y; pB[5 * MRP_SS] = wB;
+            // advance the (sweep, contact, op) counters
+            if (++j > vpc) {
+                j = 0;
+                if (++t == T) {
+                    t = 0;
+                    ++st.sweep;
+                    if (!changed || st.sweep == iters) finished = true;
+                    changed = false;
+                }
+            }
         }
-        return changed;
-    }
-    // 180 sweeps; stops early once a whole sweep changes nothing (every later sweep would be the
-    // identical no-op, so the result equals the full 180 bit for bit)
-    MRP_HD void solve_velocity(int T, int iters) {
-        if (T == 0) return;
-        int it = 0;
-        for (; it < iters; ++it)
-            if (!solve_velocity_sweep(T)) break;
-        work += (uint32_t)((it + 1) * T);
+        st.t = t; st.j = j; st.changed = changed;
+        return finished;
     }
     MRP_HD void store_impulses(int T) {
         for (int t = 0; t < T; ++t) {
@@ -624,35 +674,50 @@ struct Sim {
         B(b, 2) += h * w;
         B(b, 3) = v.x; B(b, 4) = v.y; B(b, 5) = w;
     }
-    // one position sweep over constraints whose island bit is not in doneMask; per island, records
-    // whether minSeparation >= -limit*slop.  toiA/toiB >= 0 selects b2ContactSolver::SolveTOIPositionConstraints.
-    MRP_HD uint32_t solve_position_sweep(int T, uint32_t doneMask, int toiA, int toiB) {
-        uint32_t bad = 0;  // islands still violating
+    // b2ContactSolver::SolvePositionConstraints (toiA < 0) / SolveTOIPositionConstraints, up to maxSweeps sweeps,
+    // flattened like solve_velocity: one trip = one manifold point.  Islands are solved "in parallel" inside one env:
+    // an island whose sweep ended with minSeparation >= limit is finished (Box2D breaks out of its loop) and its
+    // constraints are skipped from then on.  Per-constraint min separations are folded into per-island flags.
+    struct PosState {
+        uint32_t done, bad;
+        int t, j, sweep;
+        float minSep;
+    };
+    MRP_HD void pos_begin(PosState& st) { st.done = 0; st.bad = 0; st.t = 0; st.j = 0; st.sweep = 0; st.minSep = 0.0f; }
+    MRP_HD void solve_position(int T, int maxSweeps, int toiA, int toiB) {
+        if (T == 0) return;
+        PosState st;
+        pos_begin(st);
+        while (!pos_trip(st, T, maxSweeps, toiA, toiB)) {}
+    }
+    MRP_HD bool pos_trip(PosState& st, int T, int maxSweeps, int toiA, int toiB) {
         const bool toi = toiA >= 0;
         const float baum = toi ? kToiBaumgarte : kBaumgarte;
         const float lim = toi ? -1.5f * kLinearSlop : -3.0f * kLinearSlop;
-        for (int t = 0; t < T; ++t) {
-            uint32_t vm = vmeta(t);
-            int isl = (vm >> 16) & 0xff;
-            if ((doneMask >> isl) & 1) continue;
-            int bA = vm & 15, bB = (vm >> 4) & 15, ppc = (vm >> 10) & 3, type = (vm >> 12) & 1;
-            float mA = invMass(bA), mB = invMass(bB), iA = invI(bA), iB = invI(bB);
-            if (toi) {
-                if (bA != toiA && bA != toiB) { mA = 0.0f; iA = 0.0f; }
-                if (bB != toiA && bB != toiB) { mB = 0.0f; iB = 0.0f; }
-            }
-            V2 lcA = localCenter(bA), lcB = localCenter(bB);
-            V2 cA = mk(B(bA, 0), B(bA, 1)), cB = mk(B(bB, 0), B(bB, 1));
-            float aA = B(bA, 2), aB = B(bB, 2);
-            V2 ln = mk(V(t, VC_LNX), V(t, VC_LNY)), lp = mk(V(t, VC_LPX), V(t, VC_LPY));
-            float minSep = 0.0f;
-            for (int j = 0; j < ppc; ++j) {
+        uint32_t done = st.done, bad = st.bad;
+        int t = st.t, j = st.j;
+        float minSep = st.minSep;
+        bool finished = false;
+        {
+            const uint32_t vm = vmeta(t);
+            const int isl = (vm >> 16) & 0xff;
+            const int ppc = (vm >> 10) & 3;
+            if (!((done >> isl) & 1)) {
+                const int bA = vm & 15, bB = (vm >> 4) & 15, type = (vm >> 12) & 1;
+                float mA = V(t, VC_MA), mB = V(t, VC_MB), iA = V(t, VC_IA), iB = V(t, VC_IB);
+                if (toi) {
+                    if (bA != toiA && bA != toiB) { mA = 0.0f; iA = 0.0f; }
+                    if (bB != toiA && bB != toiB) { mB = 0.0f; iB = 0.0f; }
+                }
+                V2 cA = mk(B(bA, 0), B(bA, 1)), cB = mk(B(bB, 0), B(bB, 1));
+                float aA = B(bA, 2), aB = B(bB, 2);
+                const V2 ln = mk(V(t, VC_LNX), V(t, VC_LNY)), lp = mk(V(t, VC_LPX), V(t, VC_LPY));
                 Xf xfA, xfB;
-                xfA.q = is_dyn(bA) ? rot_set(aA) : Rot{0.0f, 1.0f};
-                xfB.q = is_dyn(bB) ? rot_set(aB) : Rot{0.0f, 1.0f};
-                xfA.p = cA - rmul(xfA.q, lcA);
-                xfB.p = cB - rmul(xfB.q, lcB);
-                V2 lpj = mk(V(t, VC_LP0X + 2 * j), V(t, VC_LP0X + 2 * j + 1));
+                xfA.q = body_rot(bA, aA);
+                xfB.q = body_rot(bB, aB);
+                xfA.p = cA - rmul(xfA.q, localCenter(bA));
+                xfB.p = cB - rmul(xfB.q, localCenter(bB));
+                const V2 lpj = mk(V(t, VC_LP0X + 2 * j), V(t, VC_LP0X + 2 * j + 1));
                 V2 normal, point;
                 float separation;
                 if (type == 0) {
@@ -669,29 +734,41 @@ struct Sim {
                     point = clip;
                     normal = -normal;
                 }
-                V2 rA = point - cA, rB = point - cB;
+                const V2 rA = point - cA, rB = point - cB;
                 minSep = fmin2(minSep, separation);
-                float C = clampf(baum * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-                float rnA = cross(rA, normal), rnB = cross(rB, normal);
-                float Kn = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                float impulse = Kn > 0.0f ? -C / Kn : 0.0f;
-                V2 Pi = impulse * normal;
+                const float C = clampf(baum * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                const float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                const float Kn = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                const float impulse = Kn > 0.0f ? -C / Kn : 0.0f;
+                const V2 Pi = impulse * normal;
                 cA = cA - mA * Pi;
                 aA -= iA * cross(rA, Pi);
                 cB = cB + mB * Pi;
                 aB += iB * cross(rB, Pi);
+                B(bA, 0) = cA.x; B(bA, 1) = cA.y; B(bA, 2) = aA;
+                B(bB, 0) = cB.x; B(bB, 1) = cB.y; B(bB, 2) = aB;
             }
-            B(bA, 0) = cA.x; B(bA, 1) = cA.y; B(bA, 2) = aA;
-            B(bB, 0) = cB.x; B(bB, 1) = cB.y; B(bB, 2) = aB;
-            if (!(minSep >= lim)) bad |= 1u << isl;
+            if (++j >= ppc || ((done >> isl) & 1)) {
+                if (!(minSep >= lim)) bad |= 1u << isl;
+                minSep = 0.0f;
+                j = 0;
+                if (++t == T) {
+                    t = 0;
+                    ++st.sweep;
+                    done = ~bad;
+                    if (!bad || st.sweep == maxSweeps) finished = true;
+                    bad = 0;
+                }
+            }
         }
-        return bad;
+        st.done = done; st.bad = bad; st.t = t; st.j = j; st.minSep = minSep;
+        return finished;
     }
 
     // ------------------------------------------------------------ b2World::Solve (A.7, A.8)
-    MRP_HD void solve_islands() {
+    // island build (A.7): fills order[] (solver order = DFS discovery order) and island_of[]; returns T
+    MRP_HD int build_islands(uint8_t* island_of) {
         // island build: DFS seeds in body-list order (newest first): agent n-1 .. agent 0, block
-        uint8_t island_of[kMaxC];
         int T = 0;
         uint32_t touch = 0;
         for (int k = 0; k < nc; ++k) touch |= ((meta[k] >> 16) & 1u) << k;
@@ -729,20 +806,18 @@ struct Sim {
                 if (T > T0) ++nisl;
             }
         }
+        return T;
+    }
+
+    MRP_HD void solve_islands() {
+        uint8_t island_of[kMaxC];
+        int T = build_islands(island_of);
         init_constraints(T, island_of, true);
         warm_start(T);
         solve_velocity(T, 180);
         store_impulses(T);
         for (int b = 0; b < K.nb; ++b) integrate_position(b, K.h);
-        if (T) {
-            uint32_t done = 0;
-            for (int it = 0; it < 60; ++it) {
-                uint32_t bad = solve_position_sweep(T, done, -1, -1);
-                work += 2u * (uint32_t)T;
-                done = ~bad;
-                if (!bad) break;
-            }
-        }
+        solve_position(T, 60, -1, -1);
     }
 
     // ------------------------------------------------------------ b2World::SolveTOI (A.10)
@@ -843,8 +918,7 @@ struct Sim {
         float subdt = (1.0f - minAlpha) * K.h;
         // b2Island::SolveTOI
         init_constraints(T, nullptr, false);
-        for (int it = 0; it < 20; ++it)
-            if (!solve_position_sweep(T, 0, bA, bB)) break;
+        solve_position(T, 20, bA, bB);
         for (int s = 0; s < 2; ++s) {
             int b = two[s];
             if (b < K.nb) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
@@ -873,13 +947,15 @@ struct Sim {
         for (int k = nc0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; enabled |= 1u << k; toiFlag &= ~(1u << k); }
     }
 
-    MRP_HD void solve_toi() {
+    // returns false when a TOI event must be processed but allow_events is false (the caller then defers this env
+    // to the event kernel, which redoes the scan from the same state)
+    MRP_HD bool solve_toi(bool allow_events = true) {
         uint32_t wallc = 0;  // contacts with a static body: the only TOI candidates (no bullets)
         for (int k = 0; k < nc; ++k) {
             uint32_t m = meta[k];
             if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc |= 1u << k;
         }
-        if (!wallc) return;
+        if (!wallc) return true;
         for (int b = 0; b < K.nb; ++b) BX(b, 13) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
@@ -906,7 +982,6 @@ struct Sim {
                         sweep_advance(bB, al0);
                     }
                     float t;
-                    work += 6u;
                     int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
                     if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
                     else alpha = 1.0f;
@@ -916,19 +991,23 @@ struct Sim {
                 if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
             }
             if (minK < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
-            work += 100u;
+            if (!allow_events) return false;
             toi_event(minK, minAlpha, toiFlag, enabled);
         }
+        return true;
     }
 
     // ------------------------------------------------------------ b2World::Step (A.6)
     MRP_HD void world_step(bool new_fixtures) {
         if (new_fixtures) find_new_contacts(0xffffffffu);
-        work += 8u * (uint32_t)nc;
         collide();
         // xf1 of SynchronizeFixtures == the transform the step started with (c0, a0 are set from c, a)
         for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
         solve_islands();
+        post_solve(true);
+    }
+    // tail of b2World::Solve + SolveTOI: SynchronizeFixtures for every dynamic body, FindNewContacts, TOI
+    MRP_HD bool post_solve(bool allow_events) {
         uint32_t moved = 0;
         for (int b = K.nb - 1; b >= 0; --b) {
             // xf1 = transform at (c0, a0); its rotation is the one the step started with
@@ -940,7 +1019,7 @@ struct Sim {
             moved |= synchronize_fixtures(b, xf1);
         }
         find_new_contacts(moved);
-        solve_toi();
+        return solve_toi(allow_events);
     }
 };
 

@@ -159,10 +159,10 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
     K->nfix = L->n_fixtures; K->ndynfix = L->n_dyn_fixtures; K->per_agent = v2 ? 3 : 1;
     K->maxc = L->max_contacts; K->obs_dim = L->obs_dim; K->act_dim = L->act_dim; K->max_steps = L->max_episode_steps;
     K->w_body = W_DIST + 2 * (n + 1);
-    K->w_aabb = K->w_body + 8 * K->nb;
+    K->w_aabb = K->w_body + kBodyWords * K->nb;
     K->w_con = K->w_aabb + 4 * K->ndynfix;
     K->w_total = K->w_con + MRP_CONTACT_WORDS * K->maxc;
-    K->smem_words = 6 * (K->nb + 4) + 8 * K->nb + 4 * K->ndynfix;
+    K->smem_words = kDynFields * K->nb + 24 + 4 * K->ndynfix;
     K->h = (float)(1.0 / 50);                       // world.Step(1.0/FPS, ...) mrp00:428
     K->lin_k = 1.0f / (1.0f + K->h * 5.0f);         // DAMP / LINEAR_DAMP = 5.0
     K->ang_k = 1.0f / (1.0f + K->h * 5.0f);

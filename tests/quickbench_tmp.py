@@ -14,7 +14,7 @@ def run(env_id, N, settle=100, K=20):
         h.sample_actions(1000+t); h.step()
     e1.record(); torch.cuda.synchronize()
     ms=e0.elapsed_time(e1)/K; kms,kc=h.get_timing()
-    print(env_id, N, 'sort' if not os.environ.get('MRP_NO_LANE_SORT') else 'nosort', 'ms/step %.3f'%ms, 'k_step ms %.3f'%(kms/kc), 'env-steps/s %.3e'%(N/ms*1e3), flush=True)
+    print(env_id, N, 'fused' if os.environ.get('MRP_FUSED_STEP') else 'pipeline', 'ms/step %.3f'%ms, 'step kernels ms %.3f'%(kms/kc), 'env-steps/s %.3e'%(N/ms*1e3), flush=True)
     h.close()
 for env_id, N in (("MultiRobotPuzzleHeavy-v0", 1048576), ("MultiRobotPuzzle-v0", 1048576), ("MultiRobotPuzzle-v2", 1048576)):
     run(env_id, N)
