@@ -76,8 +76,9 @@ MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env)
 
 // phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
 struct VelTask {
-    Sim::VelState st;
+    Sim::VelReg st;
     int T;
+    uint32_t ops;
 };
 MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
     const int64_t env = K.task_env[task];
@@ -87,9 +88,11 @@ MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
     for (int b = 0; b < K.nb; ++b)
         for (int f = 0; f < 6; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
     for (int b = K.nb; b < K.nb + 4; ++b) { s.B(b, 3) = 0.0f; s.B(b, 4) = 0.0f; s.B(b, 5) = 0.0f; }
-    s.vel_begin(vt.st);
+    vt.ops = 0;
+    s.vr_begin(vt.st, vt.T);
 }
 MRP_HD void vel_task_end(const SimConst& K, Sim& s, VelTask& vt) {
+    s.g(W_HINT) = vt.ops;
     s.store_impulses(vt.T);
     for (int b = 0; b < K.nb; ++b) {
         s.integrate_position(b, K.h);
@@ -210,7 +213,7 @@ constexpr int kRefill = 8;
 __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
-    const int ntasks = K.cnt[CNT_TASKS];
+    const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
     VelTask vt;
     bool busy = false, exhausted = false;
     for (;;) {
@@ -218,12 +221,12 @@ __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ Si
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_V], 1);
-                if (task < ntasks) { vel_task_begin(K, s, vt, task); busy = true; }
+                if (task < ntasks) { vel_task_begin(K, s, vt, task_slot(K, task)); busy = true; }
                 else exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
-        if (busy && s.vel_trip(vt.st, vt.T, 180)) {
+        if (busy && (++vt.ops, s.vr_trip(vt.st, 180))) {
             vel_task_end(K, s, vt);
             busy = false;
         }
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ Si
 __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 9);
-    const int ntasks = K.cnt[CNT_TASKS];
+    const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
     PosTask pt;
     bool busy = false, exhausted = false;
     for (;;) {
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_P], 1);
-                if (task < ntasks) { pos_task_begin(K, s, pt, task); busy = true; }
+                if (task < ntasks) { pos_task_begin(K, s, pt, task_slot(K, task)); busy = true; }
                 else exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
@@ -315,6 +318,7 @@ struct mrp_handle {
     float* act_dev;
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
     size_t smem_vel, smem_pos;
+    int solver_ctas;  // persistent solver CTAs per SM
     int64_t launches;
     size_t smem_bytes;
     // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
@@ -426,6 +430,8 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
+    h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
+    if (h->solver_ctas < 1) h->solver_ctas = 1;
     K.seed = cfg->seed;
     K.env_id_base = cfg->env_id_base;
     K.N = cfg->num_envs;
@@ -576,6 +582,7 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
     const unsigned grid = grid_for(K.N, kBlock);
     // persistent / queue kernels: a few CTAs per SM
     const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+    const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
     k_clear<<<1, 32, 0, st>>>(K.cnt);
     if (h->timing) {
         if (h->ev_n == 64) drain_timing(h);
@@ -586,8 +593,8 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         h->launches += 2;
     } else {
         k_pre<<<grid, kBlock, h->smem_bytes, st>>>(K);
-        k_solve_vel<<<pgrid, kBlock, h->smem_vel, st>>>(K);
-        k_solve_pos<<<pgrid, kBlock, h->smem_pos, st>>>(K);
+        k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
+        k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
         k_post<<<grid, kBlock, h->smem_bytes, st>>>(K);
         k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 6;
@@ -606,18 +613,18 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
     } else {
         // the same phases the device runs as kernels, executed as loops
         for (int64_t e = 0; e < K.N; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
-        const int ntasks = K.cnt[CNT_TASKS];
+        const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
         for (int i = 0; i < ntasks; ++i) {
             Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
             VelTask vt;
-            vel_task_begin(K, s, vt, i);
-            while (!s.vel_trip(vt.st, vt.T, 180)) {}
+            vel_task_begin(K, s, vt, task_slot(K, i));
+            while (++vt.ops, !s.vr_trip(vt.st, 180)) {}
             vel_task_end(K, s, vt);
         }
         for (int i = 0; i < ntasks; ++i) {
             Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
             PosTask pt;
-            pos_task_begin(K, s, pt, i);
+            pos_task_begin(K, s, pt, task_slot(K, i));
             while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
             pos_task_end(K, s, pt);
         }

@@ -336,7 +336,8 @@ struct Env : Sim {
         const int T = build_islands(island_of);
         if (T > 0) {
             const int off = atomic_add_i32(&K.cnt[CNT_POOL], T * VC_WORDS);
-            const int task = atomic_add_i32(&K.cnt[CNT_TASKS], 1);
+            const int task = g(W_HINT) >= kHeavyHint ? atomic_add_i32(&K.cnt[CNT_TASKS], 1)
+                                                     : (int)(K.N - 1) - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT], 1);
             K.task_env[task] = (int32_t)(G - K.S);
             K.task_T[task] = T;
             K.task_off[task] = off;
@@ -345,6 +346,7 @@ struct Env : Sim {
             warm_start(T);
         } else {
             for (int b = 0; b < K.nb; ++b) integrate_position(b, K.h);
+            g(W_HINT) = 0;
         }
         // hand-off to the solver / post kernels: poses + velocities, pre-step pose, contact list
         g(W_NC) = (uint32_t)nc;

@@ -35,7 +35,8 @@ constexpr int CT_WORDS = CT_SHAPES + 8 * kShapeWords;
 constexpr int W_ELAPSED = 0, W_EPISODE = 1, W_INPLACE = 2, W_NC = 3, W_GOALC = 4, W_EPLEN = 5;
 constexpr int W_EPRET = 6;   // f64
 constexpr int W_GOAL = 8;    // 2 x f64
-constexpr int W_DIST = 12;   // (n+1) x f64: agent_dist[0..n-1], block_dist
+constexpr int W_HINT = 12;   // solver operations this env needed on its previous step (task ordering hint)
+constexpr int W_DIST = 13;   // (n+1) x f64: agent_dist[0..n-1], block_dist
 // then bodies[nb][11] = {cx, cy, a, vx, vy, w, q.s, q.c, c0x, c0y, a0} (c0/a0: pose at the start of the step, written by
 // k_pre for k_post's SynchronizeFixtures); fat[ndynfix][4]; contacts[maxc][14]
 constexpr int kBodyWords = 11;
@@ -77,7 +78,14 @@ struct SimConst {
     int32_t* task_off;    // [N] offset of task i's records in pool (floats)
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
 };
-enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_N = 8 };
+// solver tasks predicted heavy (by W_HINT) are queued from slot 0 upwards, the others from slot N-1 downwards;
+// consumers take the heavy ones first so that long solves start early and short ones fill the tail
+enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_TASKS_LIGHT = 6, CNT_N = 8 };
+constexpr uint32_t kHeavyHint = 120;
+MRP_HD int task_slot(const SimConst& K, int i) {  // i-th task in consumption order -> slot
+    const int nh = K.cnt[CNT_TASKS];
+    return i < nh ? i : (int)(K.N - 1) - (i - nh);
+}
 
 MRP_HD int atomic_add_i32(int32_t* p, int v) {
 #if defined(__CUDA_ARCH__)
@@ -646,6 +654,133 @@ struct Sim {
         st.t = t; st.j = j; st.changed = changed;
         return finished;
     }
+    // ---- register-resident form of the velocity solve (solver kernel): the current contact's constraint record and
+    // the velocities of its two bodies live in registers while its point operations run; they are exchanged with
+    // memory only when the lane moves on to another contact.  Islands with one contact (the common case) therefore
+    // iterate entirely in registers.  Arithmetic and operation order are identical to vel_trip().
+    struct VelReg {
+        int T, t, j, sweep, bA, bB, vpc;
+        bool changed;
+        float mA, iA, mB, iB, fric;
+        V2 n, rA0, rB0, rA1, rB1;
+        float nM0, tM0, nI0, tI0, nM1, tM1, nI1, tI1;
+        float k11, k12, k22, m11, m12, m22;
+        V2 vA, vB;
+        float wA, wB;
+    };
+    MRP_HD void vr_load(VelReg& r) {
+        const float* C = &V(r.t, 0);
+        const uint32_t vm = __float_as_uint_(C[VC_META]);
+        r.bA = vm & 15; r.bB = (vm >> 4) & 15; r.vpc = (vm >> 8) & 3;
+        r.mA = C[VC_MA]; r.iA = C[VC_IA]; r.mB = C[VC_MB]; r.iB = C[VC_IB];
+        r.fric = C[VC_FRIC];
+        r.n = mk(C[VC_NX], C[VC_NY]);
+        r.rA0 = mk(C[VC_PT + 0], C[VC_PT + 1]); r.rB0 = mk(C[VC_PT + 2], C[VC_PT + 3]);
+        r.nM0 = C[VC_PT + 4]; r.tM0 = C[VC_PT + 5]; r.nI0 = C[VC_PT + 6]; r.tI0 = C[VC_PT + 7];
+        r.rA1 = mk(C[VC_PT + 8], C[VC_PT + 9]); r.rB1 = mk(C[VC_PT + 10], C[VC_PT + 11]);
+        r.nM1 = C[VC_PT + 12]; r.tM1 = C[VC_PT + 13]; r.nI1 = C[VC_PT + 14]; r.tI1 = C[VC_PT + 15];
+        r.k11 = C[VC_K11]; r.k12 = C[VC_K12]; r.k22 = C[VC_K22];
+        r.m11 = C[VC_M11]; r.m12 = C[VC_M12]; r.m22 = C[VC_M22];
+        const float* pA = bp(r.bA);
+        const float* pB = bp(r.bB);
+        r.vA = mk(pA[3 * MRP_SS], pA[4 * MRP_SS]); r.wA = pA[5 * MRP_SS];
+        r.vB = mk(pB[3 * MRP_SS], pB[4 * MRP_SS]); r.wB = pB[5 * MRP_SS];
+    }
+    MRP_HD void vr_store(const VelReg& r) {
+        float* C = &V(r.t, 0);
+        C[VC_PT + 6] = r.nI0; C[VC_PT + 7] = r.tI0; C[VC_PT + 14] = r.nI1; C[VC_PT + 15] = r.tI1;
+        float* pA = bp(r.bA);
+        float* pB = bp(r.bB);
+        pA[3 * MRP_SS] = r.vA.x; pA[4 * MRP_SS] = r.vA.y; pA[5 * MRP_SS] = r.wA;
+        pB[3 * MRP_SS] = r.vB.x; pB[4 * MRP_SS] = r.vB.y; pB[5 * MRP_SS] = r.wB;
+    }
+    MRP_HD void vr_begin(VelReg& r, int T) {
+        r.T = T; r.t = 0; r.j = 0; r.sweep = 0; r.changed = false;
+        vr_load(r);
+    }
+    // one point operation; returns true when the solve is finished (everything written back)
+    MRP_HD bool vr_trip(VelReg& r, int iters) {
+        const int j = r.j;
+        if (j < r.vpc || r.vpc == 1) {
+            const bool fr = j < r.vpc, second = fr && j == 1;
+            const V2 dir = fr ? crossVS(r.n, 1.0f) : r.n;
+            const V2 rA = second ? r.rA1 : r.rA0, rB = second ? r.rB1 : r.rB0;
+            const V2 dv = r.vB + crossSV(r.wB, rB) - r.vA - crossSV(r.wA, rA);
+            const float vd = dot(dv, dir);
+            const float acc = fr ? (second ? r.tI1 : r.tI0) : r.nI0;
+            const float mass = fr ? (second ? r.tM1 : r.tM0) : r.nM0;
+            float lambda = mass * (-vd);
+            const float maxFriction = r.fric * (second ? r.nI1 : r.nI0);
+            const float newImpulse = fr ? clampf(acc + lambda, -maxFriction, maxFriction) : fmax2(acc + lambda, 0.0f);
+            lambda = newImpulse - acc;
+            if (!fr) r.nI0 = newImpulse;
+            else if (second) r.tI1 = newImpulse;
+            else r.tI0 = newImpulse;
+            r.changed = r.changed || (lambda != 0.0f);
+            const V2 Pi = lambda * dir;
+            r.vA = r.vA - r.mA * Pi;
+            r.wA -= r.iA * cross(rA, Pi);
+            r.vB = r.vB + r.mB * Pi;
+            r.wB += r.iB * cross(rB, Pi);
+        } else {
+            const float ax = r.nI0, ay = r.nI1;
+            const V2 dv1 = r.vB + crossSV(r.wB, r.rB0) - r.vA - crossSV(r.wA, r.rA0);
+            const V2 dv2 = r.vB + crossSV(r.wB, r.rB1) - r.vA - crossSV(r.wA, r.rA1);
+            float vn1 = dot(dv1, r.n), vn2 = dot(dv2, r.n);
+            float bx = vn1, by = vn2;
+            bx -= r.k11 * ax + r.k12 * ay;
+            by -= r.k12 * ax + r.k22 * ay;
+            float xx, xy;
+            bool ok = false;
+            xx = -(r.m11 * bx + r.m12 * by);
+            xy = -(r.m12 * bx + r.m22 * by);
+            if (xx >= 0.0f && xy >= 0.0f) ok = true;
+            if (!ok) {
+                xx = -r.nM0 * bx; xy = 0.0f;
+                vn2 = r.k12 * xx + by;
+                if (xx >= 0.0f && vn2 >= 0.0f) ok = true;
+            }
+            if (!ok) {
+                xx = 0.0f; xy = -r.nM1 * by;
+                vn1 = r.k12 * xy + bx;
+                if (xy >= 0.0f && vn1 >= 0.0f) ok = true;
+            }
+            if (!ok) {
+                xx = 0.0f; xy = 0.0f;
+                if (bx >= 0.0f && by >= 0.0f) ok = true;
+            }
+            if (ok) {
+                const float dx = xx - ax, dy = xy - ay;
+                const V2 Pa = dx * r.n, Pb = dy * r.n;
+                r.vA = r.vA - r.mA * (Pa + Pb);
+                r.wA -= r.iA * (cross(r.rA0, Pa) + cross(r.rA1, Pb));
+                r.vB = r.vB + r.mB * (Pa + Pb);
+                r.wB += r.iB * (cross(r.rB0, Pa) + cross(r.rB1, Pb));
+                r.nI0 = xx; r.nI1 = xy;
+                r.changed = r.changed || (dx != 0.0f) || (dy != 0.0f);
+            }
+        }
+        if (++r.j > r.vpc) {
+            r.j = 0;
+            bool wrapped = true;
+            if (r.T > 1) {
+                vr_store(r);
+                wrapped = ++r.t == r.T;
+                if (wrapped) r.t = 0;
+                vr_load(r);
+            }
+            if (wrapped) {
+                ++r.sweep;
+                if (!r.changed || r.sweep == iters) {
+                    if (r.T == 1) vr_store(r);
+                    return true;
+                }
+                r.changed = false;
+            }
+        }
+        return false;
+    }
+
     MRP_HD void store_impulses(int T) {
         for (int t = 0; t < T; ++t) {
             uint32_t vm = vmeta(t);
