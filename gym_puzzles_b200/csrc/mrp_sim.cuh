@@ -29,7 +29,9 @@ constexpr int CT_FIXFRIC = 64;    // [32] friction of fixture
 constexpr int CT_WALLFAT = 96;    // [4][4] fat AABB of wall fixtures
 constexpr int CT_WALLPOS = 112;   // [4][2] wall body positions
 constexpr int CT_SHAPES = 120;    // [8][33]
-constexpr int CT_WORDS = CT_SHAPES + 8 * kShapeWords;
+constexpr int CT_SHAPEX = CT_SHAPES + 8 * kShapeWords;  // [8][6] bounding data per shape: centre x,y, half extents hx,hy, radius, is_box
+constexpr int CT_WALLBOX = CT_SHAPEX + 8 * 6;          // [4][4] wall polygons in world space (lo.x, lo.y, hi.x, hi.y), no radius
+constexpr int CT_WORDS = CT_WALLBOX + 16;
 
 // ---- internal per-env state words in HBM: S[word * N + env] ------------------------
 constexpr int W_ELAPSED = 0, W_EPISODE = 1, W_INPLACE = 2, W_NC = 3, W_GOALC = 4, W_EPLEN = 5;
@@ -123,6 +125,7 @@ struct Sim {
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
     float wallAlpha0[4];
+    float swept[12 * 4];   // swept tight AABB (incl. polygon radius) of every dynamic fixture, from SynchronizeFixtures
     int nc;
     uint32_t goalc;
     uint32_t overflow;
@@ -264,6 +267,48 @@ struct Sim {
         }
     }
 
+    // ---- exact culling -------------------------------------------------------------------------------------------
+    // b2CollidePolygons returns an empty manifold as soon as one polygon's best face separation exceeds
+    // totalRadius (0.02).  A cheap LOWER bound on that separation that already exceeds 0.02 (plus a guard band far
+    // above float rounding) therefore proves the manifold empty without running SAT + clipping:
+    //  * wall pairs: the wall's face normals are the world axes, so the separation along them is an AABB gap;
+    //  * box fixtures (T-block parts, v2 wheels): the box's own face normals against the other shape's bounding circle;
+    //  * octagon vs octagon: face normals are 45 degrees apart, so one lies within 22.5 degrees of the centre line.
+    MRP_HD const float* shape_x(int f) const { return ct + CT_SHAPEX + 6 * (int)ct[CT_FIXSHAPE + f]; }
+    // half extents of fixture f's polygon along the world axes at rotation q (bounding radius for the octagon)
+    MRP_HD V2 world_extent(const float* sx, Rot q) const {
+        if (sx[5] == 0.0f) return mk(sx[4], sx[4]);
+        const float ac = fabsf(q.c), as = fabsf(q.s);
+        return mk(ac * sx[2] + as * sx[3], as * sx[2] + ac * sx[3]);
+    }
+    MRP_HD bool manifold_provably_empty(int fa, int fb, int bA, int bB, Xf xfA, Xf xfB) {
+        const float kGuard = 0.0205f;  // totalRadius 0.02 + guard
+        const float* sa = shape_x(fa);
+        const float* sb = shape_x(fb);
+        const V2 cA = xmul(xfA, mk(sa[0], sa[1]));
+        if (bB >= K.nb) {  // fb is a wall (walls are the last fixtures)
+            const float* w = ct + CT_WALLBOX + 4 * (bB - K.nb);
+            const V2 e = world_extent(sa, xfA.q);
+            const float gx = fmax2(w[0] - (cA.x + e.x), (cA.x - e.x) - w[2]);
+            const float gy = fmax2(w[1] - (cA.y + e.y), (cA.y - e.y) - w[3]);
+            return fmax2(gx, gy) > kGuard;
+        }
+        const V2 cB = xmul(xfB, mk(sb[0], sb[1]));
+        if (sa[5] != 0.0f) {  // A is a box: its face normals vs B's bounding circle
+            const V2 p = rmulT(xfA.q, cB - cA);
+            if (fmax2(fabsf(p.x) - sa[2], fabsf(p.y) - sa[3]) - sb[4] > kGuard) return true;
+        }
+        if (sb[5] != 0.0f) {
+            const V2 p = rmulT(xfB.q, cA - cB);
+            if (fmax2(fabsf(p.x) - sb[2], fabsf(p.y) - sb[3]) - sa[4] > kGuard) return true;
+        }
+        if (sa[5] == 0.0f && sb[5] == 0.0f) {
+            const float D = length(cB - cA);
+            if (0.9238f * D - sa[4] - sb[4] > kGuard) return true;
+        }
+        return false;
+    }
+
     // b2Contact::Update for slot k (A.4): narrowphase at the bodies' current transforms, impulse
     // matching by feature id, touching flag, Begin/End events.
     MRP_HDN void update_contact(int k) {
@@ -273,7 +318,9 @@ struct Sim {
         bool was = (m >> 16) & 1;
         int oldpc = (m >> 18) & 3;
         Manifold man;
-        collide_polygons(&man, fix_shape(fa), body_xf(bA), fix_shape(fb), body_xf(bB));
+        const Xf xfA = body_xf(bA), xfB = body_xf(bB);
+        if (manifold_provably_empty(fa, fb, bA, bB, xfA, xfB)) { man.pc = 0; man.type = 0; }
+        else collide_polygons(&man, fix_shape(fa), xfA, fix_shape(fb), xfB);
         bool touching = man.pc > 0;
         if (touching) {
             uint32_t okeys = oldpc ? g(cw(k, 1)) : 0u;
@@ -358,6 +405,7 @@ struct Sim {
             Box a;
             a.lx = fmin2(a1.lx, a2.lx); a.ly = fmin2(a1.ly, a2.ly);
             a.hx = fmax2(a1.hx, a2.hx); a.hy = fmax2(a1.hy, a2.hy);
+            swept[4 * f] = a.lx; swept[4 * f + 1] = a.ly; swept[4 * f + 2] = a.hx; swept[4 * f + 3] = a.hy;
             if (contains(fat(f), a)) continue;
             a.lx = a.lx - kAabbExtension; a.ly = a.ly - kAabbExtension;
             a.hx = a.hx + kAabbExtension; a.hy = a.hy + kAabbExtension;
@@ -1082,6 +1130,27 @@ struct Sim {
         for (int k = nc0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; enabled |= 1u << k; toiFlag &= ~(1u << k); }
     }
 
+    // Exact TOI culling.  b2TimeOfImpact can only report e_touching (the one state that yields alpha < 1) if the
+    // distance between the two core polygons drops below target + tolerance = 0.00625 somewhere on the sweep: every
+    // separation it evaluates along its axis is bounded below by the true distance at that time.
+    // The swept AABB of the fixture (vertices at both ends of the sweep) minus a curvature term for the rotation in
+    // between bounds that distance from below along the wall's axis-aligned faces; when even this bound stays above
+    // 0.00625 (+ guard) the call is skipped and alpha = 1, exactly what the full algorithm would return.
+    MRP_HD bool toi_provably_one(int f, int b, int wall) {
+        const float da = B(b, 2) - BX(b, 8);
+        if (!(fabsf(da) < 0.5f)) return false;
+        const float* sx = shape_x(f);
+        const V2 lc = localCenter(b);
+        const float arm = sx[4] + length(mk(sx[0] - lc.x, sx[1] - lc.y));
+        const float curv = 0.25f * arm * da * da;
+        const float* w = ct + CT_WALLBOX + 4 * wall;
+        const float* a = swept + 4 * f;
+        const float r = kPolygonRadius;
+        const float gx = fmax2(w[0] - (a[2] - r), (a[0] + r) - w[2]);
+        const float gy = fmax2(w[1] - (a[3] - r), (a[1] + r) - w[3]);
+        return fmax2(gx, gy) - curv > 0.00625f + 0.001f;
+    }
+
     // returns false when a TOI event must be processed but allow_events is false (the caller then defers this env
     // to the event kernel, which redoes the scan from the same state)
     MRP_HD bool solve_toi(bool allow_events = true) {
@@ -1108,6 +1177,12 @@ struct Sim {
                     uint32_t m = meta[k];
                     int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
                     if (is_dyn(bA) && is_dyn(bB)) continue;
+                    // fixture A is the dynamic one (walls are the last fixtures); cull only untouched sweeps
+                    if (alpha0(bA) == 0.0f && alpha0(bB) == 0.0f && toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) {
+                        toi[k] = 1.0f;
+                        toiFlag |= 1u << k;
+                        continue;
+                    }
                     float al0 = alpha0(bA);
                     if (alpha0(bA) < alpha0(bB)) {
                         al0 = alpha0(bB);

@@ -142,6 +142,23 @@ inline void put_shape(float* ctab, int s, const HostPoly* p) {
     float* t = ctab + CT_SHAPES + kShapeWords * s;
     t[0] = (float)p->count;
     for (int i = 0; i < 8; ++i) { t[1 + i] = p->vx[i]; t[9 + i] = p->vy[i]; t[17 + i] = p->nx[i]; t[25 + i] = p->ny[i]; }
+    // bounding data for the exact culling tests (conservative: padded outwards)
+    float lx = p->vx[0], hx = p->vx[0], ly = p->vy[0], hy = p->vy[0];
+    for (int i = 1; i < p->count; ++i) {
+        lx = p->vx[i] < lx ? p->vx[i] : lx; hx = p->vx[i] > hx ? p->vx[i] : hx;
+        ly = p->vy[i] < ly ? p->vy[i] : ly; hy = p->vy[i] > hy ? p->vy[i] : hy;
+    }
+    float* x = ctab + CT_SHAPEX + 6 * s;
+    const float pad = 1e-5f;
+    x[0] = 0.5f * (lx + hx); x[1] = 0.5f * (ly + hy);
+    x[2] = 0.5f * (hx - lx) + pad; x[3] = 0.5f * (hy - ly) + pad;
+    float r2 = 0.0f;
+    for (int i = 0; i < p->count; ++i) {
+        float dx = p->vx[i] - x[0], dy = p->vy[i] - x[1];
+        r2 = dx * dx + dy * dy > r2 ? dx * dx + dy * dy : r2;
+    }
+    x[4] = sqrtf(r2) + pad;
+    x[5] = p->count == 4 ? 1.0f : 0.0f;  // every 4-gon here is an axis-aligned box in its local frame
 }
 
 // Fills the variant part of SimConst and the CT_WORDS-float constant table.
@@ -262,6 +279,8 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
             if (i == 0) { lx = hx = x; ly = hy = y; }
             else { lx = x < lx ? x : lx; ly = y < ly ? y : ly; hx = x > hx ? x : hx; hy = y > hy ? y : hy; }
         }
+        float* wb = ctab + CT_WALLBOX + 4 * k;
+        wb[0] = lx; wb[1] = ly; wb[2] = hx; wb[3] = hy;
         float* wf = ctab + CT_WALLFAT + 4 * k;
         wf[0] = (lx - kPolygonRadius) - kAabbExtension; wf[1] = (ly - kPolygonRadius) - kAabbExtension;
         wf[2] = (hx + kPolygonRadius) + kAabbExtension; wf[3] = (hy + kPolygonRadius) + kAabbExtension;
