@@ -12,8 +12,9 @@ steps applies).  One "step" = one env.step of every env of the batch.
             K steps bracketed by barrier + synchronize, CUDA-event timed, max over ranks.
   e2e       the same through mrp_step_host(): pinned HOST action buffer -> H2D, step, obs/reward/done/trunc D2H,
             every step, copies inside the timed region.
-  roofline  dominant kernel k_step: algorithmic bytes (513 B per env-step, SURVEY.md §8d / DESIGN.md) over its mean
-            launch time measured with CUDA events recorded around that launch inside the library (mrp_set_timing).
+  roofline  dominant kernel of the step's phase pipeline (k_pre / k_solve_vel / k_solve_pos / k_post / k_post_events):
+            algorithmic bytes (513 B per env-step, SURVEY.md §8d / DESIGN.md) over its mean launch time, measured with
+            CUDA events recorded between the kernels inside the library (mrp_set_timing / mrp_get_phase_timing).
   cpu_baseline  the oracle ("port": pybox2d is not installable here) on all host cores, bounded sample.
 """
 import argparse
@@ -145,16 +146,18 @@ def run_native(args):
     h = env.handle
     A, O = h.act_dim, h.obs_dim
     env.reset()
-    R = 4  # ring of pre-generated action buffers: inputs are resident in HBM before the timed region
+    # settle: all envs are reset at t=0, so the first steps resolve spawn overlaps (heavier than steady state);
+    # run them untimed (actions sampled on the fly) before the W warm-up steps so the timed region sees the
+    # rollout's stationary mix
+    for t in range(args.settle + W):
+        env.sample_actions(step_index=t)
+        env.step()
+    # inputs of the timed region are resident in HBM before it starts: one distinct pre-generated U(-1,1) action
+    # buffer per timed step (up to 64, then the ring repeats; a short ring would give every robot a net drift)
+    R = min(K, 64)
     acts = torch.empty((R, N, A), dtype=torch.float32, device=dev)
     for r in range(R):
-        env.sample_actions(step_index=r, out=acts[r])
-    # settle: all envs are reset at t=0, so the first steps resolve spawn overlaps (heavier than steady state);
-    # run them untimed before the W warm-up steps so the timed region sees the rollout's stationary mix
-    for t in range(args.settle):
-        env.step(acts[t % R])
-    for t in range(W):
-        env.step(acts[t % R])
+        env.sample_actions(step_index=args.settle + W + r, out=acts[r])
     torch.cuda.synchronize()
 
     def barrier():
@@ -186,22 +189,24 @@ def run_native(args):
     elapsed_ms = float(elapsed_ms.item())
     launches = h.launch_count - launches0
     k_ms, k_cnt = h.get_timing(reset_after=True)
+    phase_ms = h.get_phase_timing(reset_after=True)
     h.set_timing(False)
     value = world * N * K / (elapsed_ms / 1e3)
 
     # ---------------- end to end through the host-buffer C-ABI call (pinned host memory)
     Ke = max(2, min(K, args.e2e_steps))
-    host_act = acts[0].cpu().pin_memory()
+    host_acts = [acts[(K + i) % R].cpu().pin_memory() for i in range(Ke + 1)]   # a different action batch per step
     host_obs = torch.empty((N, O), dtype=torch.float32).pin_memory()
     host_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
     host_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
     host_trunc = torch.empty((N,), dtype=torch.uint8).pin_memory()
-    np_args = [x.numpy() for x in (host_act, host_obs, host_rew, host_done, host_trunc)]
-    h.step_host(np_args[0], *np_args[1:])  # warm
+    np_acts = [x.numpy() for x in host_acts]
+    np_args = [x.numpy() for x in (host_obs, host_rew, host_done, host_trunc)]
+    h.step_host(np_acts[Ke], *np_args)  # warm
     barrier()
     e0.record()
     for t in range(Ke):
-        h.step_host(np_args[0], *np_args[1:])
+        h.step_host(np_acts[t], *np_args)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -216,12 +221,19 @@ def run_native(args):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         k_mean_ms = k_ms / max(k_cnt, 1)
-        achieved = ALGO_BYTES_PER_ENV_STEP * N / (k_mean_ms / 1e3) / 1e9 if k_mean_ms > 0 else None
+        per_kernel = {k: v / max(k_cnt, 1) for k, v in phase_ms.items()}
+        dom = max(per_kernel, key=per_kernel.get)
+        dom_ms = per_kernel[dom]
+        achieved = ALGO_BYTES_PER_ENV_STEP * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+        pipeline_gbs = ALGO_BYTES_PER_ENV_STEP * N / (k_mean_ms / 1e3) / 1e9 if k_mean_ms > 0 else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture,
+                # scaled from the profiled batch size to this run's
+                rec = json.load(open(tp))[dom]
+                traffic = rec["dram_bytes_per_launch"] * (N / rec["envs"])
             except Exception:
                 traffic = None
         line = {
@@ -237,7 +249,8 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_step", "kernel_ms": k_mean_ms, "kernel_share_of_step": (k_ms / elapsed_ms) if elapsed_ms else None,
+                         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / (elapsed_ms / K) if elapsed_ms else None,
+                         "kernels_ms": per_kernel, "pipeline_ms": k_mean_ms, "pipeline_achieved": pipeline_gbs,
                          "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
             "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},
         }

@@ -24,7 +24,7 @@ STAT_NAMES = ("episodes", "done_by_env", "truncated", "sum_return", "sum_return_
 EXPORTS = (
     "mrp_last_error", "mrp_backend", "mrp_create", "mrp_destroy", "mrp_get_layout", "mrp_get_buffers", "mrp_reset",
     "mrp_step", "mrp_step_host", "mrp_reset_host", "mrp_sample_actions", "mrp_get_state", "mrp_set_state",
-    "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_set_timing", "mrp_get_timing", "mrp_launch_count",
+    "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_set_timing", "mrp_get_timing", "mrp_get_phase_timing", "mrp_launch_count",
 )
 
 
@@ -85,6 +85,7 @@ class MrpLib:
         L.mrp_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.mrp_set_timing.argtypes = [C.c_void_p, C.c_int32]
         L.mrp_get_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
+        L.mrp_get_phase_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.mrp_launch_count.argtypes = [C.c_void_p]
         L.mrp_launch_count.restype = C.c_int64
 
@@ -211,6 +212,14 @@ class Handle:
         ms, n = C.c_double(), C.c_int64()
         self.lib.check(self.lib.lib.mrp_get_timing(self.h, C.byref(ms), C.byref(n), 1 if reset_after else 0), "mrp_get_timing")
         return ms.value, n.value
+
+    PHASES = ("k_pre", "k_solve_vel", "k_solve_pos", "k_post", "k_post_events")
+
+    def get_phase_timing(self, reset_after=True):
+        """-> {kernel name: accumulated milliseconds} for the five phase kernels of step()"""
+        ms = np.zeros(5, dtype=np.float64)
+        self.lib.check(self.lib.lib.mrp_get_phase_timing(self.h, _ptr(ms), 1 if reset_after else 0), "mrp_get_phase_timing")
+        return dict(zip(self.PHASES, ms.tolist()))
 
     @property
     def launch_count(self):

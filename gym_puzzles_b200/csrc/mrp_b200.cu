@@ -328,6 +328,8 @@ struct mrp_handle {
     int64_t k_count;   // accumulated k_step launches
 #ifndef MRP_HOST_EMU
     cudaEvent_t ev0[64], ev1[64];
+    cudaEvent_t evk[64][4];   // boundaries between the five phase kernels of one step
+    double phase_ms[5];       // accumulated per-kernel milliseconds: pre, solve_vel, solve_pos, post, post_events
 #endif
 #ifdef MRP_HOST_EMU
     float* emu_sm;
@@ -540,6 +542,11 @@ static void drain_timing(mrp_handle* h) {
         float ms = 0.0f;
         cudaEventSynchronize(h->ev1[i]);
         if (cudaEventElapsedTime(&ms, h->ev0[i], h->ev1[i]) == cudaSuccess) { h->k_ms += ms; h->k_count += 1; }
+        if (!h->fused) {
+            cudaEvent_t b[6] = {h->ev0[i], h->evk[i][0], h->evk[i][1], h->evk[i][2], h->evk[i][3], h->ev1[i]};
+            for (int k = 0; k < 5; ++k)
+                if (cudaEventElapsedTime(&ms, b[k], b[k + 1]) == cudaSuccess) h->phase_ms[k] += ms;
+        }
     }
     h->ev_n = 0;
 }
@@ -550,10 +557,16 @@ int mrp_set_timing(mrp_handle* h, int32_t enable) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     if (enable && !h->timing)
-        for (int i = 0; i < 64; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); }
+        for (int i = 0; i < 64; ++i) {
+            cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]);
+            for (int k = 0; k < 4; ++k) cudaEventCreate(&h->evk[i][k]);
+        }
     if (!enable && h->timing) {
         drain_timing(h);
-        for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
+        for (int i = 0; i < 64; ++i) {
+            cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]);
+            for (int k = 0; k < 4; ++k) cudaEventDestroy(h->evk[i][k]);
+        }
     }
 #endif
     h->timing = enable ? 1 : 0;
@@ -569,6 +582,19 @@ int mrp_get_timing(mrp_handle* h, double* total_ms, int64_t* count, int32_t rese
     *total_ms = h->k_ms;
     *count = h->k_count;
     if (reset_after) { h->k_ms = 0.0; h->k_count = 0; }
+    return 0;
+}
+
+int mrp_get_phase_timing(mrp_handle* h, double* ms5, int32_t reset_after) {
+    if (!h || !ms5) return fail(-1, "mrp_get_phase_timing: null argument");
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (h->timing) drain_timing(h);
+    for (int k = 0; k < 5; ++k) ms5[k] = h->phase_ms[k];
+    if (reset_after) for (int k = 0; k < 5; ++k) h->phase_ms[k] = 0.0;
+#else
+    for (int k = 0; k < 5; ++k) ms5[k] = 0.0;
+#endif
     return 0;
 }
 
@@ -593,9 +619,13 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         h->launches += 2;
     } else {
         k_pre<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        if (h->timing) cudaEventRecord(h->evk[h->ev_n][0], st);
         k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
+        if (h->timing) cudaEventRecord(h->evk[h->ev_n][1], st);
         k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
+        if (h->timing) cudaEventRecord(h->evk[h->ev_n][2], st);
         k_post<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        if (h->timing) cudaEventRecord(h->evk[h->ev_n][3], st);
         k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 6;
     }

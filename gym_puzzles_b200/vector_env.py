@@ -53,8 +53,9 @@ class VectorEnv:
         self.actions = _wrap(torch, b.action_dev, (num_envs, h.act_dim), "<f4", h, dev)
         self.obs = _wrap(torch, b.obs_dev, (num_envs, h.obs_dim), "<f4", h, dev)
         self.reward = _wrap(torch, b.reward_dev, (num_envs,), "<f4", h, dev)
-        self._done_u8 = _wrap(torch, b.done_dev, (num_envs,), "|u1", h, dev)
-        self._trunc_u8 = _wrap(torch, b.trunc_dev, (num_envs,), "|u1", h, dev)
+        # the library writes 0/1 bytes: exposed as torch.bool without a conversion kernel
+        self.done = _wrap(torch, b.done_dev, (num_envs,), "|b1", h, dev)
+        self.truncated = _wrap(torch, b.trunc_dev, (num_envs,), "|b1", h, dev)
         self.stats_tensor = _wrap(torch, b.stats_dev, (abi.N_STATS,), "<f8", h, dev)
         self._step_index = 0
 
@@ -84,7 +85,7 @@ class VectorEnv:
             aptr = actions.data_ptr()
         self.handle.step(aptr, self._stream())
         self._step_index += 1
-        return self.obs, self.reward, self._done_u8.bool(), {"TimeLimit.truncated": self._trunc_u8.bool()}
+        return self.obs, self.reward, self.done, {"TimeLimit.truncated": self.truncated}
 
     def sample_actions(self, step_index=None, out=None):
         """Synthetic U(-1,1) actions (Philox stream ACTION keyed by global env id and step) written on the device."""

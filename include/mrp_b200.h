@@ -112,11 +112,14 @@ int mrp_get_params(mrp_handle* h, mrp_params* p);
 /* copies stats_dev to host (synchronous); reset_after != 0 zeroes the device counters */
 int mrp_get_stats(mrp_handle* h, double* out_host, int32_t reset_after);
 
-/* Device timing of the step kernel alone (CUDA events recorded around it on the caller's stream), for
- * bench.py's roofline: enable, run steps, then read the accumulated milliseconds / launch count
+/* Device timing of the step's kernels alone (CUDA events recorded around them on the caller's stream), for
+ * bench.py's roofline: enable, run steps, then read the accumulated milliseconds / step count
  * (mrp_get_timing synchronises on the recorded events). */
 int mrp_set_timing(mrp_handle* h, int32_t enable);
 int mrp_get_timing(mrp_handle* h, double* total_ms, int64_t* count, int32_t reset_after);
+/* accumulated milliseconds of the five phase kernels of mrp_step, in launch order:
+ * k_pre, k_solve_vel, k_solve_pos, k_post, k_post_events */
+int mrp_get_phase_timing(mrp_handle* h, double* ms5, int32_t reset_after);
 
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t mrp_launch_count(mrp_handle* h);
