@@ -64,7 +64,14 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
     }
 }
 
-// phase 1 (lane per env): control + Collide + island order + constraint setup -> solver task
+// phase 0 (lane per env): broadphase half of Collide — classify every contact, queue the ones that need SAT
+MRP_HD void broad_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+    Env e(K, sm, ct, env, nullptr);
+    e.load();
+    e.broad_phase(env);
+}
+
+// phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
 MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
     Env e(K, sm, ct, env, nullptr);
     e.load();
@@ -195,6 +202,24 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimCons
     int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (env >= K.N) return;
     step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+}
+
+__global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (env >= K.N) return;
+    broad_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+}
+
+// SAT + clipping for the queued contacts: one lane per contact, grid-stride over the queue
+__global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const int count = K.cnt[CNT_NARROW];
+    if ((int64_t)blockIdx.x * kBlock >= count) return;
+    const float* ct = load_ctab(K, smem);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock)
+        narrow_item(K, ct, K.narrow_list[i]);
 }
 
 __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K) {
@@ -405,6 +430,7 @@ int mrp_destroy(mrp_handle* h) {
     DEV_FREE(h->K.task_T);
     DEV_FREE(h->K.task_off);
     DEV_FREE(h->K.toi_list);
+    DEV_FREE(h->K.narrow_list);
     delete h;
     return 0;
 }
@@ -456,6 +482,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * N);
     rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * N);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
         mrp_destroy(h);
@@ -482,7 +509,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
 #ifndef MRP_HOST_EMU
-    for (auto fn : {k_step, k_pre, k_post, k_post_events, k_reset_list})
+    for (auto fn : {k_step, k_broad, k_pre, k_post, k_post_events, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
@@ -618,6 +645,8 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 2;
     } else {
+        k_broad<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
         k_pre<<<grid, kBlock, h->smem_bytes, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][0], st);
         k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
@@ -627,7 +656,7 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         k_post<<<grid, kBlock, h->smem_bytes, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][3], st);
         k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
-        h->launches += 6;
+        h->launches += 8;
     }
     if (h->timing) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     if (K.auto_reset) {
@@ -642,6 +671,9 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         for (int64_t e = 0; e < K.N; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
     } else {
         // the same phases the device runs as kernels, executed as loops
+        for (int64_t e = 0; e < K.N; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
+        const int nnarrow = K.cnt[CNT_NARROW];
+        for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
         for (int64_t e = 0; e < K.N; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
         const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
         for (int i = 0; i < ntasks; ++i) {

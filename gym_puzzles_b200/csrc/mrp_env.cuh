@@ -330,7 +330,7 @@ struct Env : Sim {
     // integrate their positions right away.  Returns T.
     MRP_HD int pre_phase(const float* a) {
         if (K.v2) control_v2(a); else control_v0(a);
-        collide();
+        finish_collide();
         for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
         uint8_t island_of[kMaxC];
         const int T = build_islands(island_of);

@@ -79,10 +79,13 @@ struct SimConst {
     int32_t* task_T;      // [N] number of constraints of task i
     int32_t* task_off;    // [N] offset of task i's records in pool (floats)
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
+    uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * 32 + slot
 };
 // solver tasks predicted heavy (by W_HINT) are queued from slot 0 upwards, the others from slot N-1 downwards;
 // consumers take the heavy ones first so that long solves start early and short ones fill the tail
-enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_TASKS_LIGHT = 6, CNT_N = 8 };
+enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_TASKS_LIGHT = 6, CNT_NARROW = 7, CNT_N = 8 };
+// transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
+constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
 MRP_HD int task_slot(const SimConst& K, int i) {  // i-th task in consumption order -> slot
     const int nh = K.cnt[CNT_TASKS];
@@ -352,18 +355,42 @@ struct Sim {
     }
 
     // b2ContactManager::Collide (A.3): world-list order = newest slot first
-    MRP_HD void collide() {
+    // ---- Collide split over three kernels: k_broad classifies every contact (destroyed / provably empty / needs
+    // SAT), k_narrow runs SAT + clipping per queued contact with all lanes busy, k_pre replays the Begin/End events in
+    // contact-list order and compacts.  The three together are exactly collide() below.
+    MRP_HD void broad_phase(int64_t env) {
+        for (int k = nc - 1; k >= 0; --k) {
+            uint32_t m = meta[k] & 0x0fffffffu;
+            if ((m >> 16) & 1) m |= kMetaWas;
+            const int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+            if (!overlap(fat(fa), fat(fb))) {
+                m |= kMetaDead;
+            } else if (manifold_provably_empty(fa, fb, bA, bB, body_xf(bA), body_xf(bB))) {
+                m &= 0xfff0ffffu | kMetaWas;  // pointCount 0, not touching
+            } else {
+                K.narrow_list[atomic_add_i32(&K.cnt[CNT_NARROW], 1)] = (uint32_t)env * 32u + (uint32_t)k;
+            }
+            g(cw(k, 0)) = m;
+        }
+    }
+    MRP_HD void finish_collide() {
         uint32_t dead = 0;
         for (int k = nc - 1; k >= 0; --k) {
             uint32_t m = meta[k];
-            int fa = m & 0xff, fb = (m >> 8) & 0xff;
-            if (!overlap(fat(fa), fat(fb))) {
-                if ((m >> 16) & 1) contact_event(m, false);
+            const bool was = (m & kMetaWas) != 0, now = ((m >> 16) & 1) != 0;
+            if (m & kMetaDead) {
+                if (was) contact_event(m, false);
                 dead |= 1u << k;
                 continue;
             }
-            update_contact(k);
+            if (!was && now) contact_event(m, true);
+            if (was && !now) contact_event(m, false);
+            meta[k] = m & 0x0fffffffu;
         }
+        compact_contacts(dead);
+    }
+    MRP_HD void compact_contacts(uint32_t dead) {
         if (dead) {  // rare: compact, preserving order
             int dst = 0;
             for (int k = 0; k < nc; ++k) {
@@ -376,6 +403,20 @@ struct Sim {
             }
             nc = dst;
         }
+    }
+    MRP_HD void collide() {
+        uint32_t dead = 0;
+        for (int k = nc - 1; k >= 0; --k) {
+            uint32_t m = meta[k];
+            int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            if (!overlap(fat(fa), fat(fb))) {
+                if ((m >> 16) & 1) contact_event(m, false);
+                dead |= 1u << k;
+                continue;
+            }
+            update_contact(k);
+        }
+        compact_contacts(dead);
     }
 
     // ------------------------------------------------------------ broadphase (A.3)
@@ -1232,5 +1273,66 @@ struct Sim {
         return solve_toi(allow_events);
     }
 };
+
+// k_narrow: b2Contact::Update's geometric half for ONE queued contact (lane per contact, not per env).
+// Reads the two body transforms straight from the state words, runs SAT + clipping, matches impulses by feature id
+// and writes the manifold + flags back.  Events are replayed later, in contact order, by finish_collide().
+MRP_HD void narrow_item(const SimConst& K, const float* ct, uint32_t item) {
+    const int64_t env = item >> 5;
+    const int k = (int)(item & 31u);
+    uint32_t* G = K.S + env;
+    const int64_t N = K.N;
+    auto gw = [&](int w) -> uint32_t& { return G[(int64_t)w * N]; };
+    auto gfl = [&](int w) { union { uint32_t u; float f; } c; c.u = G[(int64_t)w * N]; return c.f; };
+    auto gsf = [&](int w, float v) { union { uint32_t u; float f; } c; c.f = v; G[(int64_t)w * N] = c.u; };
+    const int cwk = K.w_con + k * MRP_CONTACT_WORDS;
+    uint32_t m = gw(cwk);
+    const int fa = m & 0xff, fb = (m >> 8) & 0xff;
+    const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+    const int oldpc = (m >> 18) & 3;
+    auto xf_of = [&](int b) {
+        Xf x;
+        if (b < K.nb) {
+            const int w = K.w_body + kBodyWords * b;
+            x.q.s = gfl(w + 6); x.q.c = gfl(w + 7);
+            const V2 lc = b == 0 ? mk(K.blk_lcx, K.blk_lcy) : mk(K.ag_lcx, K.ag_lcy);
+            const V2 r = rmul(x.q, lc);
+            x.p = mk(gfl(w + 0) - r.x, gfl(w + 1) - r.y);
+        } else {
+            x.p = mk(ct[CT_WALLPOS + 2 * (b - K.nb)], ct[CT_WALLPOS + 2 * (b - K.nb) + 1]);
+            x.q.s = 0.0f; x.q.c = 1.0f;
+        }
+        return x;
+    };
+    Manifold man;
+    collide_polygons(&man, ct + CT_SHAPES + kShapeWords * (int)ct[CT_FIXSHAPE + fa], xf_of(bA),
+                     ct + CT_SHAPES + kShapeWords * (int)ct[CT_FIXSHAPE + fb], xf_of(bB));
+    const bool touching = man.pc > 0;
+    if (touching) {
+        const uint32_t okeys = oldpc ? gw(cwk + 1) : 0u;
+        float nI[2] = {0.0f, 0.0f}, tI[2] = {0.0f, 0.0f};
+        for (int i = 0; i < man.pc; ++i) {
+            for (int j = 0; j < oldpc; ++j) {
+                if (((okeys >> (16 * j)) & 0xffffu) == man.key[i]) {
+                    nI[i] = gfl(cwk + 8 + 4 * j);
+                    tI[i] = gfl(cwk + 9 + 4 * j);
+                    break;
+                }
+            }
+        }
+        gw(cwk + 1) = man.key[0] | ((man.pc > 1 ? man.key[1] : 0u) << 16);
+        gsf(cwk + 2, man.ln.x); gsf(cwk + 3, man.ln.y);
+        gsf(cwk + 4, man.lp.x); gsf(cwk + 5, man.lp.y);
+        for (int i = 0; i < man.pc; ++i) {
+            gsf(cwk + 6 + 4 * i, man.pt[i].x);
+            gsf(cwk + 7 + 4 * i, man.pt[i].y);
+            gsf(cwk + 8 + 4 * i, nI[i]);
+            gsf(cwk + 9 + 4 * i, tI[i]);
+        }
+    }
+    m = (m & 0xfff0ffffu) | ((touching ? 1u : 0u) << 16) | (((uint32_t)man.type & 1u) << 17) | ((uint32_t)man.pc << 18);
+    if (!touching) m &= ~(1u << 17);
+    gw(cwk) = m;
+}
 
 }  // namespace mrp
