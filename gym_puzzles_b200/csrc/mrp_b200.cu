@@ -86,22 +86,38 @@ struct VelTask {
     Sim::VelReg st;
     int T;
     uint32_t ops;
+    uint32_t bodies;  // dynamic bodies of this island
 };
+MRP_HD uint32_t task_body_mask(const SimConst& K, Sim& s, int T) {
+    uint32_t mask = 0;
+    for (int t = 0; t < T; ++t) {
+        const uint32_t vm = s.vmeta(t);
+        mask |= (1u << (vm & 15)) | (1u << ((vm >> 4) & 15));
+    }
+    return mask & ((1u << K.nb) - 1u);
+}
 MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
     const int64_t env = K.task_env[task];
     vt.T = K.task_T[task];
     s.G = K.S + env;
     s.vcp = K.pool + K.task_off[task];
+    vt.bodies = task_body_mask(K, s, vt.T);
     for (int b = 0; b < K.nb; ++b)
-        for (int f = 0; f < 6; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
+        if ((vt.bodies >> b) & 1)
+            for (int f = 0; f < 6; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
     for (int b = K.nb; b < K.nb + 4; ++b) { s.B(b, 3) = 0.0f; s.B(b, 4) = 0.0f; s.B(b, 5) = 0.0f; }
     vt.ops = 0;
     s.vr_begin(vt.st, vt.T);
 }
 MRP_HD void vel_task_end(const SimConst& K, Sim& s, VelTask& vt) {
-    s.g(W_HINT) = vt.ops;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&s.g(W_HINT), vt.ops);
+#else
+    s.g(W_HINT) += vt.ops;
+#endif
     s.store_impulses(vt.T);
     for (int b = 0; b < K.nb; ++b) {
+        if (!((vt.bodies >> b) & 1)) continue;
         s.integrate_position(b, K.h);
         for (int f = 0; f < 6; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
     }
@@ -110,14 +126,17 @@ MRP_HD void vel_task_end(const SimConst& K, Sim& s, VelTask& vt) {
 struct PosTask {
     Sim::PosState st;
     int T;
+    uint32_t bodies;
 };
 MRP_HD void pos_task_begin(const SimConst& K, Sim& s, PosTask& pt, int task) {
     const int64_t env = K.task_env[task];
     pt.T = K.task_T[task];
     s.G = K.S + env;
     s.vcp = K.pool + K.task_off[task];
+    pt.bodies = task_body_mask(K, s, pt.T);
     const float nan = s.__uint_as_float_(0x7fc00000u);
     for (int b = 0; b < K.nb; ++b) {
+        if (!((pt.bodies >> b) & 1)) continue;
         for (int f = 0; f < 3; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
         s.set_rot_cache(b, Rot{0.0f, 1.0f}, nan);  // no rotation known for the freshly integrated angle
     }
@@ -130,7 +149,8 @@ MRP_HD void pos_task_begin(const SimConst& K, Sim& s, PosTask& pt, int task) {
 }
 MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
     for (int b = 0; b < K.nb; ++b)
-        for (int f = 0; f < 3; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
+        if ((pt.bodies >> b) & 1)
+            for (int f = 0; f < 3; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
 }
 
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
@@ -478,9 +498,9 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * CNT_N);
     // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
     rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
-    rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * N * K.nb);  // at most one island per dynamic body
+    rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * N * K.nb);
+    rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * N * K.nb);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {

@@ -334,20 +334,32 @@ struct Env : Sim {
         for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
         uint8_t island_of[kMaxC];
         const int T = build_islands(island_of);
+        uint32_t in_island = 0;  // dynamic bodies that belong to an island with touching contacts
         if (T > 0) {
             const int off = atomic_add_i32(&K.cnt[CNT_POOL], T * VC_WORDS);
-            const int task = g(W_HINT) >= kHeavyHint ? atomic_add_i32(&K.cnt[CNT_TASKS], 1)
-                                                     : (int)(K.N - 1) - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT], 1);
-            K.task_env[task] = (int32_t)(G - K.S);
-            K.task_T[task] = T;
-            K.task_off[task] = off;
             vcp = K.pool + off;
             init_constraints(T, island_of, true);
             warm_start(T);
-        } else {
-            for (int b = 0; b < K.nb; ++b) integrate_position(b, K.h);
-            g(W_HINT) = 0;
+            // one solver task per island (its constraint records are contiguous in solver order)
+            const bool heavy = g(W_HINT) >= kHeavyHint;
+            const int cap = (int)K.N * K.nb;
+            for (int start = 0; start < T;) {
+                int end = start + 1;
+                while (end < T && island_of[end] == island_of[start]) ++end;
+                const int task = heavy ? atomic_add_i32(&K.cnt[CNT_TASKS], 1) : cap - 1 - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT], 1);
+                K.task_env[task] = (int32_t)(G - K.S);
+                K.task_T[task] = end - start;
+                K.task_off[task] = off + start * VC_WORDS;
+                start = end;
+            }
+            for (int t = 0; t < T; ++t) {
+                const uint32_t m = meta[order[t]];
+                in_island |= (1u << ((m >> 20) & 15)) | (1u << ((m >> 24) & 15));
+            }
         }
+        g(W_HINT) = 0;  // solver tasks of this env add their operation counts
+        for (int b = 0; b < K.nb; ++b)
+            if (!((in_island >> b) & 1)) integrate_position(b, K.h);
         // hand-off to the solver / post kernels: poses + velocities, pre-step pose, contact list
         g(W_NC) = (uint32_t)nc;
         g(W_GOALC) = goalc;

@@ -87,9 +87,9 @@ enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
-MRP_HD int task_slot(const SimConst& K, int i) {  // i-th task in consumption order -> slot
+MRP_HD int task_slot(const SimConst& K, int i) {  // i-th task in consumption order -> slot (arrays hold N * nb slots)
     const int nh = K.cnt[CNT_TASKS];
-    return i < nh ? i : (int)(K.N - 1) - (i - nh);
+    return i < nh ? i : (int)K.N * K.nb - 1 - (i - nh);
 }
 
 MRP_HD int atomic_add_i32(int32_t* p, int v) {
