@@ -66,14 +66,14 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
 
 // phase 0 (lane per env): broadphase half of Collide — classify every contact, queue the ones that need SAT
 MRP_HD void broad_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    Env e(K, sm, ct, env, nullptr);
+    Env e(K, sm, ct, env, nullptr, 10);
     e.load();
     e.broad_phase(env);
 }
 
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
 MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    Env e(K, sm, ct, env, nullptr);
+    Env e(K, sm, ct, env, nullptr, 13);
     e.load();
     float a[3 * MRP_MAX_AGENTS];
     const float* arow = K.act + env * K.act_dim;
@@ -362,7 +362,7 @@ struct mrp_handle {
     float* ctab_dev;
     float* act_dev;
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
-    size_t smem_vel, smem_pos;
+    size_t smem_vel, smem_pos, smem_broad, smem_pre;
     int solver_ctas;  // persistent solver CTAs per SM
     int64_t launches;
     size_t smem_bytes;
@@ -526,10 +526,14 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
         free(row);
     }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
+    h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 24 + 4 * K.ndynfix) * kBlock);
+    h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
 #ifndef MRP_HOST_EMU
-    for (auto fn : {k_step, k_broad, k_pre, k_post, k_post_events, k_reset_list})
+    cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
+    cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
+    for (auto fn : {k_step, k_post, k_post_events, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
@@ -665,9 +669,9 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 2;
     } else {
-        k_broad<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
         k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
-        k_pre<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][0], st);
         k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][1], st);

@@ -283,7 +283,7 @@ struct Env : Sim {
             V2 c = xmul(xf, localCenter(b));
             B(b, 0) = c.x; B(b, 1) = c.y; B(b, 2) = ang;
             B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
-            BX(b, 9) = xf.q.s; BX(b, 10) = xf.q.c; BX(b, 11) = px; BX(b, 12) = py;
+            BX(b, 6) = xf.q.s; BX(b, 7) = xf.q.c; BX(b, 8) = px; BX(b, 9) = py;
             set_rot_cache(b, xf.q, ang);
             // proxies: fat AABB = tight AABB at creation +- 0.1 (b2DynamicTree::CreateProxy)
             int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
@@ -331,7 +331,11 @@ struct Env : Sim {
     MRP_HD int pre_phase(const float* a) {
         if (K.v2) control_v2(a); else control_v0(a);
         finish_collide();
-        for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+        // pose at the start of the step, for k_post's SynchronizeFixtures / TOI sweeps
+        for (int b = 0; b < K.nb; ++b) {
+            const int w = K.w_body + kBodyWords * b;
+            gsf(w + 8, B(b, 0)); gsf(w + 9, B(b, 1)); gsf(w + 10, B(b, 2));
+        }
         uint8_t island_of[kMaxC];
         const int T = build_islands(island_of);
         uint32_t in_island = 0;  // dynamic bodies that belong to an island with touching contacts
@@ -366,7 +370,6 @@ struct Env : Sim {
         for (int b = 0; b < K.nb; ++b) {
             const int w = K.w_body + kBodyWords * b;
             for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
-            gsf(w + 8, BX(b, 6)); gsf(w + 9, BX(b, 7)); gsf(w + 10, BX(b, 8));
         }
         for (int k = 0; k < nc; ++k) g(cw(k, 0)) = meta[k];
         return T;
@@ -375,11 +378,7 @@ struct Env : Sim {
     // Returns false (nothing stored) when a TOI event is needed and allow_events is false.
     MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events) {
         // load(): q/p are still the pre-step transform; c0/a0 from the hand-off words
-        for (int b = 0; b < K.nb; ++b) {
-            const int w = K.w_body + kBodyWords * b;
-            BX(b, 6) = gf(w + 8); BX(b, 7) = gf(w + 9); BX(b, 8) = gf(w + 10);
-            set_rot_cache(b, Rot{BX(b, 9), BX(b, 10)}, BX(b, 8));
-        }
+        for (int b = 0; b < K.nb; ++b) set_rot_cache(b, Rot{BX(b, 6), BX(b, 7)}, BX(b, 15));
         if (!post_solve(allow_events)) return false;
         *done_env = post_step(obs, reward);
         return true;

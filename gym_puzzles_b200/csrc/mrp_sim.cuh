@@ -9,6 +9,9 @@
 // contact list = reverse creation order sorted by proxy-id pair, DFS islands over
 // newest-first edges, warm starting, block solver, position solver, TOI sub-steps).
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "../../include/mrp_b200.h"
 #include "mrp_collide.cuh"
 
@@ -123,7 +126,9 @@ struct Sim {
     // per-lane scratch (local memory where dynamically indexed)
     uint32_t meta[kMaxC];  // fa | fb<<8 | touching<<16 | type<<17 | pc<<18 | bA<<20 | bB<<24
     float* vcp;            // solver constraint records: a lane-local array (fused path) or a slot of the HBM task pool
-    int fdyn;              // shared-memory words per dynamic body (17 in the per-env kernels, 6 in the solver kernels)
+    int fdyn;              // shared-memory words per dynamic body
+    int qoff;              // first of the three rotation-cache words inside a body slot
+    int fa_off;            // first shared-memory word of the fat AABBs
     uint8_t order[kMaxC];
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
@@ -133,8 +138,11 @@ struct Sim {
     uint32_t goalc;
     uint32_t overflow;
 
+    // fdyn_: 17 full (k_post, fused, reset) | 13 k_pre (no pre-step pose / alpha0, no fat AABBs) | 10 k_broad (pose only,
+    // with fat AABBs, no rotation cache) | 9 position solver (pose + cache) | 6 velocity solver
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
-        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_), nc(0), goalc(0),
+        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
+          qoff(fdyn_ >= 13 ? 10 : (fdyn_ == 9 ? 6 : -1)), fa_off((fdyn_ == 17 || fdyn_ == 10) ? k.nb * fdyn_ + 24 : -1), nc(0), goalc(0),
           overflow(0) {}
 
     // ------------------------------------------------------------ memory helpers
@@ -156,25 +164,37 @@ struct Sim {
     static MRP_HD uint64_t __double_as_ull_(double f) { union { uint64_t u; double f; } c; c.f = f; return c.u; }
     MRP_HD int cw(int k, int j) const { return K.w_con + k * MRP_CONTACT_WORDS + j; }
 
-    // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 c0x 7 c0y 8 a0 9 qs 10 qc 11 px 12 py 13 alpha0
-    // 14 cache.s 15 cache.c 16 cache angle (dynamic bodies): last Rot evaluated for this body and the angle it belongs to
+    // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 qs 7 qc 8 px 9 py | 10 cache.s 11 cache.c
+    // 12 cache angle (last Rot evaluated for this body and the angle it belongs to) | 13 c0x 14 c0y 15 a0 16 alpha0.
+    // Kernels that do not need the tail allocate fewer words per body (fdyn): k_broad 10, k_pre 13, k_post 17;
+    // the solver kernels use 6 (velocities) and 9 (pose + cache at qoff = 6).
     // body-major, lane-strided: one base computation per body, then compile-time field offsets
     MRP_HD float* bp(int b) { return sm + (b < K.nb ? b * fdyn : K.nb * fdyn + (b - K.nb) * 6) * MRP_SS; }
+#ifdef MRP_HOST_EMU
+    // the host build checks that a kernel never touches a body word its shared-memory layout does not have
+    float& B(int b, int f) {
+        if (b < K.nb ? f >= fdyn : f >= 6) { fprintf(stderr, "smem layout violation: body %d field %d fdyn %d\n", b, f, fdyn); abort(); }
+        return bp(b)[f * MRP_SS];
+    }
+    float& BX(int b, int f) { return B(b, f); }
+#else
     MRP_HD float& B(int b, int f) { return bp(b)[f * MRP_SS]; }
     MRP_HD float& BX(int b, int f) { return bp(b)[f * MRP_SS]; }
-    MRP_HD float& FA(int fx, int j) { return sm[(K.nb * kDynFields + 24 + fx * 4 + j) * MRP_SS]; }
+#endif
+    MRP_HD float& FA(int fx, int j) { return sm[(fa_off + fx * 4 + j) * MRP_SS]; }
 
     // b2Rot::Set(angle of body b) through a one-entry cache: sin/cos are pure functions of the float angle, so
     // reusing the last evaluation when the angle is bit-identical cannot change results (robots with invI = 0
     // never rotate inside the position solver; the block only when an impulse acts on it)
     MRP_HD void set_rot_cache(int b, Rot q, float angle) {
-        float* const c = bp(b) + (fdyn - 3) * MRP_SS;
+        if (qoff < 0) return;
+        float* const c = bp(b) + qoff * MRP_SS;
         c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
     }
     MRP_HD Rot body_rot(int b, float angle) {
         Rot q;
         if (b >= K.nb) { q.s = 0.0f; q.c = 1.0f; return q; }
-        float* const c = bp(b) + (fdyn - 3) * MRP_SS;  // the last three words of the body slot
+        float* const c = bp(b) + qoff * MRP_SS;
         if (c[2 * MRP_SS] == angle) { q.s = c[0]; q.c = c[MRP_SS]; return q; }
         q = rot_set(angle);
         c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
@@ -190,9 +210,9 @@ struct Sim {
     MRP_HD Xf body_xf(int b) {
         Xf x;
         if (b < K.nb) {
-            x.p = mk(BX(b, 11), BX(b, 12));
-            x.q.s = BX(b, 9);
-            x.q.c = BX(b, 10);
+            x.p = mk(BX(b, 8), BX(b, 9));
+            x.q.s = BX(b, 6);
+            x.q.c = BX(b, 7);
         } else {
             x.p = mk(B(b, 0), B(b, 1));
             x.q.s = 0.0f;
@@ -203,10 +223,10 @@ struct Sim {
     MRP_HD void sync_transform(int b) {  // b2Body::SynchronizeTransform
         Rot q = body_rot(b, B(b, 2));
         V2 r = rmul(q, localCenter(b));
-        BX(b, 9) = q.s;
-        BX(b, 10) = q.c;
-        BX(b, 11) = B(b, 0) - r.x;
-        BX(b, 12) = B(b, 1) - r.y;
+        BX(b, 6) = q.s;
+        BX(b, 7) = q.c;
+        BX(b, 8) = B(b, 0) - r.x;
+        BX(b, 9) = B(b, 1) - r.y;
     }
     MRP_HD int fix_body(int f) const { return (int)ct[CT_FIXBODY + f]; }
     MRP_HD const float* fix_shape(int f) const { return ct + CT_SHAPES + kShapeWords * (int)ct[CT_FIXSHAPE + f]; }
@@ -220,21 +240,28 @@ struct Sim {
         }
         return b;
     }
-    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, 13) : wallAlpha0[b - K.nb]; }
+    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, 16) : wallAlpha0[b - K.nb]; }
 
     // ------------------------------------------------------------ state load / store
+    // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
+    // before their results are consumed, so each batch costs one memory round trip instead of one per word.
     MRP_HD void load() {
         nc = (int)g(W_NC);
         goalc = g(W_GOALC);
         for (int b = 0; b < K.nb; ++b) {
-            int w = K.w_body + kBodyWords * b;
-            for (int f = 0; f < 6; ++f) B(b, f) = gf(w + f);
-            BX(b, 9) = gf(w + 6);
-            BX(b, 10) = gf(w + 7);
-            set_rot_cache(b, Rot{BX(b, 9), BX(b, 10)}, B(b, 2));
-            V2 r = rmul(Rot{BX(b, 9), BX(b, 10)}, localCenter(b));
-            BX(b, 11) = B(b, 0) - r.x;
-            BX(b, 12) = B(b, 1) - r.y;
+            const int w = K.w_body + kBodyWords * b;
+            float r[kBodyWords];
+#pragma unroll
+            for (int i = 0; i < kBodyWords; ++i) r[i] = gf(w + i);
+            float* p = bp(b);
+#pragma unroll
+            for (int f = 0; f < 6; ++f) p[f * MRP_SS] = r[f];
+            p[6 * MRP_SS] = r[6]; p[7 * MRP_SS] = r[7];
+            if (fdyn > 13) { p[13 * MRP_SS] = r[8]; p[14 * MRP_SS] = r[9]; p[15 * MRP_SS] = r[10]; }  // pre-step pose (k_post)
+            set_rot_cache(b, Rot{r[6], r[7]}, r[2]);
+            V2 rc = rmul(Rot{r[6], r[7]}, localCenter(b));
+            p[8 * MRP_SS] = r[0] - rc.x;
+            p[9 * MRP_SS] = r[1] - rc.y;
         }
         for (int k = 0; k < 4; ++k) {
             int b = K.nb + k;
@@ -242,9 +269,25 @@ struct Sim {
             B(b, 1) = ct[CT_WALLPOS + 2 * k + 1];
             B(b, 2) = 0.0f; B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
         }
-        for (int f = 0; f < K.ndynfix; ++f)
-            for (int j = 0; j < 4; ++j) FA(f, j) = gf(K.w_aabb + 4 * f + j);
-        for (int k = 0; k < nc; ++k) meta[k] = g(cw(k, 0));
+        for (int f = 0; fa_off >= 0 && f < K.ndynfix; f += 2) {
+            float r[8];
+            const bool two = f + 1 < K.ndynfix;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = (i < 4 || two) ? gf(K.w_aabb + 4 * f + i) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) FA(f, i) = r[i];
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) FA(f + 1, i) = r[4 + i];
+            }
+        }
+        for (int k = 0; k < nc; k += 4) {
+            uint32_t r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = k + i < nc ? g(cw(k + i, 0)) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (k + i < nc) meta[k + i] = r[i];
+        }
     }
     MRP_HD void store() {
         g(W_NC) = (uint32_t)nc;
@@ -252,8 +295,8 @@ struct Sim {
         for (int b = 0; b < K.nb; ++b) {
             int w = K.w_body + kBodyWords * b;
             for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
-            gsf(w + 6, BX(b, 9));
-            gsf(w + 7, BX(b, 10));
+            gsf(w + 6, BX(b, 6));
+            gsf(w + 7, BX(b, 7));
         }
         for (int f = 0; f < K.ndynfix; ++f)
             for (int j = 0; j < 4; ++j) gsf(K.w_aabb + 4 * f + j, FA(f, j));
@@ -512,15 +555,19 @@ struct Sim {
             int pc = (m >> 18) & 3, type = (m >> 17) & 1;
             int fa = m & 0xff, fb = (m >> 8) & 0xff;
             V(t, VC_FRIC) = sqrtf(ct[CT_FIXFRIC + fa] * ct[CT_FIXFRIC + fb]);
-            V2 ln = mk(gf(cw(k, 2)), gf(cw(k, 3))), lp = mk(gf(cw(k, 4)), gf(cw(k, 5)));
+            float mw[12];  // manifold words 2..13 of the contact slot, fetched as one batch of independent loads
+#pragma unroll
+            for (int i = 0; i < 12; ++i) mw[i] = (i < 4 + 4 * pc) ? gf(cw(k, 2 + i)) : 0.0f;
+            V2 ln = mk(mw[0], mw[1]), lp = mk(mw[2], mw[3]);
             V(t, VC_LNX) = ln.x; V(t, VC_LNY) = ln.y; V(t, VC_LPX) = lp.x; V(t, VC_LPY) = lp.y;
             V2 lpt[2];
             float nI[2], tI[2];
+#pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j < pc) {
-                    lpt[j] = mk(gf(cw(k, 6 + 4 * j)), gf(cw(k, 7 + 4 * j)));
-                    nI[j] = warm ? gf(cw(k, 8 + 4 * j)) : 0.0f;
-                    tI[j] = warm ? gf(cw(k, 9 + 4 * j)) : 0.0f;
+                    lpt[j] = mk(mw[4 + 4 * j], mw[5 + 4 * j]);
+                    nI[j] = warm ? mw[6 + 4 * j] : 0.0f;
+                    tI[j] = warm ? mw[7 + 4 * j] : 0.0f;
                 } else {
                     lpt[j] = mk(0.0f, 0.0f); nI[j] = 0.0f; tI[j] = 0.0f;
                 }
@@ -1049,8 +1096,8 @@ struct Sim {
         Sweep s;
         if (b < K.nb) {
             s.lc = localCenter(b);
-            s.c0 = mk(BX(b, 6), BX(b, 7));
-            s.a0 = BX(b, 8);
+            s.c0 = mk(BX(b, 13), BX(b, 14));
+            s.a0 = BX(b, 15);
             s.c = mk(B(b, 0), B(b, 1));
             s.a = B(b, 2);
         } else {
@@ -1066,16 +1113,16 @@ struct Sim {
         float& al0 = alpha0(b);
         if (b < K.nb) {
             float beta = (alpha - al0) / (1.0f - al0);
-            BX(b, 6) += beta * (B(b, 0) - BX(b, 6));
-            BX(b, 7) += beta * (B(b, 1) - BX(b, 7));
-            BX(b, 8) += beta * (B(b, 2) - BX(b, 8));
+            BX(b, 13) += beta * (B(b, 0) - BX(b, 13));
+            BX(b, 14) += beta * (B(b, 1) - BX(b, 14));
+            BX(b, 15) += beta * (B(b, 2) - BX(b, 15));
         }
         al0 = alpha;
     }
     MRP_HD void body_advance(int b, float alpha) {  // b2Body::Advance
         sweep_advance(b, alpha);
         if (b < K.nb) {
-            B(b, 0) = BX(b, 6); B(b, 1) = BX(b, 7); B(b, 2) = BX(b, 8);
+            B(b, 0) = BX(b, 13); B(b, 1) = BX(b, 14); B(b, 2) = BX(b, 15);
             sync_transform(b);
         }
     }
@@ -1089,7 +1136,7 @@ struct Sim {
         for (int s = 0; s < 2; ++s) {
             int b = two[s];
             if (b < K.nb) {
-                bk[s][0] = BX(b, 6); bk[s][1] = BX(b, 7); bk[s][2] = BX(b, 8);
+                bk[s][0] = BX(b, 13); bk[s][1] = BX(b, 14); bk[s][2] = BX(b, 15);
                 bk[s][3] = B(b, 0); bk[s][4] = B(b, 1); bk[s][5] = B(b, 2);
             }
             bk[s][6] = alpha0(b);
@@ -1105,7 +1152,7 @@ struct Sim {
             for (int s = 0; s < 2; ++s) {
                 int b = two[s];
                 if (b < K.nb) {
-                    BX(b, 6) = bk[s][0]; BX(b, 7) = bk[s][1]; BX(b, 8) = bk[s][2];
+                    BX(b, 13) = bk[s][0]; BX(b, 14) = bk[s][1]; BX(b, 15) = bk[s][2];
                     B(b, 0) = bk[s][3]; B(b, 1) = bk[s][4]; B(b, 2) = bk[s][5];
                     sync_transform(b);
                 }
@@ -1145,7 +1192,7 @@ struct Sim {
         solve_position(T, 20, bA, bB);
         for (int s = 0; s < 2; ++s) {
             int b = two[s];
-            if (b < K.nb) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+            if (b < K.nb) { BX(b, 13) = B(b, 0); BX(b, 14) = B(b, 1); BX(b, 15) = B(b, 2); }
         }
         init_constraints(T, nullptr, false);
         solve_velocity(T, 180);
@@ -1158,8 +1205,8 @@ struct Sim {
         for (int b = 0; b < K.nb; ++b) {
             if (!((bflag >> b) & 1)) continue;
             Xf xf1;
-            xf1.q = rot_set(BX(b, 8));
-            xf1.p = mk(BX(b, 6), BX(b, 7)) - rmul(xf1.q, localCenter(b));
+            xf1.q = rot_set(BX(b, 15));
+            xf1.p = mk(BX(b, 13), BX(b, 14)) - rmul(xf1.q, localCenter(b));
             moved |= synchronize_fixtures(b, xf1);
             for (int k = 0; k < nc; ++k) {
                 uint32_t mk_ = meta[k];
@@ -1178,7 +1225,7 @@ struct Sim {
     // between bounds that distance from below along the wall's axis-aligned faces; when even this bound stays above
     // 0.00625 (+ guard) the call is skipped and alpha = 1, exactly what the full algorithm would return.
     MRP_HD bool toi_provably_one(int f, int b, int wall) {
-        const float da = B(b, 2) - BX(b, 8);
+        const float da = B(b, 2) - BX(b, 15);
         if (!(fabsf(da) < 0.5f)) return false;
         const float* sx = shape_x(f);
         const V2 lc = localCenter(b);
@@ -1201,7 +1248,7 @@ struct Sim {
             if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc |= 1u << k;
         }
         if (!wallc) return true;
-        for (int b = 0; b < K.nb; ++b) BX(b, 13) = 0.0f;
+        for (int b = 0; b < K.nb; ++b) BX(b, 16) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
         uint32_t toiFlag = 0, enabled = 0xffffffffu;
@@ -1253,7 +1300,7 @@ struct Sim {
         if (new_fixtures) find_new_contacts(0xffffffffu);
         collide();
         // xf1 of SynchronizeFixtures == the transform the step started with (c0, a0 are set from c, a)
-        for (int b = 0; b < K.nb; ++b) { BX(b, 6) = B(b, 0); BX(b, 7) = B(b, 1); BX(b, 8) = B(b, 2); }
+        for (int b = 0; b < K.nb; ++b) { BX(b, 13) = B(b, 0); BX(b, 14) = B(b, 1); BX(b, 15) = B(b, 2); }
         solve_islands();
         post_solve(true);
     }
@@ -1263,9 +1310,9 @@ struct Sim {
         for (int b = K.nb - 1; b >= 0; --b) {
             // xf1 = transform at (c0, a0); its rotation is the one the step started with
             Xf xf1;
-            xf1.q.s = BX(b, 9);
-            xf1.q.c = BX(b, 10);
-            xf1.p = mk(BX(b, 6), BX(b, 7)) - rmul(xf1.q, localCenter(b));
+            xf1.q.s = BX(b, 6);
+            xf1.q.c = BX(b, 7);
+            xf1.p = mk(BX(b, 13), BX(b, 14)) - rmul(xf1.q, localCenter(b));
             sync_transform(b);
             moved |= synchronize_fixtures(b, xf1);
         }
