@@ -156,7 +156,7 @@ MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
 // false an env whose TOI scan finds an event is queued for the event pass and left untouched.
 MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local) {
-    Env e(K, sm, ct, env, vc_local);
+    Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 14);
     e.load();
     double r;
     bool d;
@@ -362,7 +362,7 @@ struct mrp_handle {
     float* ctab_dev;
     float* act_dev;
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
-    size_t smem_vel, smem_pos, smem_broad, smem_pre;
+    size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post;
     int solver_ctas;  // persistent solver CTAs per SM
     int64_t launches;
     size_t smem_bytes;
@@ -527,13 +527,15 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
     h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 24 + 4 * K.ndynfix) * kBlock);
+    h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(14 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
 #ifndef MRP_HOST_EMU
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
-    for (auto fn : {k_step, k_post, k_post_events, k_reset_list})
+    cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
+    for (auto fn : {k_step, k_post_events, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
@@ -677,7 +679,7 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][1], st);
         k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][2], st);
-        k_post<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        k_post<<<grid, kBlock, h->smem_post, st>>>(K);
         if (h->timing) cudaEventRecord(h->evk[h->ev_n][3], st);
         k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 8;

@@ -378,7 +378,7 @@ struct Env : Sim {
     // Returns false (nothing stored) when a TOI event is needed and allow_events is false.
     MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events) {
         // load(): q/p are still the pre-step transform; c0/a0 from the hand-off words
-        for (int b = 0; b < K.nb; ++b) set_rot_cache(b, Rot{BX(b, 6), BX(b, 7)}, BX(b, 15));
+        for (int b = 0; b < K.nb; ++b) set_rot_cache(b, Rot{BX(b, 6), BX(b, 7)}, BX(b, c0f + 2));
         if (!post_solve(allow_events)) return false;
         *done_env = post_step(obs, reward);
         return true;

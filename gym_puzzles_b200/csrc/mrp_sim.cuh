@@ -129,6 +129,8 @@ struct Sim {
     int fdyn;              // shared-memory words per dynamic body
     int qoff;              // first of the three rotation-cache words inside a body slot
     int fa_off;            // first shared-memory word of the fat AABBs
+    int c0f;               // first of the four words {c0x, c0y, a0, alpha0} inside a body slot (-1: absent)
+    int wall_off;          // first shared-memory word of the wall slots (-1: absent, walls are read from the constant table)
     uint8_t order[kMaxC];
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
@@ -138,11 +140,16 @@ struct Sim {
     uint32_t goalc;
     uint32_t overflow;
 
-    // fdyn_: 17 full (k_post, fused, reset) | 13 k_pre (no pre-step pose / alpha0, no fat AABBs) | 10 k_broad (pose only,
-    // with fat AABBs, no rotation cache) | 9 position solver (pose + cache) | 6 velocity solver
+    // layouts (words per dynamic body):
+    //   17 full: pose/vel 0-5, q 6-7, p 8-9, cache 10-12, c0/a0/alpha0 13-16, walls, fat AABBs   (fused step, reset, k_post_events)
+    //   14 k_post: 0-9, c0/a0/alpha0 10-13, fat AABBs, no cache, no wall slots
+    //   13 k_pre: 0-9, cache 10-12, walls                     10 k_broad: 0-9, fat AABBs
+    //    9 position solver: 0-5, cache 6-8, walls               6 velocity solver: 0-5, walls
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
         : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
-          qoff(fdyn_ >= 13 ? 10 : (fdyn_ == 9 ? 6 : -1)), fa_off((fdyn_ == 17 || fdyn_ == 10) ? k.nb * fdyn_ + 24 : -1), nc(0), goalc(0),
+          qoff(fdyn_ == 17 || fdyn_ == 13 ? 10 : (fdyn_ == 9 ? 6 : -1)),
+          fa_off(fdyn_ == 17 ? k.nb * 17 + 24 : (fdyn_ == 14 ? k.nb * 14 : (fdyn_ == 10 ? k.nb * 10 : -1))),
+          c0f(fdyn_ == 17 ? 13 : (fdyn_ == 14 ? 10 : -1)), wall_off(fdyn_ == 14 || fdyn_ == 10 ? -1 : k.nb * fdyn_), nc(0), goalc(0),
           overflow(0) {}
 
     // ------------------------------------------------------------ memory helpers
@@ -169,11 +176,12 @@ struct Sim {
     // Kernels that do not need the tail allocate fewer words per body (fdyn): k_broad 10, k_pre 13, k_post 17;
     // the solver kernels use 6 (velocities) and 9 (pose + cache at qoff = 6).
     // body-major, lane-strided: one base computation per body, then compile-time field offsets
-    MRP_HD float* bp(int b) { return sm + (b < K.nb ? b * fdyn : K.nb * fdyn + (b - K.nb) * 6) * MRP_SS; }
+    MRP_HD float* bp(int b) { return sm + (b < K.nb ? b * fdyn : wall_off + (b - K.nb) * 6) * MRP_SS; }
+    MRP_HD V2 wall_pos(int b) const { return mk(ct[CT_WALLPOS + 2 * (b - K.nb)], ct[CT_WALLPOS + 2 * (b - K.nb) + 1]); }
 #ifdef MRP_HOST_EMU
     // the host build checks that a kernel never touches a body word its shared-memory layout does not have
     float& B(int b, int f) {
-        if (b < K.nb ? f >= fdyn : f >= 6) { fprintf(stderr, "smem layout violation: body %d field %d fdyn %d\n", b, f, fdyn); abort(); }
+        if (b < K.nb ? f >= fdyn : (f >= 6 || wall_off < 0)) { fprintf(stderr, "smem layout violation: body %d field %d fdyn %d\n", b, f, fdyn); abort(); }
         return bp(b)[f * MRP_SS];
     }
     float& BX(int b, int f) { return B(b, f); }
@@ -194,6 +202,7 @@ struct Sim {
     MRP_HD Rot body_rot(int b, float angle) {
         Rot q;
         if (b >= K.nb) { q.s = 0.0f; q.c = 1.0f; return q; }
+        if (qoff < 0) return rot_set(angle);
         float* const c = bp(b) + qoff * MRP_SS;
         if (c[2 * MRP_SS] == angle) { q.s = c[0]; q.c = c[MRP_SS]; return q; }
         q = rot_set(angle);
@@ -214,7 +223,7 @@ struct Sim {
             x.q.s = BX(b, 6);
             x.q.c = BX(b, 7);
         } else {
-            x.p = mk(B(b, 0), B(b, 1));
+            x.p = wall_pos(b);
             x.q.s = 0.0f;
             x.q.c = 1.0f;
         }
@@ -240,7 +249,7 @@ struct Sim {
         }
         return b;
     }
-    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, 16) : wallAlpha0[b - K.nb]; }
+    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, c0f + 3) : wallAlpha0[b - K.nb]; }
 
     // ------------------------------------------------------------ state load / store
     // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
@@ -257,13 +266,13 @@ struct Sim {
 #pragma unroll
             for (int f = 0; f < 6; ++f) p[f * MRP_SS] = r[f];
             p[6 * MRP_SS] = r[6]; p[7 * MRP_SS] = r[7];
-            if (fdyn > 13) { p[13 * MRP_SS] = r[8]; p[14 * MRP_SS] = r[9]; p[15 * MRP_SS] = r[10]; }  // pre-step pose (k_post)
+            if (c0f >= 0) { p[c0f * MRP_SS] = r[8]; p[(c0f + 1) * MRP_SS] = r[9]; p[(c0f + 2) * MRP_SS] = r[10]; }  // pre-step pose
             set_rot_cache(b, Rot{r[6], r[7]}, r[2]);
             V2 rc = rmul(Rot{r[6], r[7]}, localCenter(b));
             p[8 * MRP_SS] = r[0] - rc.x;
             p[9 * MRP_SS] = r[1] - rc.y;
         }
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; wall_off >= 0 && k < 4; ++k) {
             int b = K.nb + k;
             B(b, 0) = ct[CT_WALLPOS + 2 * k];
             B(b, 1) = ct[CT_WALLPOS + 2 * k + 1];
@@ -1096,13 +1105,13 @@ struct Sim {
         Sweep s;
         if (b < K.nb) {
             s.lc = localCenter(b);
-            s.c0 = mk(BX(b, 13), BX(b, 14));
-            s.a0 = BX(b, 15);
+            s.c0 = mk(BX(b, c0f), BX(b, c0f + 1));
+            s.a0 = BX(b, c0f + 2);
             s.c = mk(B(b, 0), B(b, 1));
             s.a = B(b, 2);
         } else {
             s.lc = mk(0.0f, 0.0f);
-            s.c0 = mk(B(b, 0), B(b, 1));
+            s.c0 = wall_pos(b);
             s.c = s.c0;
             s.a0 = 0.0f;
             s.a = 0.0f;
@@ -1113,16 +1122,16 @@ struct Sim {
         float& al0 = alpha0(b);
         if (b < K.nb) {
             float beta = (alpha - al0) / (1.0f - al0);
-            BX(b, 13) += beta * (B(b, 0) - BX(b, 13));
-            BX(b, 14) += beta * (B(b, 1) - BX(b, 14));
-            BX(b, 15) += beta * (B(b, 2) - BX(b, 15));
+            BX(b, c0f) += beta * (B(b, 0) - BX(b, c0f));
+            BX(b, c0f + 1) += beta * (B(b, 1) - BX(b, c0f + 1));
+            BX(b, c0f + 2) += beta * (B(b, 2) - BX(b, c0f + 2));
         }
         al0 = alpha;
     }
     MRP_HD void body_advance(int b, float alpha) {  // b2Body::Advance
         sweep_advance(b, alpha);
         if (b < K.nb) {
-            B(b, 0) = BX(b, 13); B(b, 1) = BX(b, 14); B(b, 2) = BX(b, 15);
+            B(b, 0) = BX(b, c0f); B(b, 1) = BX(b, c0f + 1); B(b, 2) = BX(b, c0f + 2);
             sync_transform(b);
         }
     }
@@ -1136,7 +1145,7 @@ struct Sim {
         for (int s = 0; s < 2; ++s) {
             int b = two[s];
             if (b < K.nb) {
-                bk[s][0] = BX(b, 13); bk[s][1] = BX(b, 14); bk[s][2] = BX(b, 15);
+                bk[s][0] = BX(b, c0f); bk[s][1] = BX(b, c0f + 1); bk[s][2] = BX(b, c0f + 2);
                 bk[s][3] = B(b, 0); bk[s][4] = B(b, 1); bk[s][5] = B(b, 2);
             }
             bk[s][6] = alpha0(b);
@@ -1152,7 +1161,7 @@ struct Sim {
             for (int s = 0; s < 2; ++s) {
                 int b = two[s];
                 if (b < K.nb) {
-                    BX(b, 13) = bk[s][0]; BX(b, 14) = bk[s][1]; BX(b, 15) = bk[s][2];
+                    BX(b, c0f) = bk[s][0]; BX(b, c0f + 1) = bk[s][1]; BX(b, c0f + 2) = bk[s][2];
                     B(b, 0) = bk[s][3]; B(b, 1) = bk[s][4]; B(b, 2) = bk[s][5];
                     sync_transform(b);
                 }
@@ -1192,7 +1201,7 @@ struct Sim {
         solve_position(T, 20, bA, bB);
         for (int s = 0; s < 2; ++s) {
             int b = two[s];
-            if (b < K.nb) { BX(b, 13) = B(b, 0); BX(b, 14) = B(b, 1); BX(b, 15) = B(b, 2); }
+            if (b < K.nb) { BX(b, c0f) = B(b, 0); BX(b, c0f + 1) = B(b, 1); BX(b, c0f + 2) = B(b, 2); }
         }
         init_constraints(T, nullptr, false);
         solve_velocity(T, 180);
@@ -1205,8 +1214,8 @@ struct Sim {
         for (int b = 0; b < K.nb; ++b) {
             if (!((bflag >> b) & 1)) continue;
             Xf xf1;
-            xf1.q = rot_set(BX(b, 15));
-            xf1.p = mk(BX(b, 13), BX(b, 14)) - rmul(xf1.q, localCenter(b));
+            xf1.q = rot_set(BX(b, c0f + 2));
+            xf1.p = mk(BX(b, c0f), BX(b, c0f + 1)) - rmul(xf1.q, localCenter(b));
             moved |= synchronize_fixtures(b, xf1);
             for (int k = 0; k < nc; ++k) {
                 uint32_t mk_ = meta[k];
@@ -1225,7 +1234,7 @@ struct Sim {
     // between bounds that distance from below along the wall's axis-aligned faces; when even this bound stays above
     // 0.00625 (+ guard) the call is skipped and alpha = 1, exactly what the full algorithm would return.
     MRP_HD bool toi_provably_one(int f, int b, int wall) {
-        const float da = B(b, 2) - BX(b, 15);
+        const float da = B(b, 2) - BX(b, c0f + 2);
         if (!(fabsf(da) < 0.5f)) return false;
         const float* sx = shape_x(f);
         const V2 lc = localCenter(b);
@@ -1248,7 +1257,7 @@ struct Sim {
             if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc |= 1u << k;
         }
         if (!wallc) return true;
-        for (int b = 0; b < K.nb; ++b) BX(b, 16) = 0.0f;
+        for (int b = 0; b < K.nb; ++b) BX(b, c0f + 3) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
         uint32_t toiFlag = 0, enabled = 0xffffffffu;
@@ -1300,7 +1309,7 @@ struct Sim {
         if (new_fixtures) find_new_contacts(0xffffffffu);
         collide();
         // xf1 of SynchronizeFixtures == the transform the step started with (c0, a0 are set from c, a)
-        for (int b = 0; b < K.nb; ++b) { BX(b, 13) = B(b, 0); BX(b, 14) = B(b, 1); BX(b, 15) = B(b, 2); }
+        for (int b = 0; b < K.nb; ++b) { BX(b, c0f) = B(b, 0); BX(b, c0f + 1) = B(b, 1); BX(b, c0f + 2) = B(b, 2); }
         solve_islands();
         post_solve(true);
     }
@@ -1312,7 +1321,7 @@ struct Sim {
             Xf xf1;
             xf1.q.s = BX(b, 6);
             xf1.q.c = BX(b, 7);
-            xf1.p = mk(BX(b, 13), BX(b, 14)) - rmul(xf1.q, localCenter(b));
+            xf1.p = mk(BX(b, c0f), BX(b, c0f + 1)) - rmul(xf1.q, localCenter(b));
             sync_transform(b);
             moved |= synchronize_fixtures(b, xf1);
         }
