@@ -107,7 +107,6 @@ MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
             for (int f = 0; f < 6; ++f) s.B(b, f) = s.gf(K.w_body + kBodyWords * b + f);
     for (int b = K.nb; b < K.nb + 4; ++b) { s.B(b, 3) = 0.0f; s.B(b, 4) = 0.0f; s.B(b, 5) = 0.0f; }
     vt.ops = 0;
-    s.vr_begin(vt.st, vt.T);
 }
 MRP_HD void vel_task_end(const SimConst& K, Sim& s, VelTask& vt) {
 #if defined(__CUDA_ARCH__)
@@ -214,6 +213,7 @@ __device__ __forceinline__ const float* load_ctab(const SimConst& K, float* smem
 __global__ void k_clear(int32_t* cnt) {
     if (threadIdx.x < CNT_N) cnt[threadIdx.x] = 0;
 }
+static_assert(CNT_N <= 32, "k_clear is launched with 32 threads");
 
 // fused single-kernel step (MRP_FUSED_STEP=1): kept for A/B measurements against the phase pipeline
 __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimConst K) {
@@ -255,33 +255,53 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
 // stay busy although islands need anywhere between 2 and ~1000 operations.
 constexpr int kRefill = 8;
 
-__global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
-    extern __shared__ float smem[];
-    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
-    const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
+template <int CLS>
+__device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
+    const int ntasks = task_count(K, CLS);
     VelTask vt;
+    Sim::VelReg st1;  // second contact (class 2 only)
     bool busy = false, exhausted = false;
     for (;;) {
         const unsigned bm = __ballot_sync(0xffffffffu, busy);
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
-                const int task = atomicAdd(&K.cnt[CNT_HEAD_V], 1);
-                if (task < ntasks) { vel_task_begin(K, s, vt, task_slot(K, task)); busy = true; }
-                else exhausted = true;
+                const int task = atomicAdd(&K.cnt[CNT_HEAD_V + CLS], 1);
+                if (task < ntasks) {
+                    vel_task_begin(K, s, vt, task_slot(K, CLS, task));
+                    if (CLS == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
+                    busy = true;
+                } else exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
-        if (busy && (++vt.ops, s.vr_trip(vt.st, 180))) {
-            vel_task_end(K, s, vt);
-            busy = false;
+        if (busy) {
+            bool fin;
+            if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
+            else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
+            else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
+            else { vt.ops += 1; fin = s.vr_trip(vt.st, 180); }
+            if (fin) {
+                vel_task_end(K, s, vt);
+                busy = false;
+            }
         }
     }
+}
+
+__global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
+    // every warp serves one class at a time (uniform instruction stream); multi-contact islands first, they run longest
+    solve_vel_class<3>(K, s);
+    solve_vel_class<2>(K, s);
+    solve_vel_class<1>(K, s);
+    solve_vel_class<0>(K, s);
 }
 
 __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 9);
-    const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
+    const int ntasks = task_count_all(K);
     PosTask pt;
     bool busy = false, exhausted = false;
     for (;;) {
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_P], 1);
-                if (task < ntasks) { pos_task_begin(K, s, pt, task_slot(K, task)); busy = true; }
+                if (task < ntasks) { pos_task_begin(K, s, pt, task_slot_any(K, task)); busy = true; }
                 else exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
@@ -498,9 +518,9 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * CNT_N);
     // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
     rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
-    rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * N * K.nb);  // at most one island per dynamic body
-    rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * N * K.nb);
-    rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * N * K.nb);
+    rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * kTaskClasses * N * K.nb);  // classes x at most one island per dynamic body
+    rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * kTaskClasses * N * K.nb);
+    rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * kTaskClasses * N * K.nb);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
@@ -701,20 +721,30 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         const int nnarrow = K.cnt[CNT_NARROW];
         for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
         for (int64_t e = 0; e < K.N; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
-        const int ntasks = K.cnt[CNT_TASKS] + K.cnt[CNT_TASKS_LIGHT];
-        for (int i = 0; i < ntasks; ++i) {
-            Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
-            VelTask vt;
-            vel_task_begin(K, s, vt, task_slot(K, i));
-            while (++vt.ops, !s.vr_trip(vt.st, 180)) {}
-            vel_task_end(K, s, vt);
+        for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
+            const int ntasks = task_count(K, cls);
+            for (int i = 0; i < ntasks; ++i) {
+                Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
+                VelTask vt;
+                Sim::VelReg st1;
+                vel_task_begin(K, s, vt, task_slot(K, cls, i));
+                if (cls == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
+                if (cls == 0) { while (vt.ops += 2, !s.vr_sweep_single<1>(vt.st, 180)) {} }
+                else if (cls == 1) { while (vt.ops += 3, !s.vr_sweep_single<2>(vt.st, 180)) {} }
+                else if (cls == 2) { while (vt.ops += 5, !s.vr_sweep_pair(vt.st, st1, 180)) {} }
+                else { while (++vt.ops, !s.vr_trip(vt.st, 180)) {} }
+                vel_task_end(K, s, vt);
+            }
         }
-        for (int i = 0; i < ntasks; ++i) {
-            Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
-            PosTask pt;
-            pos_task_begin(K, s, pt, task_slot(K, i));
-            while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
-            pos_task_end(K, s, pt);
+        {
+            const int ntasks = task_count_all(K);
+            for (int i = 0; i < ntasks; ++i) {
+                Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
+                PosTask pt;
+                pos_task_begin(K, s, pt, task_slot_any(K, i));
+                while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
+                pos_task_end(K, s, pt);
+            }
         }
         for (int64_t e = 0; e < K.N; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
         const int ntoi = K.cnt[CNT_TOI];

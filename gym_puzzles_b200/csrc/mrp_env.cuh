@@ -350,7 +350,9 @@ struct Env : Sim {
             for (int start = 0; start < T;) {
                 int end = start + 1;
                 while (end < T && island_of[end] == island_of[start]) ++end;
-                const int task = heavy ? atomic_add_i32(&K.cnt[CNT_TASKS], 1) : cap - 1 - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT], 1);
+                const int cls = end - start > 2 ? 3 : (end - start == 2 ? 2 : (int)((vmeta(start) >> 8) & 3) - 1);  // single contact: vpc is 1 or 2
+                const int task = cls * cap + (heavy ? atomic_add_i32(&K.cnt[CNT_TASKS + cls], 1)
+                                                    : cap - 1 - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT + cls], 1));
                 K.task_env[task] = (int32_t)(G - K.S);
                 K.task_T[task] = end - start;
                 K.task_off[task] = off + start * VC_WORDS;

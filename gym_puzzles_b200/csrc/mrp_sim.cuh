@@ -86,13 +86,33 @@ struct SimConst {
 };
 // solver tasks predicted heavy (by W_HINT) are queued from slot 0 upwards, the others from slot N-1 downwards;
 // consumers take the heavy ones first so that long solves start early and short ones fill the tail
-enum { CNT_RESET = 0, CNT_TASKS = 1, CNT_POOL = 2, CNT_HEAD_V = 3, CNT_HEAD_P = 4, CNT_TOI = 5, CNT_TASKS_LIGHT = 6, CNT_NARROW = 7, CNT_N = 8 };
+// Solver tasks come in three classes so that the lanes of a warp run the same instruction stream:
+//   0: one contact, 1-point manifold   1: one contact, 2-point manifold (block solver)   2: two contacts   3: more.
+// Class c owns slots [c*cap, (c+1)*cap), cap = N * nb.
+constexpr int kTaskClasses = 4;
+enum { CNT_RESET = 0, CNT_POOL = 1, CNT_TOI = 2, CNT_NARROW = 3, CNT_HEAD_P = 4, CNT_TASKS = 8 /*[4] heavy*/, CNT_TASKS_LIGHT = 12 /*[4]*/,
+       CNT_HEAD_V = 16 /*[4]*/, CNT_N = 20 };
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
-MRP_HD int task_slot(const SimConst& K, int i) {  // i-th task in consumption order -> slot (arrays hold N * nb slots)
-    const int nh = K.cnt[CNT_TASKS];
-    return i < nh ? i : (int)K.N * K.nb - 1 - (i - nh);
+MRP_HD int task_count(const SimConst& K, int cls) { return K.cnt[CNT_TASKS + cls] + K.cnt[CNT_TASKS_LIGHT + cls]; }
+MRP_HD int task_slot(const SimConst& K, int cls, int i) {  // i-th task of a class in consumption order -> slot
+    const int cap = (int)K.N * K.nb;
+    const int nh = K.cnt[CNT_TASKS + cls];
+    return cls * cap + (i < nh ? i : cap - 1 - (i - nh));
+}
+MRP_HD int task_slot_any(const SimConst& K, int i) {  // i-th task over all classes, heaviest class first
+    for (int cls = kTaskClasses - 1; cls > 0; --cls) {
+        const int n = task_count(K, cls);
+        if (i < n) return task_slot(K, cls, i);
+        i -= n;
+    }
+    return task_slot(K, 0, i);
+}
+MRP_HD int task_count_all(const SimConst& K) {
+    int n = 0;
+    for (int cls = 0; cls < kTaskClasses; ++cls) n += task_count(K, cls);
+    return n;
 }
 
 MRP_HD int atomic_add_i32(int32_t* p, int v) {
@@ -826,10 +846,19 @@ struct Sim {
         r.nM1 = C[VC_PT + 12]; r.tM1 = C[VC_PT + 13]; r.nI1 = C[VC_PT + 14]; r.tI1 = C[VC_PT + 15];
         r.k11 = C[VC_K11]; r.k12 = C[VC_K12]; r.k22 = C[VC_K22];
         r.m11 = C[VC_M11]; r.m12 = C[VC_M12]; r.m22 = C[VC_M22];
+        vr_load_vel(r);
+    }
+    MRP_HD void vr_load_vel(VelReg& r) {
         const float* pA = bp(r.bA);
         const float* pB = bp(r.bB);
         r.vA = mk(pA[3 * MRP_SS], pA[4 * MRP_SS]); r.wA = pA[5 * MRP_SS];
         r.vB = mk(pB[3 * MRP_SS], pB[4 * MRP_SS]); r.wB = pB[5 * MRP_SS];
+    }
+    MRP_HD void vr_store_vel(const VelReg& r) {
+        float* pA = bp(r.bA);
+        float* pB = bp(r.bB);
+        pA[3 * MRP_SS] = r.vA.x; pA[4 * MRP_SS] = r.vA.y; pA[5 * MRP_SS] = r.wA;
+        pB[3 * MRP_SS] = r.vB.x; pB[4 * MRP_SS] = r.vB.y; pB[5 * MRP_SS] = r.wB;
     }
     MRP_HD void vr_store(const VelReg& r) {
         float* C = &V(r.t, 0);
@@ -844,67 +873,74 @@ struct Sim {
         vr_load(r);
     }
     // one point operation; returns true when the solve is finished (everything written back)
+    // the two kinds of point operation on the register-resident contact
+    template <int KIND>  // 0: friction point 0, 1: friction point 1, 2: normal point 0 (1-point manifolds)
+    MRP_HD void vr_op_1d(VelReg& r) {
+        constexpr bool fr = KIND != 2, second = KIND == 1;
+        const V2 dir = fr ? crossVS(r.n, 1.0f) : r.n;
+        const V2 rA = second ? r.rA1 : r.rA0, rB = second ? r.rB1 : r.rB0;
+        const V2 dv = r.vB + crossSV(r.wB, rB) - r.vA - crossSV(r.wA, rA);
+        const float vd = dot(dv, dir);
+        const float acc = fr ? (second ? r.tI1 : r.tI0) : r.nI0;
+        const float mass = fr ? (second ? r.tM1 : r.tM0) : r.nM0;
+        float lambda = mass * (-vd);  // tangentMass*(-vt)  ==  -normalMass*vn (exact sign symmetry)
+        const float maxFriction = r.fric * (second ? r.nI1 : r.nI0);
+        const float newImpulse = fr ? clampf(acc + lambda, -maxFriction, maxFriction) : fmax2(acc + lambda, 0.0f);
+        lambda = newImpulse - acc;
+        if (!fr) r.nI0 = newImpulse;
+        else if (second) r.tI1 = newImpulse;
+        else r.tI0 = newImpulse;
+        r.changed = r.changed || (lambda != 0.0f);
+        const V2 Pi = lambda * dir;
+        r.vA = r.vA - r.mA * Pi;
+        r.wA -= r.iA * cross(rA, Pi);
+        r.vB = r.vB + r.mB * Pi;
+        r.wB += r.iB * cross(rB, Pi);
+    }
+    MRP_HD void vr_op_block(VelReg& r) {
+        const float ax = r.nI0, ay = r.nI1;
+        const V2 dv1 = r.vB + crossSV(r.wB, r.rB0) - r.vA - crossSV(r.wA, r.rA0);
+        const V2 dv2 = r.vB + crossSV(r.wB, r.rB1) - r.vA - crossSV(r.wA, r.rA1);
+        float vn1 = dot(dv1, r.n), vn2 = dot(dv2, r.n);
+        float bx = vn1, by = vn2;
+        bx -= r.k11 * ax + r.k12 * ay;
+        by -= r.k12 * ax + r.k22 * ay;
+        float xx, xy;
+        bool ok = false;
+        xx = -(r.m11 * bx + r.m12 * by);
+        xy = -(r.m12 * bx + r.m22 * by);
+        if (xx >= 0.0f && xy >= 0.0f) ok = true;
+        if (!ok) {
+            xx = -r.nM0 * bx; xy = 0.0f;
+            vn2 = r.k12 * xx + by;
+            if (xx >= 0.0f && vn2 >= 0.0f) ok = true;
+        }
+        if (!ok) {
+            xx = 0.0f; xy = -r.nM1 * by;
+            vn1 = r.k12 * xy + bx;
+            if (xy >= 0.0f && vn1 >= 0.0f) ok = true;
+        }
+        if (!ok) {
+            xx = 0.0f; xy = 0.0f;
+            if (bx >= 0.0f && by >= 0.0f) ok = true;
+        }
+        if (ok) {
+            const float dx = xx - ax, dy = xy - ay;
+            const V2 Pa = dx * r.n, Pb = dy * r.n;
+            r.vA = r.vA - r.mA * (Pa + Pb);
+            r.wA -= r.iA * (cross(r.rA0, Pa) + cross(r.rA1, Pb));
+            r.vB = r.vB + r.mB * (Pa + Pb);
+            r.wB += r.iB * (cross(r.rB0, Pa) + cross(r.rB1, Pb));
+            r.nI0 = xx; r.nI1 = xy;
+            r.changed = r.changed || (dx != 0.0f) || (dy != 0.0f);
+        }
+    }
+    // generic form: one point operation per trip, any island; returns true when finished (everything written back)
     MRP_HD bool vr_trip(VelReg& r, int iters) {
         const int j = r.j;
-        if (j < r.vpc || r.vpc == 1) {
-            const bool fr = j < r.vpc, second = fr && j == 1;
-            const V2 dir = fr ? crossVS(r.n, 1.0f) : r.n;
-            const V2 rA = second ? r.rA1 : r.rA0, rB = second ? r.rB1 : r.rB0;
-            const V2 dv = r.vB + crossSV(r.wB, rB) - r.vA - crossSV(r.wA, rA);
-            const float vd = dot(dv, dir);
-            const float acc = fr ? (second ? r.tI1 : r.tI0) : r.nI0;
-            const float mass = fr ? (second ? r.tM1 : r.tM0) : r.nM0;
-            float lambda = mass * (-vd);
-            const float maxFriction = r.fric * (second ? r.nI1 : r.nI0);
-            const float newImpulse = fr ? clampf(acc + lambda, -maxFriction, maxFriction) : fmax2(acc + lambda, 0.0f);
-            lambda = newImpulse - acc;
-            if (!fr) r.nI0 = newImpulse;
-            else if (second) r.tI1 = newImpulse;
-            else r.tI0 = newImpulse;
-            r.changed = r.changed || (lambda != 0.0f);
-            const V2 Pi = lambda * dir;
-            r.vA = r.vA - r.mA * Pi;
-            r.wA -= r.iA * cross(rA, Pi);
-            r.vB = r.vB + r.mB * Pi;
-            r.wB += r.iB * cross(rB, Pi);
-        } else {
-            const float ax = r.nI0, ay = r.nI1;
-            const V2 dv1 = r.vB + crossSV(r.wB, r.rB0) - r.vA - crossSV(r.wA, r.rA0);
-            const V2 dv2 = r.vB + crossSV(r.wB, r.rB1) - r.vA - crossSV(r.wA, r.rA1);
-            float vn1 = dot(dv1, r.n), vn2 = dot(dv2, r.n);
-            float bx = vn1, by = vn2;
-            bx -= r.k11 * ax + r.k12 * ay;
-            by -= r.k12 * ax + r.k22 * ay;
-            float xx, xy;
-            bool ok = false;
-            xx = -(r.m11 * bx + r.m12 * by);
-            xy = -(r.m12 * bx + r.m22 * by);
-            if (xx >= 0.0f && xy >= 0.0f) ok = true;
-            if (!ok) {
-                xx = -r.nM0 * bx; xy = 0.0f;
-                vn2 = r.k12 * xx + by;
-                if (xx >= 0.0f && vn2 >= 0.0f) ok = true;
-            }
-            if (!ok) {
-                xx = 0.0f; xy = -r.nM1 * by;
-                vn1 = r.k12 * xy + bx;
-                if (xy >= 0.0f && vn1 >= 0.0f) ok = true;
-            }
-            if (!ok) {
-                xx = 0.0f; xy = 0.0f;
-                if (bx >= 0.0f && by >= 0.0f) ok = true;
-            }
-            if (ok) {
-                const float dx = xx - ax, dy = xy - ay;
-                const V2 Pa = dx * r.n, Pb = dy * r.n;
-                r.vA = r.vA - r.mA * (Pa + Pb);
-                r.wA -= r.iA * (cross(r.rA0, Pa) + cross(r.rA1, Pb));
-                r.vB = r.vB + r.mB * (Pa + Pb);
-                r.wB += r.iB * (cross(r.rB0, Pa) + cross(r.rB1, Pb));
-                r.nI0 = xx; r.nI1 = xy;
-                r.changed = r.changed || (dx != 0.0f) || (dy != 0.0f);
-            }
-        }
+        if (j < r.vpc) { if (j == 0) vr_op_1d<0>(r); else vr_op_1d<1>(r); }
+        else if (r.vpc == 1) vr_op_1d<2>(r);
+        else vr_op_block(r);
         if (++r.j > r.vpc) {
             r.j = 0;
             bool wrapped = true;
@@ -923,6 +959,52 @@ struct Sim {
                 r.changed = false;
             }
         }
+        return false;
+    }
+    // two-contact islands: both constraint records stay in registers; only the body velocities travel through the
+    // lane's shared-memory slots between the two contacts (they may share one or both bodies)
+    MRP_HD void vr_begin_pair(VelReg& r0, VelReg& r1) {
+        r0.T = 2; r0.t = 0; r0.j = 0; r0.sweep = 0; r0.changed = false;
+        vr_load(r0);
+        r1.T = 2; r1.t = 1; r1.j = 0; r1.sweep = 0; r1.changed = false;
+        vr_load(r1);
+    }
+    MRP_HD void vr_contact_ops(VelReg& r) {
+        vr_op_1d<0>(r);
+        if (r.vpc == 2) { vr_op_1d<1>(r); vr_op_block(r); }
+        else vr_op_1d<2>(r);
+    }
+    MRP_HD bool vr_sweep_pair(VelReg& r0, VelReg& r1, int iters) {
+        vr_load_vel(r0);
+        vr_contact_ops(r0);
+        vr_store_vel(r0);
+        vr_load_vel(r1);
+        vr_contact_ops(r1);
+        vr_store_vel(r1);
+        ++r0.sweep;
+        if (!(r0.changed || r1.changed) || r0.sweep == iters) {
+            vr_store(r0);
+            vr_store(r1);   // contact 1 ran last: its velocities are the final ones for shared bodies
+            return true;
+        }
+        r0.changed = false;
+        r1.changed = false;
+        return false;
+    }
+
+    // single-contact islands: one trip = one whole sweep, branch-free op sequence, nothing leaves the registers.
+    // VPC = 1: friction, normal.  VPC = 2: friction, friction, block solve.
+    template <int VPC>
+    MRP_HD bool vr_sweep_single(VelReg& r, int iters) {
+        vr_op_1d<0>(r);
+        if (VPC == 2) { vr_op_1d<1>(r); vr_op_block(r); }
+        else vr_op_1d<2>(r);
+        ++r.sweep;
+        if (!r.changed || r.sweep == iters) {
+            vr_store(r);
+            return true;
+        }
+        r.changed = false;
         return false;
     }
 
