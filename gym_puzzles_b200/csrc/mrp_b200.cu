@@ -100,7 +100,7 @@ MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
     const int64_t env = K.task_env[task];
     vt.T = K.task_T[task];
     s.G = K.S + env;
-    s.vcp = K.pool + K.task_off[task];
+    s.vcp = K.pool + (size_t)K.task_off[task] * VC_WORDS;
     vt.bodies = task_body_mask(K, s, vt.T);
     for (int b = 0; b < K.nb; ++b)
         if ((vt.bodies >> b) & 1)
@@ -131,7 +131,7 @@ MRP_HD void pos_task_begin(const SimConst& K, Sim& s, PosTask& pt, int task) {
     const int64_t env = K.task_env[task];
     pt.T = K.task_T[task];
     s.G = K.S + env;
-    s.vcp = K.pool + K.task_off[task];
+    s.vcp = K.pool + (size_t)K.task_off[task] * VC_WORDS;
     pt.bodies = task_body_mask(K, s, pt.T);
     const float nan = s.__uint_as_float_(0x7fc00000u);
     for (int b = 0; b < K.nb; ++b) {
@@ -479,6 +479,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     if (!cfg || !out) return fail(-1, "mrp_create: null argument");
     *out = nullptr;
     if (cfg->num_envs <= 0) return fail(-2, "mrp_create: num_envs must be > 0");
+    if (cfg->num_envs > (1 << 26)) return fail(-2, "mrp_create: num_envs must be <= 67108864 per handle");
 #ifndef MRP_HOST_EMU
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

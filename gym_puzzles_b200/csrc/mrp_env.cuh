@@ -340,8 +340,8 @@ struct Env : Sim {
         const int T = build_islands(island_of);
         uint32_t in_island = 0;  // dynamic bodies that belong to an island with touching contacts
         if (T > 0) {
-            const int off = atomic_add_i32(&K.cnt[CNT_POOL], T * VC_WORDS);
-            vcp = K.pool + off;
+            const int off = atomic_add_i32(&K.cnt[CNT_POOL], T);  // in records
+            vcp = K.pool + (size_t)off * VC_WORDS;
             init_constraints(T, island_of, true);
             warm_start(T);
             // one solver task per island (its constraint records are contiguous in solver order)
@@ -355,7 +355,7 @@ struct Env : Sim {
                                                     : cap - 1 - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT + cls], 1));
                 K.task_env[task] = (int32_t)(G - K.S);
                 K.task_T[task] = end - start;
-                K.task_off[task] = off + start * VC_WORDS;
+                K.task_off[task] = off + start;
                 start = end;
             }
             for (int t = 0; t < T; ++t) {

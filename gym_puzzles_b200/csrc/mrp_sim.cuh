@@ -80,7 +80,7 @@ struct SimConst {
     int32_t* cnt;         // [CNT_*] counters, zeroed at the start of every step
     int32_t* task_env;    // [N] env of task i
     int32_t* task_T;      // [N] number of constraints of task i
-    int32_t* task_off;    // [N] offset of task i's records in pool (floats)
+    int32_t* task_off;    // [..] index of task i's first record in pool
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
     uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * 32 + slot
 };
@@ -715,6 +715,19 @@ struct Sim {
     MRP_HD void vel_begin(VelState& st) { st.t = 0; st.j = 0; st.sweep = 0; st.changed = false; }
     MRP_HD void solve_velocity(int T, int iters) {
         if (T == 0) return;
+        if (T == 1) {  // register-resident forms (identical arithmetic, see vr_*)
+            VelReg r;
+            vr_begin(r, 1);
+            if (r.vpc == 2) { while (!vr_sweep_single<2>(r, iters)) {} }
+            else { while (!vr_sweep_single<1>(r, iters)) {} }
+            return;
+        }
+        if (T == 2) {
+            VelReg r0, r1;
+            vr_begin_pair(r0, r1);
+            while (!vr_sweep_pair(r0, r1, iters)) {}
+            return;
+        }
         VelState st;
         vel_begin(st);
         while (!vel_trip(st, T, iters)) {}
@@ -1134,6 +1147,11 @@ struct Sim {
         int T = 0;
         uint32_t touch = 0;
         for (int k = 0; k < nc; ++k) touch |= ((meta[k] >> 16) & 1u) << k;
+        if (touch && (touch & (touch - 1)) == 0) {  // a single touching contact is its own island: no search needed
+            order[0] = (uint8_t)ctz32(touch);
+            island_of[0] = 0;
+            return 1;
+        }
         if (touch) {
             uint32_t bflag = 0, cflag = 0;
             int nisl = 0;
