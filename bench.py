@@ -172,9 +172,7 @@ def run_native(args):
         except Exception:
             gpu_sel = str(local_rank)
         sampler = ClockSampler(gpu_sel)
-    # ---------------- device-resident throughput
-    h.set_timing(True)
-    h.get_timing(reset_after=True)
+    # ---------------- device-resident throughput (library timers off: production configuration)
     launches0 = h.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -188,14 +186,23 @@ def run_native(args):
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
     launches = h.launch_count - launches0
+    value = world * N * K / (elapsed_ms / 1e3)
+
+    # ---------------- per-kernel durations for the roofline: the same steps again with the library's CUDA-event timers
+    # on (events between the phase kernels on the launching stream; the timers force a single chunk / single stream)
+    h.set_timing(True)
+    h.get_timing(reset_after=True)
+    h.get_phase_timing(reset_after=True)
+    for t in range(K):
+        env.step(acts[(K + t) % R])
+    torch.cuda.synchronize()
     k_ms, k_cnt = h.get_timing(reset_after=True)
     phase_ms = h.get_phase_timing(reset_after=True)
     h.set_timing(False)
-    value = world * N * K / (elapsed_ms / 1e3)
 
     # ---------------- end to end through the host-buffer C-ABI call (pinned host memory)
     Ke = max(2, min(K, args.e2e_steps))
-    host_acts = [acts[(K + i) % R].cpu().pin_memory() for i in range(Ke + 1)]   # a different action batch per step
+    host_acts = [acts[(2 * K + i) % R].cpu().pin_memory() for i in range(Ke + 1)]   # a different action batch per step
     host_obs = torch.empty((N, O), dtype=torch.float32).pin_memory()
     host_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
     host_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
@@ -249,7 +256,7 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / (elapsed_ms / K) if elapsed_ms else None,
+                         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / k_mean_ms if k_mean_ms else None,
                          "kernels_ms": per_kernel, "pipeline_ms": k_mean_ms, "pipeline_achieved": pipeline_gbs,
                          "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
             "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},

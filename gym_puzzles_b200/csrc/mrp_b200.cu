@@ -219,16 +219,18 @@ static_assert(CNT_N <= 32, "k_clear is launched with 32 threads");
 __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (env >= K.N) return;
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (loc >= K.nloc) return;
+    const int64_t env = K.env0 + loc;
     step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
 
 __global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (env >= K.N) return;
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (loc >= K.nloc) return;
+    const int64_t env = K.env0 + loc;
     broad_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
 
@@ -245,8 +247,9 @@ __global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimCo
 __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (env >= K.N) return;
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (loc >= K.nloc) return;
+    const int64_t env = K.env0 + loc;
     pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
 
@@ -324,8 +327,9 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
 __global__ void __launch_bounds__(kBlock) k_post(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (env >= K.N) return;
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (loc >= K.nloc) return;
+    const int64_t env = K.env0 + loc;
     post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr);
 }
 
@@ -375,6 +379,8 @@ __global__ void k_fix_rot(const __grid_constant__ SimConst K, int64_t begin, int
 // ------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 8;
+
 struct mrp_handle {
     SimConst K;
     mrp_layout L;
@@ -384,6 +390,13 @@ struct mrp_handle {
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
     size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post;
     int solver_ctas;  // persistent solver CTAs per SM
+    int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
+    int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
+    int host_chain;    // mrp_step_host: chunk pipelines execute in chunk order (copies still overlap)
+#ifndef MRP_HOST_EMU
+    cudaStream_t cstream[kMaxChunks];
+    cudaEvent_t cfork, cjoin[kMaxChunks];
+#endif
     int64_t launches;
     size_t smem_bytes;
     // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
@@ -452,6 +465,10 @@ int mrp_destroy(mrp_handle* h) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     if (h->timing) mrp_set_timing(h, 0);
+    if (h->cfork) {
+        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); }
+        cudaEventDestroy(h->cfork);
+    }
 #else
     free(h->emu_sm);
 #endif
@@ -501,9 +518,19 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
     h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
     if (h->solver_ctas < 1) h->solver_ctas = 1;
+    // small batches are one chunk unless the environment variables say otherwise (tests exercise chunking that way)
+    auto chunks_from = [&](const char* var, int dflt) {
+        int v = getenv(var) ? atoi(getenv(var)) : (cfg->num_envs >= 16384 * dflt ? dflt : 1);
+        return v < 1 ? 1 : (v > kMaxChunks ? kMaxChunks : v);
+    };
+    h->host_chain = getenv("MRP_HOST_CHAIN") ? atoi(getenv("MRP_HOST_CHAIN")) : 0;
+    h->nchunks = chunks_from("MRP_CHUNKS", 1);
+    h->nchunks_host = chunks_from("MRP_CHUNKS_HOST", 4);
     K.seed = cfg->seed;
     K.env_id_base = cfg->env_id_base;
     K.N = cfg->num_envs;
+    K.env0 = 0;
+    K.nloc = cfg->num_envs;
     h->device = cfg->device;
     const size_t N = (size_t)cfg->num_envs;
     int rc = 0;
@@ -516,7 +543,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.trunc, N);
     rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
     rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * CNT_N);
+    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * 32 * kMaxChunks);
     // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
     rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
     rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * kTaskClasses * N * K.nb);  // classes x at most one island per dynamic body
@@ -561,6 +588,20 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
     cudaFuncSetAttribute(k_reset_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    {
+        // earlier chunks get higher stream priority: their CTAs are scheduled first, so they finish first and their
+        // D2H copies run under the later chunks' kernels
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least (numerically largest), hi = greatest
+        const int use_prio = getenv("MRP_STREAM_PRIO") ? atoi(getenv("MRP_STREAM_PRIO")) : 1;
+        for (int c = 0; c < kMaxChunks; ++c) {
+            int pr = hi + c;
+            if (pr > lo || !use_prio) pr = lo;
+            cudaStreamCreateWithPriority(&h->cstream[c], cudaStreamNonBlocking, pr);
+            cudaEventCreateWithFlags(&h->cjoin[c], cudaEventDisableTiming);
+        }
+    }
+    cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
     if (check_launch("mrp_create")) { mrp_destroy(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
@@ -672,19 +713,41 @@ int mrp_get_phase_timing(mrp_handle* h, double* ms5, int32_t reset_after) {
     return 0;
 }
 
-int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
-    if (!h) return fail(-1, "mrp_step: null handle");
-    SimConst K = h->K;
-    if (actions_dev) K.act = actions_dev;
+// The env range of a handle is processed as `nch` independent chunks.  Every chunk has its own counters, task
+// queues, pool region and event lists (disjoint slices of the handle's arrays), so the pipelines of different chunks
+// can run concurrently on separate streams: the serial tails of one chunk's persistent solver kernels and the
+// host copies of mrp_step_host overlap with the other chunks' kernels.  Results do not depend on the chunking
+// (envs are independent; tested in tests/test_emu_parity.py and tests/test_gpu_parity.py).
+static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int nch) {
+    SimConst K = K0;
+    const int64_t per = ((K0.N + nch - 1) / nch + kBlock - 1) / kBlock * kBlock;
+    int64_t b = per * c, e = b + per;
+    if (b > K0.N) b = K0.N;
+    if (e > K0.N) e = K0.N;
+    K.env0 = b;
+    K.nloc = (int32_t)(e - b);
+    K.cnt = K0.cnt + 32 * c;
+    K.pool = K0.pool + (size_t)b * K0.maxc * VC_WORDS;
+    K.task_env = K0.task_env + (size_t)kTaskClasses * b * K0.nb;
+    K.task_T = K0.task_T + (size_t)kTaskClasses * b * K0.nb;
+    K.task_off = K0.task_off + (size_t)kTaskClasses * b * K0.nb;
+    K.toi_list = K0.toi_list + b;
+    K.narrow_list = K0.narrow_list + (size_t)b * K0.maxc;
+    K.reset_list = K0.reset_list + b;
+    (void)h;
+    return K;
+}
+
 #ifndef MRP_HOST_EMU
-    cudaSetDevice(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = grid_for(K.N, kBlock);
+// one chunk's phase pipeline on one stream; `timed` records the phase-boundary events (single-chunk steps only)
+static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
+    const unsigned grid = grid_for(K.nloc, kBlock);
+    if (grid == 0) return;
     // persistent / queue kernels: a few CTAs per SM
     const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
     const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
     k_clear<<<1, 32, 0, st>>>(K.cnt);
-    if (h->timing) {
+    if (timed) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
     }
@@ -695,33 +758,34 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
         k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
         k_pre<<<grid, kBlock, h->smem_pre, st>>>(K);
-        if (h->timing) cudaEventRecord(h->evk[h->ev_n][0], st);
+        if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
         k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
-        if (h->timing) cudaEventRecord(h->evk[h->ev_n][1], st);
+        if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
         k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
-        if (h->timing) cudaEventRecord(h->evk[h->ev_n][2], st);
+        if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
         k_post<<<grid, kBlock, h->smem_post, st>>>(K);
-        if (h->timing) cudaEventRecord(h->evk[h->ev_n][3], st);
+        if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
         k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 8;
     }
-    if (h->timing) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+    if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
     }
-    return check_launch("mrp_step");
+}
 #else
-    (void)stream;
+static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
     for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
+    const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
     if (h->fused) {
-        for (int64_t e = 0; e < K.N; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
+        for (int64_t e = e0; e < e1; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
     } else {
         // the same phases the device runs as kernels, executed as loops
-        for (int64_t e = 0; e < K.N; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
+        for (int64_t e = e0; e < e1; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
         const int nnarrow = K.cnt[CNT_NARROW];
         for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
-        for (int64_t e = 0; e < K.N; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
+        for (int64_t e = e0; e < e1; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
         for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
             const int ntasks = task_count(K, cls);
             for (int i = 0; i < ntasks; ++i) {
@@ -747,7 +811,7 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
                 pos_task_end(K, s, pt);
             }
         }
-        for (int64_t e = 0; e < K.N; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
+        for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
         const int ntoi = K.cnt[CNT_TOI];
         for (int i = 0; i < ntoi; ++i) {
             float vc_local[kMaxC * VC_WORDS];
@@ -758,6 +822,40 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
         const int nreset = K.cnt[CNT_RESET];
         for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
     }
+}
+#endif
+
+// chunks of one step call: 1 while the per-phase timers are on (their events live on one stream)
+static int step_chunks(const mrp_handle* h, int wanted) {
+    int nch = h->timing ? 1 : wanted;
+    if ((int64_t)nch > (h->K.N + kBlock - 1) / kBlock) nch = (int)((h->K.N + kBlock - 1) / kBlock);
+    return nch < 1 ? 1 : nch;
+}
+
+int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
+    if (!h) return fail(-1, "mrp_step: null handle");
+    SimConst K = h->K;
+    if (actions_dev) K.act = actions_dev;
+    const int nch = step_chunks(h, h->nchunks);
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nch == 1) {
+        launch_pipeline(h, chunk_const(h, K, 0, 1), st, h->timing != 0);
+    } else {
+        // fork the chunk pipelines off the caller's stream and join them back: stream-ordered like one kernel
+        cudaEventRecord(h->cfork, st);
+        for (int c = 0; c < nch; ++c) {
+            cudaStreamWaitEvent(h->cstream[c], h->cfork, 0);
+            launch_pipeline(h, chunk_const(h, K, c, nch), h->cstream[c], false);
+            cudaEventRecord(h->cjoin[c], h->cstream[c]);
+            cudaStreamWaitEvent(st, h->cjoin[c], 0);
+        }
+    }
+    return check_launch("mrp_step");
+#else
+    (void)stream;
+    for (int c = 0; c < nch; ++c) run_pipeline_emu(h, chunk_const(h, K, c, nch));
     return 0;
 #endif
 }
@@ -765,28 +863,45 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
 int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
                   uint8_t* trunc_host) {
     if (!h || !actions_host) return fail(-1, "mrp_step_host: null argument");
-    const size_t N = (size_t)h->K.N;
+    const SimConst& K0 = h->K;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
-    cudaStream_t st = 0;
-    if (cudaMemcpyAsync(h->act_dev, actions_host, sizeof(float) * N * h->K.act_dim, cudaMemcpyHostToDevice, st) != cudaSuccess)
-        return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
-    int rc = mrp_step(h, nullptr, st);
-    if (rc) return rc;
-    if (obs_host) cudaMemcpyAsync(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim, cudaMemcpyDeviceToHost, st);
-    if (reward_host) cudaMemcpyAsync(reward_host, h->K.rew, sizeof(float) * N, cudaMemcpyDeviceToHost, st);
-    if (done_host) cudaMemcpyAsync(done_host, h->K.done, N, cudaMemcpyDeviceToHost, st);
-    if (trunc_host) cudaMemcpyAsync(trunc_host, h->K.trunc, N, cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(-9, "mrp_step_host: %s", dev_err());
-    return 0;
+    // per chunk: H2D of its action rows, its pipeline, D2H of its result rows, all on the chunk's stream, so the
+    // PCIe copies of one chunk run under the kernels of the others (the host buffers should be pinned)
+    const int nch = step_chunks(h, h->nchunks_host);
+    cudaEventRecord(h->cfork, 0);  // order after whatever the caller queued on the default stream
+    for (int c = 0; c < nch; ++c) {
+        const SimConst K = chunk_const(h, K0, c, nch);
+        if (K.nloc == 0) continue;
+        cudaStream_t st = h->cstream[c];
+        cudaStreamWaitEvent(st, h->cfork, 0);
+        const size_t b = (size_t)K.env0, n = (size_t)K.nloc;
+        if (cudaMemcpyAsync(h->act_dev + b * K.act_dim, actions_host + b * K.act_dim, sizeof(float) * n * K.act_dim,
+                            cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
+        // compute runs in chunk order (chunk c+1's kernels queue behind chunk c's): chunk c finishes early and its
+        // D2H overlaps the kernels of chunk c+1, whose H2D already ran under chunk c
+        if (h->host_chain && c > 0) cudaStreamWaitEvent(st, h->cjoin[c - 1], 0);
+        launch_pipeline(h, K, st, nch == 1 && h->timing);
+        cudaEventRecord(h->cjoin[c], st);
+        if (obs_host) cudaMemcpyAsync(obs_host + b * K.obs_dim, K.obs + b * K.obs_dim, sizeof(float) * n * K.obs_dim, cudaMemcpyDeviceToHost, st);
+        if (reward_host) cudaMemcpyAsync(reward_host + b, K.rew + b, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+        if (done_host) cudaMemcpyAsync(done_host + b, K.done + b, n, cudaMemcpyDeviceToHost, st);
+        if (trunc_host) cudaMemcpyAsync(trunc_host + b, K.trunc + b, n, cudaMemcpyDeviceToHost, st);
+    }
+    int rc = check_launch("mrp_step_host");
+    for (int c = 0; c < nch; ++c)
+        if (cudaStreamSynchronize(h->cstream[c]) != cudaSuccess && !rc) rc = fail(-9, "mrp_step_host: %s", dev_err());
+    return rc;
 #else
-    memcpy(h->act_dev, actions_host, sizeof(float) * N * h->K.act_dim);
-    int rc = mrp_step(h, nullptr, nullptr);
-    if (rc) return rc;
-    if (obs_host) memcpy(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim);
-    if (reward_host) memcpy(reward_host, h->K.rew, sizeof(float) * N);
-    if (done_host) memcpy(done_host, h->K.done, N);
-    if (trunc_host) memcpy(trunc_host, h->K.trunc, N);
+    const size_t N = (size_t)K0.N;
+    memcpy(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim);
+    const int nch = step_chunks(h, h->nchunks_host);
+    for (int c = 0; c < nch; ++c) run_pipeline_emu(h, chunk_const(h, K0, c, nch));
+    if (obs_host) memcpy(obs_host, K0.obs, sizeof(float) * N * K0.obs_dim);
+    if (reward_host) memcpy(reward_host, K0.rew, sizeof(float) * N);
+    if (done_host) memcpy(done_host, K0.done, N);
+    if (trunc_host) memcpy(trunc_host, K0.trunc, N);
     return 0;
 #endif
 }

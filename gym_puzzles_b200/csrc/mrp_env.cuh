@@ -346,7 +346,7 @@ struct Env : Sim {
             warm_start(T);
             // one solver task per island (its constraint records are contiguous in solver order)
             const bool heavy = g(W_HINT) >= kHeavyHint;
-            const int cap = (int)K.N * K.nb;
+            const int cap = K.nloc * K.nb;
             for (int start = 0; start < T;) {
                 int end = start + 1;
                 while (end < T && island_of[end] == island_of[start]) ++end;

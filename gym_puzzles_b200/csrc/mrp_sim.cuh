@@ -65,7 +65,10 @@ struct SimConst {
     uint64_t seed, env_id_base;
     // memory
     uint32_t* S;
-    int64_t N;
+    int64_t N;       // envs of the handle (stride of the [word][env] state)
+    int64_t env0;    // first env of the chunk this launch works on
+    int32_t nloc;    // envs in the chunk (chunks are pipelined on separate streams; queues and counters are per chunk)
+    int32_t pad1;
     const float* ctab;
     const float* act;
     float* obs;
@@ -97,7 +100,7 @@ constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
 MRP_HD int task_count(const SimConst& K, int cls) { return K.cnt[CNT_TASKS + cls] + K.cnt[CNT_TASKS_LIGHT + cls]; }
 MRP_HD int task_slot(const SimConst& K, int cls, int i) {  // i-th task of a class in consumption order -> slot
-    const int cap = (int)K.N * K.nb;
+    const int cap = K.nloc * K.nb;
     const int nh = K.cnt[CNT_TASKS + cls];
     return cls * cap + (i < nh ? i : cap - 1 - (i - nh));
 }

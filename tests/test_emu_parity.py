@@ -116,3 +116,23 @@ def test_params_change_rewards():
     a = np.zeros((4, 6), dtype=np.float32)
     r1, r2 = h.step_host(a)[1], g.step_host(a)[1]
     assert (r2 > r1).all()    # distance penalties removed
+
+
+def test_chunked_pipeline_is_invariant(monkeypatch):
+    """mrp_step / mrp_step_host split the env range into independently queued chunks (separate streams on the
+    device): results must not depend on the chunk count."""
+    N = 700   # ragged: 6 CTAs of 128, last chunk short
+    ref = abi.Handle(1, N, seed=4, max_episode_steps=25, lib=emu_lib())
+    monkeypatch.setenv("MRP_CHUNKS", "3")
+    monkeypatch.setenv("MRP_CHUNKS_HOST", "5")
+    chk = abi.Handle(1, N, seed=4, max_episode_steps=25, lib=emu_lib())
+    assert np.array_equal(ref.reset_host(), chk.reset_host())
+    rng = np.random.default_rng(2)
+    for t in range(60):
+        act = rng.uniform(-1, 1, (N, 15)).astype(np.float32)
+        for x, y in zip(ref.step_host(act), chk.step_host(act)):
+            assert np.array_equal(x, y)
+    assert np.array_equal(ref.get_state(), chk.get_state())
+    sr, sc = ref.stats(), chk.stats()
+    assert sr["episodes"] > 0 and all(sr[k] == sc[k] for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"))
+    assert abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # summation order differs

@@ -68,3 +68,33 @@ def test_sharding_invariance():
         for x, y0, y1 in zip(ra, r0, r1):
             assert np.array_equal(x, np.concatenate([y0, y1]))
     assert np.array_equal(a.get_state(), np.concatenate([b0.get_state(), b1.get_state()]))
+
+
+def test_chunked_streams_are_invariant(monkeypatch):
+    """Chunk pipelines on separate streams (mrp_step) and chunked H2D / D2H overlap (mrp_step_host) give the same
+    results as one chunk."""
+    import torch
+
+    N = 8192 + 300
+    monkeypatch.setenv("MRP_CHUNKS", "1")
+    monkeypatch.setenv("MRP_CHUNKS_HOST", "1")
+    ref = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25)
+    monkeypatch.setenv("MRP_CHUNKS", "4")
+    monkeypatch.setenv("MRP_CHUNKS_HOST", "8")
+    chk = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25)
+    assert np.array_equal(ref.reset_host(), chk.reset_host())
+    rng = np.random.default_rng(2)
+    for t in range(60):
+        act = rng.uniform(-1, 1, (N, 15)).astype(np.float32)
+        if t % 2:   # host-buffer call
+            for x, y in zip(ref.step_host(act), chk.step_host(act)):
+                assert np.array_equal(x, y)
+        else:       # device-resident call on torch's current stream
+            a = torch.from_numpy(act).cuda()
+            ref.step(a.data_ptr()); chk.step(a.data_ptr())
+            torch.cuda.synchronize()
+    assert np.array_equal(ref.get_state(), chk.get_state())
+    sr, sc = ref.stats(), chk.stats()
+    for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"):
+        assert sr[k] == sc[k]
+    assert sr["episodes"] > 0 and abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # atomics order
