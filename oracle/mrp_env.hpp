@@ -5,7 +5,11 @@
 //   reference gym_puzzles/envs/multi_robot_puzzle_02.py  (mrp02)  v2 / Heavy-v2
 // on top of oracle/b2core.hpp.  Python float arithmetic is float64, pybox2d b2Vec2
 // arithmetic is float32; each expression below keeps the width the reference has.
-// *** PARITY UNPINNED *** (see b2core.hpp header).
+// Pinning: this env logic IS checked against the reference's own Python, executed unmodified in the build container
+// over a pybox2d stand-in backed by b2core.hpp (tests/refshim, tests/test_reference_python.py) and through the committed
+// fixtures it produced (tests/golden/, tests/test_golden.py): flags and body state identical, observation / reward
+// equal up to the float64 ulps of `**0.5` vs sqrt.  The Box2D arithmetic underneath is *** PARITY UNPINNED ***
+// (see b2core.hpp header).
 //
 // Deliberate differences (DESIGN.md "Deviations"):
 //  * spawns use counter-based Philox instead of numpy's global RNG (north star);
