@@ -25,6 +25,7 @@ EXPORTS = (
     "mrp_last_error", "mrp_backend", "mrp_create", "mrp_destroy", "mrp_get_layout", "mrp_get_buffers", "mrp_reset",
     "mrp_step", "mrp_step_host", "mrp_reset_host", "mrp_sample_actions", "mrp_get_state", "mrp_set_state",
     "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_set_timing", "mrp_get_timing", "mrp_get_phase_timing", "mrp_launch_count",
+    "mrp_enable_terminal_info", "mrp_enable_curriculum",
 )
 
 
@@ -45,6 +46,10 @@ class Buffers(C.Structure):
     _fields_ = [("action_dev", C.c_void_p), ("obs_dev", C.c_void_p), ("reward_dev", C.c_void_p),
                 ("done_dev", C.c_void_p), ("trunc_dev", C.c_void_p), ("stats_dev", C.c_void_p),
                 ("num_envs", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("reserved", C.c_int32)]
+
+
+class TerminalBuffers(C.Structure):
+    _fields_ = [("terminal_obs_dev", C.c_void_p), ("episode_return_dev", C.c_void_p), ("episode_length_dev", C.c_void_p)]
 
 
 class Params(C.Structure):
@@ -78,6 +83,8 @@ class MrpLib:
         L.mrp_step_host.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.mrp_reset_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrp_sample_actions.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.mrp_enable_terminal_info.argtypes = [C.c_void_p, C.POINTER(TerminalBuffers)]
+        L.mrp_enable_curriculum.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.mrp_get_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mrp_set_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.mrp_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
@@ -198,6 +205,18 @@ class Handle:
     def get_params(self):
         p = self.get_params_struct()
         return {n: getattr(p, n) for n, _ in Params._fields_}
+
+    def enable_terminal_info(self):
+        """-> TerminalBuffers (device pointers): terminal observation / episode return / length of envs done this step"""
+        t = TerminalBuffers()
+        self.lib.check(self.lib.lib.mrp_enable_terminal_info(self.h, C.byref(t)), "mrp_enable_terminal_info")
+        return t
+
+    def enable_curriculum(self):
+        """-> (scaled_epsilon_dev, decay_pow_dev): device pointers of the per-env f64[num_envs] curriculum vectors"""
+        e, d = C.c_void_p(), C.c_void_p()
+        self.lib.check(self.lib.lib.mrp_enable_curriculum(self.h, C.byref(e), C.byref(d)), "mrp_enable_curriculum")
+        return e.value, d.value
 
     def stats(self, reset_after=False):
         s = np.zeros(N_STATS, dtype=np.float64)

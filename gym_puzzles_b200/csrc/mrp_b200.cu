@@ -54,6 +54,13 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
     e.store();
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
     if (done) {
+        if (K.term_obs) {  // keep what the auto-reset is about to overwrite
+            const float* orow = K.obs + env * K.obs_dim;
+            float* trow = K.term_obs + env * K.obs_dim;
+            for (int i = 0; i < K.obs_dim; ++i) trow[i] = orow[i];
+            K.term_ret[env] = (float)ret;
+            K.term_len[env] = (int32_t)len;
+        }
         stat_add(K.stats, MRP_STAT_EPISODES, 1.0);
         if (d) stat_add(K.stats, MRP_STAT_DONE_BY_ENV, 1.0);
         if (limit && !d) stat_add(K.stats, MRP_STAT_TRUNCATED, 1.0);
@@ -488,6 +495,11 @@ int mrp_destroy(mrp_handle* h) {
     DEV_FREE(h->K.task_off);
     DEV_FREE(h->K.toi_list);
     DEV_FREE(h->K.narrow_list);
+    DEV_FREE((void*)h->K.eps_env);
+    DEV_FREE((void*)h->K.decay_env);
+    DEV_FREE(h->K.term_obs);
+    DEV_FREE(h->K.term_ret);
+    DEV_FREE(h->K.term_len);
     delete h;
     return 0;
 }
@@ -1053,6 +1065,57 @@ int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uin
     int rc = push_internal(h, env_begin, env_count, buf);
     free(buf);
     if (rc) return fail(-9, "mrp_set_state: copy failed: %s", dev_err());
+    return 0;
+}
+
+int mrp_enable_terminal_info(mrp_handle* h, mrp_terminal_buffers* out) {
+    if (!h || !out) return fail(-1, "mrp_enable_terminal_info: null argument");
+    SimConst& K = h->K;
+    if (!K.term_obs) {
+#ifndef MRP_HOST_EMU
+        cudaSetDevice(h->device);
+#endif
+        const size_t N = (size_t)K.N;
+        int rc = DEV_ALLOC(K.term_obs, sizeof(float) * N * K.obs_dim);
+        rc |= DEV_ALLOC(K.term_ret, sizeof(float) * N);
+        rc |= DEV_ALLOC(K.term_len, sizeof(int32_t) * N);
+        if (rc) {
+            DEV_FREE(K.term_obs); DEV_FREE(K.term_ret); DEV_FREE(K.term_len);
+            K.term_obs = nullptr; K.term_ret = nullptr; K.term_len = nullptr;
+            return fail(-7, "mrp_enable_terminal_info: device allocation failed: %s", dev_err());
+        }
+    }
+    out->terminal_obs_dev = K.term_obs;
+    out->episode_return_dev = K.term_ret;
+    out->episode_length_dev = K.term_len;
+    return 0;
+}
+
+int mrp_enable_curriculum(mrp_handle* h, double** scaled_epsilon_dev, double** decay_pow_dev) {
+    if (!h || !scaled_epsilon_dev || !decay_pow_dev) return fail(-1, "mrp_enable_curriculum: null argument");
+    SimConst& K = h->K;
+    if (!K.eps_env) {
+#ifndef MRP_HOST_EMU
+        cudaSetDevice(h->device);
+#endif
+        const size_t N = (size_t)K.N;
+        double *e = nullptr, *d = nullptr;
+        if (DEV_ALLOC_RAW(e, sizeof(double) * N) | DEV_ALLOC_RAW(d, sizeof(double) * N)) {
+            DEV_FREE(e); DEV_FREE(d);
+            return fail(-7, "mrp_enable_curriculum: device allocation failed: %s", dev_err());
+        }
+        // start from the handle's scalar values
+        double* row = (double*)malloc(sizeof(double) * N);
+        for (size_t i = 0; i < N; ++i) row[i] = K.rp.scaled_epsilon;
+        H2D(e, row, sizeof(double) * N);
+        for (size_t i = 0; i < N; ++i) row[i] = K.rp.decay_pow;
+        H2D(d, row, sizeof(double) * N);
+        free(row);
+        K.eps_env = e;
+        K.decay_env = d;
+    }
+    *scaled_epsilon_dev = (double*)K.eps_env;
+    *decay_pow_dev = (double*)K.decay_env;
     return 0;
 }
 

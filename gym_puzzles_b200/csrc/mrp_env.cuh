@@ -171,6 +171,10 @@ struct Env : Sim {
             *reward_out = reward;
             return done;
         }
+        // curriculum knobs: per-env vectors when installed (mrp_enable_curriculum), else the handle's scalars
+        const int64_t env_ix = G - K.S;
+        const double eps = K.eps_env ? K.eps_env[env_ix] : K.rp.scaled_epsilon;
+        const double decay_pow = K.decay_env ? K.decay_env[env_ix] : K.rp.decay_pow;
         for (int i = 0; i < n; ++i) {
             int b = 1 + i;
             double aX = (double)B(b, 0) * K.ratio, aY = (double)B(b, 1) * K.ratio;
@@ -191,7 +195,7 @@ struct Env : Sim {
             double x = (double)bc.x * K.ratio, y = (double)bc.y * K.ratio;
             double angle = py_mod((double)B(0, 2), kTwoPiD);
             double a_diff = (0.0 - angle) / kPiD;
-            in_place = !(fabs(gx - x) > K.rp.scaled_epsilon) && !(fabs(gy - y) > K.rp.scaled_epsilon);
+            in_place = !(fabs(gx - x) > eps) && !(fabs(gy - y) > eps);
             obs[o++] = (float)(x - gx);
             obs[o++] = (float)(y - gy);
             obs[o++] = (float)a_diff;
@@ -202,7 +206,7 @@ struct Env : Sim {
                 obs[o++] = (float)((double)p.y * K.ratio);
             }
         }
-        obs[o++] = (float)K.rp.scaled_epsilon;
+        obs[o++] = (float)eps;
         reward += (prev_bd - bd) * K.rp.blockDelta;
         reward -= K.rp.blockDistance * bd;
         for (int i = 0; i < n; ++i) {
@@ -217,7 +221,7 @@ struct Env : Sim {
             else if (y < BOUNDS || y > (K.H - BOUNDS)) agt_oob = true;
         }
         if (agt_oob) {
-            reward -= K.rp.outOfBounds * K.rp.decay_pow;
+            reward -= K.rp.outOfBounds * decay_pow;
             *reward_out = reward;
             return true;
         }
@@ -225,7 +229,7 @@ struct Env : Sim {
             double x = (double)bc.x, y = (double)bc.y;
             bool oob = (x < BOUNDS || x > (K.W - BOUNDS)) || (y < BOUNDS || y > (K.H - BOUNDS));
             if (oob) {
-                reward -= K.rp.blkOutOfBounds * K.rp.decay_pow;
+                reward -= K.rp.blkOutOfBounds * decay_pow;
                 *reward_out = reward;
                 return true;
             }
@@ -237,7 +241,7 @@ struct Env : Sim {
         bool done = false;
         if (now == 1) {
             done = true;
-            reward += K.rp.puzzleComp * K.rp.decay_pow * ((double)num_in_contact / (double)n);
+            reward += K.rp.puzzleComp * decay_pow * ((double)num_in_contact / (double)n);
         }
         *reward_out = reward;
         return done;

@@ -86,6 +86,13 @@ struct SimConst {
     int32_t* task_off;    // [..] index of task i's first record in pool
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
     uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * 32 + slot
+    // optional per-env curriculum vectors (NULL: the scalar mrp_params apply): update_goal / update_params per env
+    const double* eps_env;       // [N] scaled_epsilon   (mrp02:232-233)
+    const double* decay_env;     // [N] decay**(-timestep) (mrp02:227-230)
+    // optional terminal records of envs that finished inside this step, written before the auto-reset overwrites them
+    float* term_obs;             // [N][obs_dim] last observation of the finished episode (SB3 "terminal_observation")
+    float* term_ret;             // [N] return of the finished episode (Monitor info["episode"]["r"])
+    int32_t* term_len;           // [N] its length                   (info["episode"]["l"])
 };
 // solver tasks predicted heavy (by W_HINT) are queued from slot 0 upwards, the others from slot N-1 downwards;
 // consumers take the heavy ones first so that long solves start early and short ones fill the tail

@@ -67,7 +67,14 @@ class MultiRobotPuzzle:
         return obs[0].copy(), float(rew[0]), bool(done[0]), info
 
     def render(self, mode="human", close=False):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path; use the reference viewer on get_state()")
+        """reference mrp00:528-592 / mrp02:590-707.  'rgb_array' is drawn on the host from get_state() by
+        gym_puzzles_b200.render (numpy, no pyglet); an interactive window ('human') is not provided."""
+        if close:
+            return None
+        if mode == "rgb_array":
+            from . import render as _render
+            return _render.rgb_array(self._h, 0)
+        raise NotImplementedError("only render(mode='rgb_array') is provided; rendering is host-side and outside the B200 hot path")
 
     def close(self):
         self._h.close()

@@ -58,6 +58,30 @@ class VectorEnv:
         self.truncated = _wrap(torch, b.trunc_dev, (num_envs,), "|b1", h, dev)
         self.stats_tensor = _wrap(torch, b.stats_dev, (abi.N_STATS,), "<f8", h, dev)
         self._step_index = 0
+        self.terminal_obs = self.episode_return = self.episode_length = None
+        self.scaled_epsilon = self.decay_pow = None
+
+    # ------------------------------------------------------------------ SURVEY.md §8f "next" rows
+    def enable_terminal_info(self):
+        """Keep, for envs that finish inside step(), the last observation of the episode and its return / length
+        (SB3's infos[i]["terminal_observation"], Monitor's info["episode"]): `terminal_obs[N, O]`,
+        `episode_return[N]`, `episode_length[N]` — rows are valid where `done` is set by the same step."""
+        if self.terminal_obs is None:
+            t, h, dev, torch = self.handle.enable_terminal_info(), self.handle, self.device, self.torch
+            self.terminal_obs = _wrap(torch, t.terminal_obs_dev, (self.num_envs, h.obs_dim), "<f4", h, dev)
+            self.episode_return = _wrap(torch, t.episode_return_dev, (self.num_envs,), "<f4", h, dev)
+            self.episode_length = _wrap(torch, t.episode_length_dev, (self.num_envs,), "<i4", h, dev)
+        return self.terminal_obs, self.episode_return, self.episode_length
+
+    def enable_curriculum(self):
+        """Per-env curriculum vectors (float64 CUDA tensors [N], written by the caller, read by the next step):
+        `scaled_epsilon` = update_goal's tolerance (mrp02:232-233), `decay_pow` = decay**(-timestep) of update_params
+        (mrp02:227-230).  After this, update_goal / update_params also accept per-env arrays."""
+        if self.scaled_epsilon is None:
+            e, d = self.handle.enable_curriculum()
+            self.scaled_epsilon = _wrap(self.torch, e, (self.num_envs,), "<f8", self.handle, self.device)
+            self.decay_pow = _wrap(self.torch, d, (self.num_envs,), "<f8", self.handle, self.device)
+        return self.scaled_epsilon, self.decay_pow
 
     # ------------------------------------------------------------------ core API
     def _stream(self):
@@ -113,13 +137,37 @@ class VectorEnv:
             kw[k] = cur[k] if v is None else v
         self.handle.set_params(**kw)
 
+    def _per_env(self, x):
+        t = self.torch
+        return t.is_tensor(x) or (hasattr(x, "__len__") and len(x) == self.num_envs)
+
     def update_params(self, timestep, decay):
-        """reference mrp02:227-230: shaped rewards = base * decay**(-timestep)."""
-        self.handle.set_params(decay_pow=float(decay) ** (-float(timestep)))
+        """reference mrp02:227-230: shaped rewards = base * decay**(-timestep).  Arrays / tensors of length N set
+        the value per env (needs enable_curriculum(); computed in float64 like the reference's Python)."""
+        if self._per_env(timestep) or self._per_env(decay):
+            self.enable_curriculum()
+            t = self.torch
+            ts = t.as_tensor(timestep, dtype=t.float64, device=self.device)
+            dc = t.as_tensor(decay, dtype=t.float64, device=self.device)
+            self.decay_pow.copy_((dc ** (-ts)).expand(self.num_envs))
+            return
+        v = float(decay) ** (-float(timestep))
+        self.handle.set_params(decay_pow=v)
+        if self.decay_pow is not None:
+            self.decay_pow.fill_(v)
 
     def update_goal(self, epoch, nb_epochs):
         """reference mrp02:232-233: scaled_epsilon = EPSILON * (2 - epoch / nb_epochs), EPSILON = 0.1."""
-        self.handle.set_params(scaled_epsilon=0.1 * (2 - epoch / nb_epochs))
+        if self._per_env(epoch):
+            self.enable_curriculum()
+            t = self.torch
+            ep = t.as_tensor(epoch, dtype=t.float64, device=self.device)
+            self.scaled_epsilon.copy_(0.1 * (2 - ep / nb_epochs))
+            return
+        v = 0.1 * (2 - epoch / nb_epochs)
+        self.handle.set_params(scaled_epsilon=v)
+        if self.scaled_epsilon is not None:
+            self.scaled_epsilon.fill_(v)
 
     def get_deltaAgent(self):
         return self.handle.get_params()["agentDelta"]

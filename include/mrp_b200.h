@@ -106,6 +106,24 @@ int mrp_sample_actions(mrp_handle* h, uint64_t step_index, float* dst_dev, void*
 int mrp_get_state(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t* words_host);
 int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uint32_t* words_host);
 
+/* "Next" rows of SURVEY.md §8f — what the reference's callers (train/train.py:63-82: Monitor, DummyVecEnv,
+ * VecNormalize) need from a batched env that resets inside step():
+ * the last observation of a finished episode (SB3 infos[i]["terminal_observation"]) and its return / length
+ * (Monitor's info["episode"] = {"r", "l"}), kept in library-owned buffers before the auto-reset overwrites them.
+ * Rows are valid for envs whose done flag is set by the same step.  Off (no cost) until enabled. */
+typedef struct mrp_terminal_buffers {
+    float* terminal_obs_dev;     /* f32[num_envs][obs_dim] */
+    float* episode_return_dev;   /* f32[num_envs] */
+    int32_t* episode_length_dev; /* i32[num_envs] */
+} mrp_terminal_buffers;
+int mrp_enable_terminal_info(mrp_handle* h, mrp_terminal_buffers* out);
+
+/* Per-env curriculum: update_goal(epoch, nb_epochs) (mrp02:232-233) and update_params(timestep, decay)
+ * (mrp02:227-230) as vectors, one value per env, so that envs of one batch can sit at different curriculum stages.
+ * Returns library-owned device arrays f64[num_envs] initialised from the scalar mrp_params; the caller writes them
+ * (stream-ordered before mrp_step).  v2 family only (v0 uses the fixed EPSILON = 25 px, mrp00:54). */
+int mrp_enable_curriculum(mrp_handle* h, double** scaled_epsilon_dev, double** decay_pow_dev);
+
 int mrp_set_params(mrp_handle* h, const mrp_params* p);
 int mrp_get_params(mrp_handle* h, mrp_params* p);
 

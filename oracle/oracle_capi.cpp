@@ -78,6 +78,15 @@ int orc_set_params(void* h, const double* p9) {
     }
     return 0;
 }
+// per-env curriculum vectors (update_goal / update_params per env; checker for mrp_enable_curriculum)
+int orc_set_curriculum(void* h, const double* eps, const double* decay_pow) {
+    OrcBatch* b = (OrcBatch*)h;
+    for (size_t i = 0; i < b->envs.size(); ++i) {
+        if (eps) b->envs[i]->rp.scaled_epsilon = eps[i];
+        if (decay_pow) b->envs[i]->rp.decay_pow = decay_pow[i];
+    }
+    return 0;
+}
 int orc_get_params(void* h, double* p9) {
     Env* e = ((OrcBatch*)h)->envs[0];
     p9[0] = e->rp.agentDelta; p9[1] = e->rp.agentDistance; p9[2] = e->rp.blockDelta; p9[3] = e->rp.blockDistance;

@@ -79,6 +79,11 @@ class OracleBatch:
         p = np.ascontiguousarray(p9, dtype=np.float64)
         self.L.orc_set_params(self.h, _p(p))
 
+    def set_curriculum(self, eps=None, decay_pow=None):
+        e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float64)
+        d = None if decay_pow is None else np.ascontiguousarray(decay_pow, dtype=np.float64)
+        self.L.orc_set_curriculum(self.h, None if e is None else _p(e), None if d is None else _p(d))
+
     def get_params(self):
         p = np.zeros(9)
         self.L.orc_get_params(self.h, _p(p))
