@@ -42,8 +42,9 @@
 namespace {
 
 constexpr int kVnMaxObs = 96;              // columns (66 for v2 with 5 agents)
-constexpr int kVnColsPerLane = kVnMaxObs / 32;
 constexpr int kVnBlock = 256;
+constexpr int kVnSlots = 8;               // shared-memory partial-sum copies per CTA (one per warp)
+constexpr int kVnBlockM = 256;           // moments CTA (1024-thread CTAs at 2 per SM measured 2x slower: 32 registers per thread)
 
 struct VnConst {
     int32_t N, O;
@@ -61,47 +62,66 @@ struct VnConst {
 };
 
 #ifndef MRP_HOST_EMU
-__global__ void __launch_bounds__(kVnBlock) k_vn_moments(const __grid_constant__ VnConst V, const float* __restrict__ obs,
-                                                          const float* __restrict__ rew) {
-    __shared__ double red[2][kVnBlock / 32][kVnMaxObs + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = kVnBlock / 32;
-    const int O = V.O;
-    double s1[kVnColsPerLane], s2[kVnColsPerLane];
-    float m[kVnColsPerLane];
+// Flat float4 walk over obs[N*O]: `nthr` threads (a multiple of O / gcd(O, 4), so 4 * nthr is a multiple of O) each
+// stride by nthr float4s, which keeps the four columns a thread touches fixed for the whole walk: running means and the
+// eight f64 partial sums live in registers, four independent 16-byte loads are in flight per thread.
+__global__ void __launch_bounds__(kVnBlockM) k_vn_moments(const __grid_constant__ VnConst V, const float* __restrict__ obs,
+                                                          const float* __restrict__ rew, int64_t nthr) {
+    // partial sums per warp (keeps the contention of the shared-memory f64 atomics low)
+    __shared__ double redw[kVnSlots][2][kVnMaxObs + 1];
+    const int O = V.O, slot = threadIdx.x / (kVnBlockM / kVnSlots);
+    for (int i = threadIdx.x; i < kVnSlots * 2 * (kVnMaxObs + 1); i += kVnBlockM) (&redw[0][0][0])[i] = 0.0;
+    __syncthreads();
+    double (*red)[kVnMaxObs + 1] = redw[slot];
+    const int64_t tid = (int64_t)blockIdx.x * kVnBlockM + threadIdx.x;
+    if (obs && tid < nthr) {
+        const int64_t total = (int64_t)V.N * O, n4 = total >> 2;
+        int col[4];
+        double m[4], s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < kVnColsPerLane; ++c) {
-        s1[c] = 0.0; s2[c] = 0.0;
-        const int col = lane + 32 * c;
-        m[c] = col < O ? (float)V.mean[col] : 0.0f;
-    }
-    // each warp walks rows gw, gw + W, ...; four rows in flight per trip for memory-level parallelism
-    const int64_t W = (int64_t)gridDim.x * nwarp, gw = (int64_t)blockIdx.x * nwarp + warp;
-    constexpr int U = 4;
-    for (int64_t r0 = gw; obs && r0 < V.N; r0 += U * W) {
-        float x[U][kVnColsPerLane];
+        for (int j = 0; j < 4; ++j) {
+            col[j] = (int)((4 * tid + j) % O);
+            m[j] = (double)(float)V.mean[col[j]];
+        }
+        const float4* in4 = reinterpret_cast<const float4*>(obs);
+        constexpr int U = 4;
+        int64_t i = tid;
+        for (; i + (U - 1) * nthr < n4; i += U * nthr) {
+            float4 x[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t r = r0 + u * W;
+            for (int u = 0; u < U; ++u) x[u] = __ldg(in4 + i + u * nthr);
 #pragma unroll
-            for (int c = 0; c < kVnColsPerLane; ++c) {
-                const int col = lane + 32 * c;
-                x[u][c] = (r < V.N && col < O) ? __ldg(obs + r * O + col) : m[c];
+            for (int u = 0; u < U; ++u) {
+                const double d0 = (double)x[u].x - m[0], d1 = (double)x[u].y - m[1], d2 = (double)x[u].z - m[2], d3 = (double)x[u].w - m[3];
+                s1[0] += d0; s2[0] += d0 * d0;
+                s1[1] += d1; s2[1] += d1 * d1;
+                s1[2] += d2; s2[2] += d2 * d2;
+                s1[3] += d3; s2[3] += d3 * d3;
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int c = 0; c < kVnColsPerLane; ++c) {
-                const double d = (double)x[u][c] - (double)m[c];
-                s1[c] += d;
-                s2[c] += d * d;
+        for (; i < n4; i += nthr) {
+            const float4 x = __ldg(in4 + i);
+            const double d0 = (double)x.x - m[0], d1 = (double)x.y - m[1], d2 = (double)x.z - m[2], d3 = (double)x.w - m[3];
+            s1[0] += d0; s2[0] += d0 * d0;
+            s1[1] += d1; s2[1] += d1 * d1;
+            s1[2] += d2; s2[2] += d2 * d2;
+            s1[3] += d3; s2[3] += d3 * d3;
+        }
+        if (tid == 0)   // up to three trailing elements when N*O is not a multiple of 4
+            for (int64_t e = n4 << 2; e < total; ++e) {
+                const int c = (int)(e % O);
+                const double d = (double)obs[e] - (double)(float)V.mean[c];
+                atomicAdd(&red[0][c], d);
+                atomicAdd(&red[1][c], d * d);
             }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { atomicAdd(&red[0][col[j]], s1[j]); atomicAdd(&red[1][col[j]], s2[j]); }
     }
     // discounted returns (column O): thread per env
-    double r1 = 0.0, r2 = 0.0;
     if (rew) {
+        double r1 = 0.0, r2 = 0.0;
         const double mr = V.mean[O];
-        for (int64_t e = (int64_t)blockIdx.x * kVnBlock + threadIdx.x; e < V.N; e += (int64_t)gridDim.x * kVnBlock) {
+        for (int64_t e = tid; e < V.N; e += (int64_t)gridDim.x * kVnBlockM) {
             const double ret = V.returns[e] * V.gamma + (double)rew[e];
             V.returns[e] = ret;
             const double d = ret - mr;
@@ -109,22 +129,16 @@ __global__ void __launch_bounds__(kVnBlock) k_vn_moments(const __grid_constant__
             r2 += d * d;
         }
         for (int o = 16; o > 0; o >>= 1) { r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&red[0][O], r1); atomicAdd(&red[1][O], r2); }
     }
-#pragma unroll
-    for (int c = 0; c < kVnColsPerLane; ++c) {
-        const int col = lane + 32 * c;
-        if (col < O) { red[0][warp][col] = s1[c]; red[1][warp][col] = s2[c]; }
-    }
-    if (lane == 0) { red[0][warp][O] = r1; red[1][warp][O] = r2; }
     __syncthreads();
-    for (int col = threadIdx.x; col <= O; col += kVnBlock) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < nwarp; ++w) { a += red[0][w][col]; b += red[1][w][col]; }
-        if (col < O ? obs != nullptr : rew != nullptr) {
-            atomicAdd(V.accum + col, a);
-            atomicAdd(V.accum + (O + 1) + col, b);
+    for (int c = threadIdx.x; c <= O; c += kVnBlockM)
+        if (c < O ? obs != nullptr : rew != nullptr) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < kVnSlots; ++w) { a += redw[w][0][c]; b += redw[w][1][c]; }
+            atomicAdd(V.accum + c, a);
+            atomicAdd(V.accum + (O + 1) + c, b);
         }
-    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (obs) atomicAdd(V.accum + 2 * (O + 1), (double)V.N);
         if (rew) atomicAdd(V.accum + 2 * (O + 1) + 1, (double)V.N);
@@ -188,26 +202,29 @@ __global__ void __launch_bounds__(kVnBlock) k_vn_apply(const __grid_constant__ V
     const int64_t total = (int64_t)V.N * O, stride = (int64_t)gridDim.x * kVnBlock;
     const int64_t tid = (int64_t)blockIdx.x * kVnBlock + threadIdx.x;
     if (obs_out) {
-        if ((total & 3) == 0 && (O & 3) == 0) {   // rows are 16-byte multiples: float4 path
-            const float4* in4 = reinterpret_cast<const float4*>(obs);
-            float4* out4 = reinterpret_cast<float4*>(obs_out);
-            for (int64_t i = tid; i < total / 4; i += stride) {
-                float4 v = V.norm_obs ? __ldg(in4 + i) : in4[i];
-                if (V.norm_obs) {
-                    const int c = (int)((i * 4) % O);
-                    v.x = vn_norm(v.x, sm[c], si[c], V.clip_obs);
-                    v.y = vn_norm(v.y, sm[c + 1], si[c + 1], V.clip_obs);
-                    v.z = vn_norm(v.z, sm[c + 2], si[c + 2], V.clip_obs);
-                    v.w = vn_norm(v.w, sm[c + 3], si[c + 3], V.clip_obs);
-                }
-                out4[i] = v;
+        // flat float4 walk (obs is contiguous, so this holds for any O); columns advance with wrap-around
+        const int64_t n4 = total >> 2;
+        const float4* in4 = reinterpret_cast<const float4*>(obs);
+        float4* out4 = reinterpret_cast<float4*>(obs_out);
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 v = __ldg(in4 + i);
+            if (V.norm_obs) {
+                int c0 = (int)((i * 4) % O);
+                int c1 = c0 + 1 == O ? 0 : c0 + 1;
+                int c2 = c1 + 1 == O ? 0 : c1 + 1;
+                int c3 = c2 + 1 == O ? 0 : c2 + 1;
+                v.x = vn_norm(v.x, sm[c0], si[c0], V.clip_obs);
+                v.y = vn_norm(v.y, sm[c1], si[c1], V.clip_obs);
+                v.z = vn_norm(v.z, sm[c2], si[c2], V.clip_obs);
+                v.w = vn_norm(v.w, sm[c3], si[c3], V.clip_obs);
             }
-        } else {
-            for (int64_t i = tid; i < total; i += stride) {
-                const float x = obs[i];
-                obs_out[i] = V.norm_obs ? vn_norm(x, sm[(int)(i % O)], si[(int)(i % O)], V.clip_obs) : x;
-            }
+            out4[i] = v;
         }
+        if (tid == 0)
+            for (int64_t e = n4 << 2; e < total; ++e) {
+                const float x = obs[e];
+                obs_out[e] = V.norm_obs ? vn_norm(x, sm[(int)(e % O)], si[(int)(e % O)], V.clip_obs) : x;
+            }
     }
     for (int64_t e = tid; e < V.N; e += stride) {
         const bool d = done && done[e];
@@ -362,10 +379,18 @@ int mrp_vecnorm_moments(mrp_vecnorm* vn, const float* obs_dev, const float* rewa
     const VnConst& V = vn->V;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(vn->device);
-    const int64_t rows_per_cta = (kVnBlock / 32) * 4;
-    int64_t grid = (V.N + rows_per_cta - 1) / rows_per_cta;
-    if (grid > 148 * 8) grid = 148 * 8;   // persistent: 8 CTAs of 256 threads per SM
-    k_vn_moments<<<(unsigned)grid, kVnBlock, 0, (cudaStream_t)stream>>>(V, V.norm_obs ? obs_dev : nullptr, V.norm_reward ? reward_dev : nullptr);
+    // persistent grid: 8 CTAs of 256 threads per SM (fewer for small batches); the obs walk uses the largest thread
+    // count that is a multiple of O / gcd(O, 4)
+    const int64_t n4 = ((int64_t)V.N * V.O) >> 2;
+    int64_t grid = (n4 / 4 + kVnBlockM - 1) / kVnBlockM;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    int g = 4, o = V.O;
+    while (o) { int t = g % o; g = o; o = t; }   // gcd(4, O)
+    const int64_t L = V.O / g;
+    int64_t nthr = grid * kVnBlockM / L * L;
+    if (nthr < L) { grid = (L + kVnBlockM - 1) / kVnBlockM; nthr = L; }
+    k_vn_moments<<<(unsigned)grid, kVnBlockM, 0, (cudaStream_t)stream>>>(V, V.norm_obs ? obs_dev : nullptr, V.norm_reward ? reward_dev : nullptr, nthr);
     vn->launches += 1;
     if (cudaGetLastError() != cudaSuccess) return vn_fail(-10, "mrp_vecnorm_moments: launch failed");
 #else
