@@ -8,11 +8,28 @@
 // The same translation unit also builds as plain C++ with -DMRP_HOST_EMU (g++ -x c++) into
 // tests/emu/libmrp_emu.so: a host execution of the *kernel source* used only to debug
 // kernel logic in the GPU-less build container.  The Python package never loads it.
+//
+// This file is compiled TWICE into the library: once as is (contact capacity 32: every registered variant) and once
+// with -DMRP_MAXC=192 ("wide": MultiRobotPuzzle2(num_agents > 2), mrp02:139).  The wide compilation renames its
+// namespace, its handle type and its entry points (suffix _wide) so the two live side by side; the default build's
+// entry points forward to the wide ones for handles created with such a configuration.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <new>
+
+#ifndef MRP_MAXC
+#define MRP_MAXC 32
+#endif
+#if MRP_MAXC > 32
+#define MRP_WIDE 1
+#define mrp mrp_wide                 // namespace of all inline code (the two builds differ in array sizes: keep the ODR)
+#define mrp_handle mrp_handle_wide
+#define MRP_API(name) name##_wide
+#else
+#define MRP_API(name) name
+#endif
 
 #include "mrp_env.cuh"
 #include "mrp_variant.hpp"
@@ -174,8 +191,17 @@ MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env
 }
 
 // fused single-lane step (used by the host emulation's reference path and kept for debugging)
+// Constraint records of the fused per-env paths (fused step, TOI event pass, reset): a lane-local array in the default
+// build; the wide build (192 x 38 words) borrows the env's own slice of the task pool, which no solver kernel of the
+// same chunk touches while these paths run.
+#ifdef MRP_WIDE
+#define MRP_VC_SCRATCH(K, env) float* vc_local = (K).pool + (size_t)((env) - (K).env0) * (K).maxc * VC_WORDS
+#else
+#define MRP_VC_SCRATCH(K, env) float vc_local[kMaxC * VC_WORDS]
+#endif
+
 MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    float vc_local[kMaxC * VC_WORDS];
+    MRP_VC_SCRATCH(K, env);
     Env e(K, sm, ct, env, vc_local);
     e.load();
     float a[3 * MRP_MAX_AGENTS];
@@ -187,7 +213,7 @@ MRP_HD void step_lane(const SimConst& K, float* sm, const float* ct, int64_t env
 }
 
 MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
-    float vc_local[kMaxC * VC_WORDS];
+    MRP_VC_SCRATCH(K, env);
     Env e(K, sm, ct, env, vc_local);
     e.reset_env(K.obs + env * K.obs_dim);
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
@@ -347,8 +373,9 @@ __global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ 
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock) {
-        float vc_local[kMaxC * VC_WORDS];
-        post_lane(K, smem + kCtPad + threadIdx.x, ct, K.toi_list[i], true, vc_local);
+        const int64_t env = K.toi_list[i];
+        MRP_VC_SCRATCH(K, env);
+        post_lane(K, smem + kCtPad + threadIdx.x, ct, env, true, vc_local);
     }
 }
 
@@ -389,6 +416,9 @@ __global__ void k_fix_rot(const __grid_constant__ SimConst K, int64_t begin, int
 constexpr int kMaxChunks = 8;
 
 struct mrp_handle {
+#ifndef MRP_WIDE
+    struct mrp_handle_wide* wide;   // set: this handle only fronts a wide-capacity handle (every call forwards to it)
+#endif
     SimConst K;
     mrp_layout L;
     int device;
@@ -453,11 +483,47 @@ static int check_launch(const char* what) {
 }
 #endif
 
+#ifndef MRP_WIDE
+// entry points of the wide-capacity compilation of this file (same signatures, suffix _wide)
+extern "C" {
+const char* mrp_last_error_wide(void);
+int mrp_destroy_wide(mrp_handle_wide*);
+int mrp_create_wide(const mrp_config*, mrp_handle_wide**);
+int mrp_get_layout_wide(mrp_handle_wide*, mrp_layout*);
+int mrp_get_buffers_wide(mrp_handle_wide*, mrp_buffers*);
+int mrp_reset_wide(mrp_handle_wide*, const uint8_t*, void*);
+int mrp_set_timing_wide(mrp_handle_wide*, int32_t);
+int mrp_get_timing_wide(mrp_handle_wide*, double*, int64_t*, int32_t);
+int mrp_get_phase_timing_wide(mrp_handle_wide*, double*, int32_t);
+int mrp_step_wide(mrp_handle_wide*, const float*, void*);
+int mrp_step_host_wide(mrp_handle_wide*, const float*, float*, float*, uint8_t*, uint8_t*);
+int mrp_reset_host_wide(mrp_handle_wide*, const uint8_t*, float*);
+int mrp_sample_actions_wide(mrp_handle_wide*, uint64_t, float*, void*);
+int mrp_get_state_wide(mrp_handle_wide*, int32_t, int32_t, uint32_t*);
+int mrp_set_state_wide(mrp_handle_wide*, int32_t, int32_t, const uint32_t*);
+int mrp_enable_terminal_info_wide(mrp_handle_wide*, mrp_terminal_buffers*);
+int mrp_enable_curriculum_wide(mrp_handle_wide*, double**, double**);
+int mrp_set_params_wide(mrp_handle_wide*, const mrp_params*);
+int mrp_get_params_wide(mrp_handle_wide*, mrp_params*);
+int mrp_get_stats_wide(mrp_handle_wide*, double*, int32_t);
+int64_t mrp_launch_count_wide(mrp_handle_wide*);
+}
+// forward a call on a fronting handle to the wide build, carrying its error text over
+#define FWD(call)                                                                          \
+    if (h && h->wide) {                                                                    \
+        const int rc_ = (call);                                                            \
+        if (rc_) snprintf(g_err, sizeof(g_err), "%s", mrp_last_error_wide());              \
+        return rc_;                                                                        \
+    }
+#else
+#define FWD(call)
+#endif
+
 extern "C" {
 
-const char* mrp_last_error(void) { return g_err; }
+const char* MRP_API(mrp_last_error)(void) { return g_err; }
 
-const char* mrp_backend(void) {
+const char* MRP_API(mrp_backend)(void) {
 #ifdef MRP_HOST_EMU
     return "host-emu (test only)";
 #else
@@ -465,13 +531,20 @@ const char* mrp_backend(void) {
 #endif
 }
 
-int mrp_set_timing(mrp_handle* h, int32_t enable);
+int MRP_API(mrp_set_timing)(mrp_handle* h, int32_t enable);
 
-int mrp_destroy(mrp_handle* h) {
+int MRP_API(mrp_destroy)(mrp_handle* h) {
     if (!h) return 0;
+#ifndef MRP_WIDE
+    if (h->wide) {
+        const int rc = mrp_destroy_wide(h->wide);
+        delete h;
+        return rc;
+    }
+#endif
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
-    if (h->timing) mrp_set_timing(h, 0);
+    if (h->timing) MRP_API(mrp_set_timing)(h, 0);
     if (h->cfork) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); }
         cudaEventDestroy(h->cfork);
@@ -504,11 +577,11 @@ int mrp_destroy(mrp_handle* h) {
     return 0;
 }
 
-int mrp_create(const mrp_config* cfg, mrp_handle** out) {
+int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (!cfg || !out) return fail(-1, "mrp_create: null argument");
     *out = nullptr;
     if (cfg->num_envs <= 0) return fail(-2, "mrp_create: num_envs must be > 0");
-    if (cfg->num_envs > (1 << 26)) return fail(-2, "mrp_create: num_envs must be <= 67108864 per handle");
+    if (cfg->num_envs > (int)(0xffffffffu / (uint32_t)kMaxC)) return fail(-2, "mrp_create: num_envs too large for one handle (2^32 / contact capacity)");
 #ifndef MRP_HOST_EMU
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -519,10 +592,22 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     mrp_handle* h = new (std::nothrow) mrp_handle();
     if (!h) return fail(-5, "mrp_create: out of host memory");
     memset(h, 0, sizeof(*h));
+#ifndef MRP_WIDE
+    if (cfg->variant >= 2 && cfg->n_agents > 2) {  // MultiRobotPuzzle2(num_agents > 2): contact capacity 192 build
+        const int rc = mrp_create_wide(cfg, &h->wide);
+        if (rc) {
+            snprintf(g_err, sizeof(g_err), "%s", mrp_last_error_wide());
+            delete h;
+            return rc;
+        }
+        *out = h;
+        return 0;
+    }
+#endif
     float ctab[CT_WORDS];
     if (build_variant(cfg->variant, cfg->n_agents, &h->K, ctab, &h->L) != 0) {
         delete h;
-        return fail(-6, "mrp_create: bad variant / n_agents (v2 variants support num_agents <= 2 in this build)");
+        return fail(-6, "mrp_create: bad variant / n_agents (1..8 robots)");
     }
     SimConst& K = h->K;
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
@@ -565,7 +650,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
-        mrp_destroy(h);
+        MRP_API(mrp_destroy)(h);
         return -7;
     }
     K.ctab = h->ctab_dev;
@@ -614,7 +699,7 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
         }
     }
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
-    if (check_launch("mrp_create")) { mrp_destroy(h); return -10; }
+    if (check_launch("mrp_create")) { MRP_API(mrp_destroy)(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
     memcpy(h->ctab_dev, ctab, sizeof(ctab));
@@ -623,13 +708,15 @@ int mrp_create(const mrp_config* cfg, mrp_handle** out) {
     return 0;
 }
 
-int mrp_get_layout(mrp_handle* h, mrp_layout* out) {
+int MRP_API(mrp_get_layout)(mrp_handle* h, mrp_layout* out) {
+    FWD(mrp_get_layout_wide(h->wide, out))
     if (!h || !out) return fail(-1, "mrp_get_layout: null argument");
     *out = h->L;
     return 0;
 }
 
-int mrp_get_buffers(mrp_handle* h, mrp_buffers* out) {
+int MRP_API(mrp_get_buffers)(mrp_handle* h, mrp_buffers* out) {
+    FWD(mrp_get_buffers_wide(h->wide, out))
     if (!h || !out) return fail(-1, "mrp_get_buffers: null argument");
     out->action_dev = h->act_dev;
     out->obs_dev = h->K.obs;
@@ -646,7 +733,8 @@ int mrp_get_buffers(mrp_handle* h, mrp_buffers* out) {
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-int mrp_reset(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
+int MRP_API(mrp_reset)(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
+    FWD(mrp_reset_wide(h->wide, mask_dev, stream))
     if (!h) return fail(-1, "mrp_reset: null handle");
     SimConst K = h->K;
     K.reset_mask = mask_dev;
@@ -679,7 +767,8 @@ static void drain_timing(mrp_handle* h) {
 }
 #endif
 
-int mrp_set_timing(mrp_handle* h, int32_t enable) {
+int MRP_API(mrp_set_timing)(mrp_handle* h, int32_t enable) {
+    FWD(mrp_set_timing_wide(h->wide, enable))
     if (!h) return fail(-1, "mrp_set_timing: null handle");
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
@@ -700,7 +789,8 @@ int mrp_set_timing(mrp_handle* h, int32_t enable) {
     return 0;
 }
 
-int mrp_get_timing(mrp_handle* h, double* total_ms, int64_t* count, int32_t reset_after) {
+int MRP_API(mrp_get_timing)(mrp_handle* h, double* total_ms, int64_t* count, int32_t reset_after) {
+    FWD(mrp_get_timing_wide(h->wide, total_ms, count, reset_after))
     if (!h || !total_ms || !count) return fail(-1, "mrp_get_timing: null argument");
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
@@ -712,7 +802,8 @@ int mrp_get_timing(mrp_handle* h, double* total_ms, int64_t* count, int32_t rese
     return 0;
 }
 
-int mrp_get_phase_timing(mrp_handle* h, double* ms5, int32_t reset_after) {
+int MRP_API(mrp_get_phase_timing)(mrp_handle* h, double* ms5, int32_t reset_after) {
+    FWD(mrp_get_phase_timing_wide(h->wide, ms5, reset_after))
     if (!h || !ms5) return fail(-1, "mrp_get_phase_timing: null argument");
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
@@ -826,8 +917,9 @@ static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
         for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
         const int ntoi = K.cnt[CNT_TOI];
         for (int i = 0; i < ntoi; ++i) {
-            float vc_local[kMaxC * VC_WORDS];
-            post_lane(K, h->emu_sm, h->ctab_dev, K.toi_list[i], true, vc_local);
+            const int64_t env = K.toi_list[i];
+            MRP_VC_SCRATCH(K, env);
+            post_lane(K, h->emu_sm, h->ctab_dev, env, true, vc_local);
         }
     }
     if (K.auto_reset) {
@@ -844,7 +936,8 @@ static int step_chunks(const mrp_handle* h, int wanted) {
     return nch < 1 ? 1 : nch;
 }
 
-int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
+int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
+    FWD(mrp_step_wide(h->wide, actions_dev, stream))
     if (!h) return fail(-1, "mrp_step: null handle");
     SimConst K = h->K;
     if (actions_dev) K.act = actions_dev;
@@ -872,8 +965,9 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream) {
 #endif
 }
 
-int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
                   uint8_t* trunc_host) {
+    FWD(mrp_step_host_wide(h->wide, actions_host, obs_host, reward_host, done_host, trunc_host))
     if (!h || !actions_host) return fail(-1, "mrp_step_host: null argument");
     const SimConst& K0 = h->K;
 #ifndef MRP_HOST_EMU
@@ -918,7 +1012,8 @@ int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, flo
 #endif
 }
 
-int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host) {
+int MRP_API(mrp_reset_host)(mrp_handle* h, const uint8_t* mask_host, float* obs_host) {
+    FWD(mrp_reset_host_wide(h->wide, mask_host, obs_host))
     if (!h) return fail(-1, "mrp_reset_host: null handle");
     const size_t N = (size_t)h->K.N;
     uint8_t* mask_dev = nullptr;
@@ -927,7 +1022,7 @@ int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host) {
         mask_dev = h->K.done;
         if (H2D(mask_dev, mask_host, N)) return fail(-8, "mrp_reset_host: H2D failed: %s", dev_err());
     }
-    int rc = mrp_reset(h, mask_dev, nullptr);
+    int rc = MRP_API(mrp_reset)(h, mask_dev, nullptr);
     if (rc) return rc;
     if (obs_host && D2H(obs_host, h->K.obs, sizeof(float) * N * h->K.obs_dim)) return fail(-9, "mrp_reset_host: D2H failed: %s", dev_err());
 #ifndef MRP_HOST_EMU
@@ -936,7 +1031,8 @@ int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host) {
     return 0;
 }
 
-int mrp_sample_actions(mrp_handle* h, uint64_t step_index, float* dst_dev, void* stream) {
+int MRP_API(mrp_sample_actions)(mrp_handle* h, uint64_t step_index, float* dst_dev, void* stream) {
+    FWD(mrp_sample_actions_wide(h->wide, step_index, dst_dev, stream))
     if (!h) return fail(-1, "mrp_sample_actions: null handle");
     float* dst = dst_dev ? dst_dev : h->act_dev;
 #ifndef MRP_HOST_EMU
@@ -982,7 +1078,8 @@ static int push_internal(mrp_handle* h, int64_t begin, int64_t count, const uint
     return 0;
 }
 
-int mrp_get_state(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t* words) {
+int MRP_API(mrp_get_state)(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t* words) {
+    FWD(mrp_get_state_wide(h->wide, env_begin, env_count, words))
     if (!h || !words) return fail(-1, "mrp_get_state: null argument");
     if (env_begin < 0 || env_count < 0 || (int64_t)env_begin + env_count > h->K.N) return fail(-2, "mrp_get_state: bad env range");
     const SimConst& K = h->K;
@@ -1024,7 +1121,8 @@ int mrp_get_state(mrp_handle* h, int32_t env_begin, int32_t env_count, uint32_t*
     return 0;
 }
 
-int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uint32_t* words) {
+int MRP_API(mrp_set_state)(mrp_handle* h, int32_t env_begin, int32_t env_count, const uint32_t* words) {
+    FWD(mrp_set_state_wide(h->wide, env_begin, env_count, words))
     if (!h || !words) return fail(-1, "mrp_set_state: null argument");
     if (env_begin < 0 || env_count < 0 || (int64_t)env_begin + env_count > h->K.N) return fail(-2, "mrp_set_state: bad env range");
     const SimConst& K = h->K;
@@ -1068,7 +1166,8 @@ int mrp_set_state(mrp_handle* h, int32_t env_begin, int32_t env_count, const uin
     return 0;
 }
 
-int mrp_enable_terminal_info(mrp_handle* h, mrp_terminal_buffers* out) {
+int MRP_API(mrp_enable_terminal_info)(mrp_handle* h, mrp_terminal_buffers* out) {
+    FWD(mrp_enable_terminal_info_wide(h->wide, out))
     if (!h || !out) return fail(-1, "mrp_enable_terminal_info: null argument");
     SimConst& K = h->K;
     if (!K.term_obs) {
@@ -1091,7 +1190,8 @@ int mrp_enable_terminal_info(mrp_handle* h, mrp_terminal_buffers* out) {
     return 0;
 }
 
-int mrp_enable_curriculum(mrp_handle* h, double** scaled_epsilon_dev, double** decay_pow_dev) {
+int MRP_API(mrp_enable_curriculum)(mrp_handle* h, double** scaled_epsilon_dev, double** decay_pow_dev) {
+    FWD(mrp_enable_curriculum_wide(h->wide, scaled_epsilon_dev, decay_pow_dev))
     if (!h || !scaled_epsilon_dev || !decay_pow_dev) return fail(-1, "mrp_enable_curriculum: null argument");
     SimConst& K = h->K;
     if (!K.eps_env) {
@@ -1119,18 +1219,21 @@ int mrp_enable_curriculum(mrp_handle* h, double** scaled_epsilon_dev, double** d
     return 0;
 }
 
-int mrp_set_params(mrp_handle* h, const mrp_params* p) {
+int MRP_API(mrp_set_params)(mrp_handle* h, const mrp_params* p) {
+    FWD(mrp_set_params_wide(h->wide, p))
     if (!h || !p) return fail(-1, "mrp_set_params: null argument");
     h->K.rp = *p;
     return 0;
 }
-int mrp_get_params(mrp_handle* h, mrp_params* p) {
+int MRP_API(mrp_get_params)(mrp_handle* h, mrp_params* p) {
+    FWD(mrp_get_params_wide(h->wide, p))
     if (!h || !p) return fail(-1, "mrp_get_params: null argument");
     *p = h->K.rp;
     return 0;
 }
 
-int mrp_get_stats(mrp_handle* h, double* out_host, int32_t reset_after) {
+int MRP_API(mrp_get_stats)(mrp_handle* h, double* out_host, int32_t reset_after) {
+    FWD(mrp_get_stats_wide(h->wide, out_host, reset_after))
     if (!h || !out_host) return fail(-1, "mrp_get_stats: null argument");
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
@@ -1141,6 +1244,11 @@ int mrp_get_stats(mrp_handle* h, double* out_host, int32_t reset_after) {
     return 0;
 }
 
-int64_t mrp_launch_count(mrp_handle* h) { return h ? h->launches : 0; }
+int64_t MRP_API(mrp_launch_count)(mrp_handle* h) {
+#ifndef MRP_WIDE
+    if (h && h->wide) return mrp_launch_count_wide(h->wide);
+#endif
+    return h ? h->launches : 0;
+}
 
 }  // extern "C"

@@ -23,7 +23,50 @@ namespace mrp {
 #define MRP_SS 1
 #endif
 constexpr int kBlock = 128;
-constexpr int kMaxC = 32;  // contact slots per env (mrp_layout.max_contacts <= 32)
+// Contact slots per env.  The library is compiled for two capacities (see __graft_entry__.build()): 32 — every
+// registered variant (measured maximum 21) — and MRP_MAXC = 192 for MultiRobotPuzzle2(num_agents > 2), whose three-fixture
+// robots reach >100 simultaneous fat-AABB pairs (188 possible with 5 robots).  Sets of contacts are CMask values.
+#ifndef MRP_MAXC
+#define MRP_MAXC 32
+#endif
+constexpr int kMaxC = MRP_MAXC;  // mrp_layout.max_contacts <= kMaxC
+constexpr int kMaxDynFix = 28;   // fixtures on dynamic bodies: 2 + 3 * 8 agents at most (v0: 2 + 8)
+MRP_HD int ctz_u32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+#if MRP_MAXC == 32
+typedef uint32_t CMask;
+MRP_HD CMask cm_none() { return 0u; }
+MRP_HD CMask cm_all() { return 0xffffffffu; }
+MRP_HD void cm_set(CMask& m, int k) { m |= 1u << k; }
+MRP_HD void cm_clr(CMask& m, int k) { m &= ~(1u << k); }
+MRP_HD bool cm_test(const CMask& m, int k) { return ((m >> k) & 1u) != 0u; }
+MRP_HD bool cm_any(const CMask& m) { return m != 0u; }
+MRP_HD bool cm_single(const CMask& m) { return m != 0u && (m & (m - 1u)) == 0u; }
+MRP_HD int cm_first(const CMask& m) { return ctz_u32(m); }
+#else
+static_assert(MRP_MAXC % 32 == 0 && MRP_MAXC <= 224, "contact capacity: a multiple of 32, slot index must fit VC_META's 8 bits");
+struct CMask { uint32_t w[kMaxC / 32]; };
+MRP_HD CMask cm_none() { CMask m; for (int i = 0; i < kMaxC / 32; ++i) m.w[i] = 0u; return m; }
+MRP_HD CMask cm_all() { CMask m; for (int i = 0; i < kMaxC / 32; ++i) m.w[i] = 0xffffffffu; return m; }
+MRP_HD void cm_set(CMask& m, int k) { m.w[k >> 5] |= 1u << (k & 31); }
+MRP_HD void cm_clr(CMask& m, int k) { m.w[k >> 5] &= ~(1u << (k & 31)); }
+MRP_HD bool cm_test(const CMask& m, int k) { return ((m.w[k >> 5] >> (k & 31)) & 1u) != 0u; }
+MRP_HD bool cm_any(const CMask& m) { uint32_t a = 0u; for (int i = 0; i < kMaxC / 32; ++i) a |= m.w[i]; return a != 0u; }
+MRP_HD bool cm_single(const CMask& m) {
+    int bits = 0;
+    for (int i = 0; i < kMaxC / 32; ++i) for (uint32_t x = m.w[i]; x; x &= x - 1u) ++bits;
+    return bits == 1;
+}
+MRP_HD int cm_first(const CMask& m) {
+    for (int i = 0; i < kMaxC / 32; ++i) if (m.w[i]) return 32 * i + ctz_u32(m.w[i]);
+    return -1;
+}
+#endif
 
 // ---- per-CTA constant table (floats; small ints stored as floats) -----------------
 constexpr int CT_FIXBODY = 0;     // [32] body index of fixture
@@ -85,7 +128,7 @@ struct SimConst {
     int32_t* task_T;      // [N] number of constraints of task i
     int32_t* task_off;    // [..] index of task i's first record in pool
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
-    uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * 32 + slot
+    uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * kMaxC + slot
     // optional per-env curriculum vectors (NULL: the scalar mrp_params apply): update_goal / update_params per env
     const double* eps_env;       // [N] scaled_epsilon   (mrp02:232-233)
     const double* decay_env;     // [N] decay**(-timestep) (mrp02:227-230)
@@ -165,7 +208,7 @@ struct Sim {
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
     float wallAlpha0[4];
-    float swept[12 * 4];   // swept tight AABB (incl. polygon radius) of every dynamic fixture, from SynchronizeFixtures
+    float swept[kMaxDynFix * 4];   // swept tight AABB (incl. polygon radius) of every dynamic fixture, from SynchronizeFixtures
     int nc;
     uint32_t goalc;
     uint32_t overflow;
@@ -451,19 +494,19 @@ struct Sim {
             } else if (manifold_provably_empty(fa, fb, bA, bB, body_xf(bA), body_xf(bB))) {
                 m &= 0xfff0ffffu | kMetaWas;  // pointCount 0, not touching
             } else {
-                K.narrow_list[atomic_add_i32(&K.cnt[CNT_NARROW], 1)] = (uint32_t)env * 32u + (uint32_t)k;
+                K.narrow_list[atomic_add_i32(&K.cnt[CNT_NARROW], 1)] = (uint32_t)env * (uint32_t)kMaxC + (uint32_t)k;
             }
             g(cw(k, 0)) = m;
         }
     }
     MRP_HD void finish_collide() {
-        uint32_t dead = 0;
+        CMask dead = cm_none();
         for (int k = nc - 1; k >= 0; --k) {
             uint32_t m = meta[k];
             const bool was = (m & kMetaWas) != 0, now = ((m >> 16) & 1) != 0;
             if (m & kMetaDead) {
                 if (was) contact_event(m, false);
-                dead |= 1u << k;
+                cm_set(dead, k);
                 continue;
             }
             if (!was && now) contact_event(m, true);
@@ -472,11 +515,11 @@ struct Sim {
         }
         compact_contacts(dead);
     }
-    MRP_HD void compact_contacts(uint32_t dead) {
-        if (dead) {  // rare: compact, preserving order
+    MRP_HD void compact_contacts(const CMask& dead) {
+        if (cm_any(dead)) {  // rare: compact, preserving order
             int dst = 0;
             for (int k = 0; k < nc; ++k) {
-                if ((dead >> k) & 1) continue;
+                if (cm_test(dead, k)) continue;
                 if (dst != k) {
                     meta[dst] = meta[k];
                     for (int j = 1; j < MRP_CONTACT_WORDS; ++j) g(cw(dst, j)) = g(cw(k, j));
@@ -487,13 +530,13 @@ struct Sim {
         }
     }
     MRP_HD void collide() {
-        uint32_t dead = 0;
+        CMask dead = cm_none();
         for (int k = nc - 1; k >= 0; --k) {
             uint32_t m = meta[k];
             int fa = m & 0xff, fb = (m >> 8) & 0xff;
             if (!overlap(fat(fa), fat(fb))) {
                 if ((m >> 16) & 1) contact_event(m, false);
-                dead |= 1u << k;
+                cm_set(dead, k);
                 continue;
             }
             update_contact(k);
@@ -1155,15 +1198,16 @@ struct Sim {
     MRP_HD int build_islands(uint8_t* island_of) {
         // island build: DFS seeds in body-list order (newest first): agent n-1 .. agent 0, block
         int T = 0;
-        uint32_t touch = 0;
-        for (int k = 0; k < nc; ++k) touch |= ((meta[k] >> 16) & 1u) << k;
-        if (touch && (touch & (touch - 1)) == 0) {  // a single touching contact is its own island: no search needed
-            order[0] = (uint8_t)ctz32(touch);
+        CMask touch = cm_none();
+        for (int k = 0; k < nc; ++k) if ((meta[k] >> 16) & 1u) cm_set(touch, k);
+        if (cm_single(touch)) {  // a single touching contact is its own island: no search needed
+            order[0] = (uint8_t)cm_first(touch);
             island_of[0] = 0;
             return 1;
         }
-        if (touch) {
-            uint32_t bflag = 0, cflag = 0;
+        if (cm_any(touch)) {
+            uint32_t bflag = 0;
+            CMask cflag = cm_none();
             int nisl = 0;
             for (int seed = K.nb - 1; seed >= 0; --seed) {
                 if ((bflag >> seed) & 1) continue;
@@ -1177,14 +1221,14 @@ struct Sim {
                     int b = (int)((stack >> (4 * sp)) & 15u);
                     if (!is_dyn(b)) { statics |= 1u << b; continue; }
                     for (int k = nc - 1; k >= 0; --k) {
-                        if (!((touch >> k) & 1) || ((cflag >> k) & 1)) continue;
+                        if (!cm_test(touch, k) || cm_test(cflag, k)) continue;
                         uint32_t m = meta[k];
                         int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
                         if (bA != b && bB != b) continue;
                         order[T] = (uint8_t)k;
                         island_of[T] = (uint8_t)nisl;
                         ++T;
-                        cflag |= 1u << k;
+                        cm_set(cflag, k);
                         int other = bA == b ? bB : bA;
                         if ((bflag >> other) & 1) continue;
                         stack = (stack & ~(15ull << (4 * sp))) | ((uint64_t)other << (4 * sp));
@@ -1246,7 +1290,7 @@ struct Sim {
         }
     }
 
-    MRP_HDN void toi_event(int minK, float minAlpha, uint32_t& toiFlag, uint32_t& enabled) {
+    MRP_HDN void toi_event(int minK, float minAlpha, CMask& toiFlag, CMask& enabled) {
         uint32_t m = meta[minK];
         int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
         // backups of the two sweeps
@@ -1263,11 +1307,11 @@ struct Sim {
         body_advance(bA, minAlpha);
         body_advance(bB, minAlpha);
         update_contact(minK);
-        enabled |= 1u << minK;
-        toiFlag &= ~(1u << minK);
+        cm_set(enabled, minK);
+        cm_clr(toiFlag, minK);
         ++toiCount[minK];
         if (!((meta[minK] >> 16) & 1)) {
-            enabled &= ~(1u << minK);
+            cm_clr(enabled, minK);
             for (int s = 0; s < 2; ++s) {
                 int b = two[s];
                 if (b < K.nb) {
@@ -1282,14 +1326,15 @@ struct Sim {
         // mini island: bA, bB, minContact + the dynamic body's other touching static contacts
         int T = 0;
         order[T++] = (uint8_t)minK;
-        uint32_t cflag = 1u << minK;
+        CMask cflag = cm_none();
+        cm_set(cflag, minK);
         uint32_t bflag = (1u << bA) | (1u << bB);
         for (int s = 0; s < 2; ++s) {
             int body = two[s];
             if (!is_dyn(body)) continue;
             for (int k = nc - 1; k >= 0; --k) {
                 if (T == kMaxC) break;
-                if ((cflag >> k) & 1) continue;
+                if (cm_test(cflag, k)) continue;
                 uint32_t mk_ = meta[k];
                 int cA = (mk_ >> 20) & 15, cB = (mk_ >> 24) & 15;
                 if (cA != body && cB != body) continue;
@@ -1298,9 +1343,9 @@ struct Sim {
                 float backupAlpha = alpha0(other);
                 if (!((bflag >> other) & 1)) body_advance(other, minAlpha);
                 update_contact(k);
-                enabled |= 1u << k;
+                cm_set(enabled, k);
                 if (!((meta[k] >> 16) & 1)) { alpha0(other) = backupAlpha; continue; }
-                cflag |= 1u << k;
+                cm_set(cflag, k);
                 order[T++] = (uint8_t)k;
                 bflag |= 1u << other;
             }
@@ -1329,12 +1374,12 @@ struct Sim {
             moved |= synchronize_fixtures(b, xf1);
             for (int k = 0; k < nc; ++k) {
                 uint32_t mk_ = meta[k];
-                if ((int)((mk_ >> 20) & 15) == b || (int)((mk_ >> 24) & 15) == b) toiFlag &= ~(1u << k);
+                if ((int)((mk_ >> 20) & 15) == b || (int)((mk_ >> 24) & 15) == b) cm_clr(toiFlag, k);
             }
         }
         int nc0 = nc;
         find_new_contacts(moved);
-        for (int k = nc0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; enabled |= 1u << k; toiFlag &= ~(1u << k); }
+        for (int k = nc0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; cm_set(enabled, k); cm_clr(toiFlag, k); }
     }
 
     // Exact TOI culling.  b2TimeOfImpact can only report e_touching (the one state that yields alpha < 1) if the
@@ -1361,24 +1406,24 @@ struct Sim {
     // returns false when a TOI event must be processed but allow_events is false (the caller then defers this env
     // to the event kernel, which redoes the scan from the same state)
     MRP_HD bool solve_toi(bool allow_events = true) {
-        uint32_t wallc = 0;  // contacts with a static body: the only TOI candidates (no bullets)
+        bool wallc = false;  // contacts with a static body: the only TOI candidates (no bullets)
         for (int k = 0; k < nc; ++k) {
             uint32_t m = meta[k];
-            if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc |= 1u << k;
+            if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc = true;
         }
         if (!wallc) return true;
         for (int b = 0; b < K.nb; ++b) BX(b, c0f + 3) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
-        uint32_t toiFlag = 0, enabled = 0xffffffffu;
+        CMask toiFlag = cm_none(), enabled = cm_all();
         for (;;) {
             int minK = -1;
             float minAlpha = 1.0f;
             for (int k = nc - 1; k >= 0; --k) {
-                if (!((enabled >> k) & 1)) continue;
+                if (!cm_test(enabled, k)) continue;
                 if (toiCount[k] > kMaxSubSteps) continue;
                 float alpha = 1.0f;
-                if ((toiFlag >> k) & 1) {
+                if (cm_test(toiFlag, k)) {
                     alpha = toi[k];
                 } else {
                     uint32_t m = meta[k];
@@ -1387,7 +1432,7 @@ struct Sim {
                     // fixture A is the dynamic one (walls are the last fixtures); cull only untouched sweeps
                     if (alpha0(bA) == 0.0f && alpha0(bB) == 0.0f && toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) {
                         toi[k] = 1.0f;
-                        toiFlag |= 1u << k;
+                        cm_set(toiFlag, k);
                         continue;
                     }
                     float al0 = alpha0(bA);
@@ -1403,7 +1448,7 @@ struct Sim {
                     if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
                     else alpha = 1.0f;
                     toi[k] = alpha;
-                    toiFlag |= 1u << k;
+                    cm_set(toiFlag, k);
                 }
                 if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
             }
@@ -1444,8 +1489,8 @@ struct Sim {
 // Reads the two body transforms straight from the state words, runs SAT + clipping, matches impulses by feature id
 // and writes the manifold + flags back.  Events are replayed later, in contact order, by finish_collide().
 MRP_HD void narrow_item(const SimConst& K, const float* ct, uint32_t item) {
-    const int64_t env = item >> 5;
-    const int k = (int)(item & 31u);
+    const int64_t env = item / (uint32_t)kMaxC;
+    const int k = (int)(item % (uint32_t)kMaxC);
     uint32_t* G = K.S + env;
     const int64_t N = K.N;
     auto gw = [&](int w) -> uint32_t& { return G[(int64_t)w * N]; };

@@ -13,7 +13,7 @@
  * one record per env, records contiguous (AoS, host or device memory).
  *
  * Layout for a variant with n robots, F_dyn fixtures on dynamic bodies and a
- * contact capacity MAXC (all three reported by mrp_state_words()/mrp_layout):
+ * contact capacity MAXC (all three reported by mrp_layout; MAXC <= 32, or <= 192 for v2 with num_agents > 2):
  *
  *   word 0            i32  elapsed_steps   (TimeLimit counter, gym_puzzles/__init__.py:3-29)
  *   word 1            i32  episode         (Philox spawn counter)
@@ -91,7 +91,11 @@ static inline int mrp_layout_for(int variant, int n_agents, mrp_layout* L) {
     /* potential contacts: fixture pairs on different bodies with >=1 dynamic body */
     int fa = per_agent * n_agents;
     int pot = 2 * fa + per_agent * per_agent * n_agents * (n_agents - 1) / 2 + 4 * L->n_dyn_fixtures;
-    L->max_contacts = pot < 32 ? pot : 32;
+    /* capacity: 32 covers every registered variant (measured maximum 21 on long rollouts; overflow is counted);
+     * MultiRobotPuzzle2(num_agents > 2) puts three-fixture robots side by side and reaches > 100 live fat-AABB pairs
+     * (188 possible with 5 robots), so it gets the wide capacity */
+    int cap = (v2 && n_agents > 2) ? 192 : 32;
+    L->max_contacts = pot < cap ? pot : cap;
     L->obs_dim = v2 ? 9 * n_agents + 21 : 4 * n_agents + 20;
     L->act_dim = v2 ? 2 * n_agents : 3 * n_agents;
     L->max_episode_steps = (variant == MRP_VARIANT_HEAVY_V0) ? 3000 : 2000;

@@ -102,9 +102,25 @@ def test_variant_constants_match_oracle():
         assert np.array_equal(oo.astype(np.float32), ho)
 
 
-def test_v2_agent_limit_is_reported():
-    with pytest.raises(abi.MrpError, match="num_agents <= 2"):
-        abi.Handle(2, 4, n_agents=5, lib=emu_lib())
+@pytest.mark.parametrize("variant,n_agents", [(2, 3), (2, 5), (3, 4)])
+def test_v2_more_agents_wide_capacity(variant, n_agents):
+    """MultiRobotPuzzle2(num_agents > 2) (mrp02:139) runs on the wide-capacity compilation (192 contact slots): three-fixture
+    robots spawn side by side, so far more than 32 fat-AABB pairs are alive."""
+    N, T, cap = 40, 110, 60
+    h = abi.Handle(variant, N, seed=21, max_episode_steps=cap, n_agents=n_agents, lib=emu_lib())
+    assert h.layout.max_contacts > 32
+    rep = rollout_compare(h, variant, N, T, seed=21, max_episode_steps=cap, n_agents=n_agents, nthreads=4)
+    _exact(rep)
+    assert rep["dones"] >= N
+    from oracle_lib import StateView
+    assert StateView(h.layout, h.get_state()).n_contacts.max() > 32
+    assert h.stats()["overflow"] == 0
+    h.close()
+
+
+def test_agent_count_limit_is_reported():
+    with pytest.raises(abi.MrpError, match="n_agents"):
+        abi.Handle(2, 4, n_agents=9, lib=emu_lib())
 
 
 def test_params_change_rewards():

@@ -98,3 +98,15 @@ def test_chunked_streams_are_invariant(monkeypatch):
     for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"):
         assert sr[k] == sc[k]
     assert sr["episodes"] > 0 and abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # atomics order
+
+
+@pytest.mark.parametrize("env_id,n_agents", [("MultiRobotPuzzle-v2", 5), ("MultiRobotPuzzleHeavy-v2", 3)])
+def test_v2_more_agents_parity(env_id, n_agents):
+    """BASELINE.json configs[3] with the num_agents ctor kw (mrp02:139): wide-capacity build of the kernels."""
+    N, T = 512, 100
+    h = abi.Handle(env_id, N, seed=17, max_episode_steps=50, n_agents=n_agents)
+    assert h.layout.max_contacts > 32
+    rep = rollout_compare(h, env_id, N, T, seed=17, max_episode_steps=50, n_agents=n_agents)
+    _assert_parity(rep)
+    assert rep["dones"] >= N and h.stats()["overflow"] == 0
+    h.close()
