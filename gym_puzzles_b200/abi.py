@@ -112,7 +112,8 @@ def load():
     """The product library (CUDA, sm_100a).  Fails loudly when it has not been built."""
     global _default
     if _default is None:
-        _default = MrpLib(LIB_PATH)
+        # MRP_LIB_PATH: another build of the same library (A/B measurements of two builds on one box); still CUDA-only
+        _default = MrpLib(os.environ.get("MRP_LIB_PATH", LIB_PATH))
     return _default
 
 

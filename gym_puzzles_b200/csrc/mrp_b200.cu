@@ -179,7 +179,7 @@ MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
 // false an env whose TOI scan finds an event is queued for the event pass and left untouched.
 MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local) {
-    Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 14);
+    Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 11);
     e.load();
     double r;
     bool d;
@@ -350,14 +350,14 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
-        if (busy && s.pos_trip(pt.st, pt.T, 60, -1, -1)) {
+        if (busy && s.pos_trip<true>(pt.st, pt.T, 60, -1, -1)) {
             pos_task_end(K, s, pt);
             busy = false;
         }
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_post(const __grid_constant__ SimConst K) {
+__global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -672,7 +672,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
     h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 24 + 4 * K.ndynfix) * kBlock);
-    h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(14 * K.nb + 4 * K.ndynfix) * kBlock);
+    h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(11 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;

@@ -10,12 +10,12 @@
 
 namespace mrp {
 
-MRP_HD double py_mod(double a, double b) {  // Python float %
+MRP_HDN double py_mod(double a, double b) {  // Python float % (not inlined: float64 fmod is ~300 instructions)
     double r = fmod(a, b);
     if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
     return r;
 }
-MRP_HD double py_distance(double ax, double ay, double bx, double by) {  // mrp00:130-132
+MRP_HDN double py_distance(double ax, double ay, double bx, double by) {  // mrp00:130-132 (not inlined: float64 sqrt)
     double x = (ax - bx) * (ax - bx), y = (ay - by) * (ay - by);
     return sqrt(x + y);
 }

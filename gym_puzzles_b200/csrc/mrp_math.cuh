@@ -67,8 +67,24 @@ struct Xf {
 };
 
 // b2Rot::Set with correctly-rounded sin/cos (see DESIGN.md "sincos"): evaluated in
-// float64 and rounded once, on the device with CUDA's sincos(double).
-MRP_HD Rot rot_set(float a) {
+// float64 and rounded once, on the device with CUDA's sincos(double).  Not inlined: the float64 sincos expands to
+// ~400 SASS instructions and the per-env kernels call it from many places; one shared copy keeps their hot code inside the
+// instruction cache (k_post spent 24 % of its stall samples waiting on instruction fetch).
+MRP_HDN Rot rot_set(float a) {
+    Rot r;
+#if defined(__CUDA_ARCH__)
+    double sd, cd;
+    ::sincos((double)a, &sd, &cd);
+    r.s = (float)sd;
+    r.c = (float)cd;
+#else
+    r.s = (float)::sin((double)a);
+    r.c = (float)::cos((double)a);
+#endif
+    return r;
+}
+// inlined form for the persistent position solver, whose one call site sits in its hot loop
+MRP_HD Rot rot_set_inline(float a) {
     Rot r;
 #if defined(__CUDA_ARCH__)
     double sd, cd;

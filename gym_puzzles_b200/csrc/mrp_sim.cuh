@@ -30,7 +30,8 @@ constexpr int kBlock = 128;
 #define MRP_MAXC 32
 #endif
 constexpr int kMaxC = MRP_MAXC;  // mrp_layout.max_contacts <= kMaxC
-constexpr int kMaxDynFix = 28;   // fixtures on dynamic bodies: 2 + 3 * 8 agents at most (v0: 2 + 8)
+// fixtures on dynamic bodies: v0 2 + 8 robots, v2 2 + 3 * 2 in the default build; 2 + 3 * 8 in the wide one
+constexpr int kMaxDynFix = MRP_MAXC == 32 ? 12 : 28;
 MRP_HD int ctz_u32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __ffs((int)x) - 1;
@@ -208,6 +209,7 @@ struct Sim {
     float toi[kMaxC];
     uint8_t toiCount[kMaxC];
     float wallAlpha0[4];
+    float alpha_none;      // alpha0 of every dynamic body in the k_post layout (no TOI event is processed there)
     float swept[kMaxDynFix * 4];   // swept tight AABB (incl. polygon radius) of every dynamic fixture, from SynchronizeFixtures
     int nc;
     uint32_t goalc;
@@ -215,14 +217,15 @@ struct Sim {
 
     // layouts (words per dynamic body):
     //   17 full: pose/vel 0-5, q 6-7, p 8-9, cache 10-12, c0/a0/alpha0 13-16, walls, fat AABBs   (fused step, reset, k_post_events)
-    //   14 k_post: 0-9, c0/a0/alpha0 10-13, fat AABBs, no cache, no wall slots
+    //   11 k_post: 0-7, c0/a0 8-10, fat AABBs; no p (recomputed from c, q), no alpha0 (0: no TOI event is processed
+    //      in this layout), no cache, no wall slots
     //   13 k_pre: 0-9, cache 10-12, walls                     10 k_broad: 0-9, fat AABBs
     //    9 position solver: 0-5, cache 6-8, walls               6 velocity solver: 0-5, walls
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
         : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
           qoff(fdyn_ == 17 || fdyn_ == 13 ? 10 : (fdyn_ == 9 ? 6 : -1)),
-          fa_off(fdyn_ == 17 ? k.nb * 17 + 24 : (fdyn_ == 14 ? k.nb * 14 : (fdyn_ == 10 ? k.nb * 10 : -1))),
-          c0f(fdyn_ == 17 ? 13 : (fdyn_ == 14 ? 10 : -1)), wall_off(fdyn_ == 14 || fdyn_ == 10 ? -1 : k.nb * fdyn_), nc(0), goalc(0),
+          fa_off(fdyn_ == 17 ? k.nb * 17 + 24 : (fdyn_ == 11 ? k.nb * 11 : (fdyn_ == 10 ? k.nb * 10 : -1))),
+          c0f(fdyn_ == 17 ? 13 : (fdyn_ == 11 ? 8 : -1)), wall_off(fdyn_ == 11 || fdyn_ == 10 ? -1 : k.nb * fdyn_), nc(0), goalc(0),
           overflow(0) {}
 
     // ------------------------------------------------------------ memory helpers
@@ -272,13 +275,14 @@ struct Sim {
         float* const c = bp(b) + qoff * MRP_SS;
         c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
     }
+    template <bool INL = false>
     MRP_HD Rot body_rot(int b, float angle) {
         Rot q;
         if (b >= K.nb) { q.s = 0.0f; q.c = 1.0f; return q; }
-        if (qoff < 0) return rot_set(angle);
+        if (qoff < 0) return INL ? rot_set_inline(angle) : rot_set(angle);
         float* const c = bp(b) + qoff * MRP_SS;
         if (c[2 * MRP_SS] == angle) { q.s = c[0]; q.c = c[MRP_SS]; return q; }
-        q = rot_set(angle);
+        q = INL ? rot_set_inline(angle) : rot_set(angle);
         c[0] = q.s; c[MRP_SS] = q.c; c[2 * MRP_SS] = angle;
         return q;
     }
@@ -292,7 +296,12 @@ struct Sim {
     MRP_HD Xf body_xf(int b) {
         Xf x;
         if (b < K.nb) {
-            x.p = mk(BX(b, 8), BX(b, 9));
+            if (fdyn == 11) {  // p = c - R(q) * localCenter: the very expression sync_transform stores
+                const V2 r = rmul(Rot{BX(b, 6), BX(b, 7)}, localCenter(b));
+                x.p = mk(B(b, 0) - r.x, B(b, 1) - r.y);
+            } else {
+                x.p = mk(BX(b, 8), BX(b, 9));
+            }
             x.q.s = BX(b, 6);
             x.q.c = BX(b, 7);
         } else {
@@ -307,8 +316,10 @@ struct Sim {
         V2 r = rmul(q, localCenter(b));
         BX(b, 6) = q.s;
         BX(b, 7) = q.c;
-        BX(b, 8) = B(b, 0) - r.x;
-        BX(b, 9) = B(b, 1) - r.y;
+        if (fdyn != 11) {
+            BX(b, 8) = B(b, 0) - r.x;
+            BX(b, 9) = B(b, 1) - r.y;
+        }
     }
     MRP_HD int fix_body(int f) const { return (int)ct[CT_FIXBODY + f]; }
     MRP_HD const float* fix_shape(int f) const { return ct + CT_SHAPES + kShapeWords * (int)ct[CT_FIXSHAPE + f]; }
@@ -322,7 +333,7 @@ struct Sim {
         }
         return b;
     }
-    MRP_HD float& alpha0(int b) { return b < K.nb ? BX(b, c0f + 3) : wallAlpha0[b - K.nb]; }
+    MRP_HD float& alpha0(int b) { return b < K.nb ? (fdyn == 11 ? alpha_none : BX(b, c0f + 3)) : wallAlpha0[b - K.nb]; }
 
     // ------------------------------------------------------------ state load / store
     // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
@@ -341,9 +352,11 @@ struct Sim {
             p[6 * MRP_SS] = r[6]; p[7 * MRP_SS] = r[7];
             if (c0f >= 0) { p[c0f * MRP_SS] = r[8]; p[(c0f + 1) * MRP_SS] = r[9]; p[(c0f + 2) * MRP_SS] = r[10]; }  // pre-step pose
             set_rot_cache(b, Rot{r[6], r[7]}, r[2]);
-            V2 rc = rmul(Rot{r[6], r[7]}, localCenter(b));
-            p[8 * MRP_SS] = r[0] - rc.x;
-            p[9 * MRP_SS] = r[1] - rc.y;
+            if (fdyn != 11) {
+                V2 rc = rmul(Rot{r[6], r[7]}, localCenter(b));
+                p[8 * MRP_SS] = r[0] - rc.x;
+                p[9 * MRP_SS] = r[1] - rc.y;
+            }
         }
         for (int k = 0; wall_off >= 0 && k < 4; ++k) {
             int b = K.nb + k;
@@ -1118,6 +1131,7 @@ struct Sim {
         pos_begin(st);
         while (!pos_trip(st, T, maxSweeps, toiA, toiB)) {}
     }
+    template <bool INL = false>
     MRP_HD bool pos_trip(PosState& st, int T, int maxSweeps, int toiA, int toiB) {
         const bool toi = toiA >= 0;
         const float baum = toi ? kToiBaumgarte : kBaumgarte;
@@ -1141,8 +1155,8 @@ struct Sim {
                 float aA = B(bA, 2), aB = B(bB, 2);
                 const V2 ln = mk(V(t, VC_LNX), V(t, VC_LNY)), lp = mk(V(t, VC_LPX), V(t, VC_LPY));
                 Xf xfA, xfB;
-                xfA.q = body_rot(bA, aA);
-                xfB.q = body_rot(bB, aB);
+                xfA.q = body_rot<INL>(bA, aA);
+                xfB.q = body_rot<INL>(bB, aB);
                 xfA.p = cA - rmul(xfA.q, localCenter(bA));
                 xfB.p = cB - rmul(xfB.q, localCenter(bB));
                 const V2 lpj = mk(V(t, VC_LP0X + 2 * j), V(t, VC_LP0X + 2 * j + 1));
@@ -1412,7 +1426,8 @@ struct Sim {
             if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc = true;
         }
         if (!wallc) return true;
-        for (int b = 0; b < K.nb; ++b) BX(b, c0f + 3) = 0.0f;
+        alpha_none = 0.0f;
+        for (int b = 0; fdyn != 11 && b < K.nb; ++b) BX(b, c0f + 3) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
         CMask toiFlag = cm_none(), enabled = cm_all();

@@ -168,7 +168,7 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
     // contact capacity is 32 slots per env (one 32-bit mask per flag set): enough for the registered
     // variants (measured max 21 over 1.2M env-steps) but not for v2 with > 2 three-fixture robots,
     // whose fat-AABB pair count averages 20 (n=3) .. 60 (n=5).  See DESIGN.md "Limits".
-    if (L->max_contacts > kMaxC) return -3;  // needs the wide-capacity compilation (mrp_b200.cu)
+    if (L->max_contacts > kMaxC || L->n_dyn_fixtures > kMaxDynFix) return -3;  // needs the wide-capacity compilation (mrp_b200.cu)
     memset(ctab, 0, sizeof(float) * CT_WORDS);
     const bool v2 = variant >= 2, heavy = (variant & 1) != 0;
     const int n = L->n_agents;
