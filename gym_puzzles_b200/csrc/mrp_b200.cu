@@ -429,10 +429,9 @@ struct mrp_handle {
     int solver_ctas;  // persistent solver CTAs per SM
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
-    int host_chain;    // mrp_step_host: chunk pipelines execute in chunk order (copies still overlap)
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cjoin[kMaxChunks];
+    cudaEvent_t cfork, cact, cjoin[kMaxChunks], cpost[kMaxChunks];
 #endif
     int64_t launches;
     size_t smem_bytes;
@@ -546,8 +545,9 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     cudaSetDevice(h->device);
     if (h->timing) MRP_API(mrp_set_timing)(h, 0);
     if (h->cfork) {
-        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); }
+        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); }
         cudaEventDestroy(h->cfork);
+        cudaEventDestroy(h->cact);
     }
 #else
     free(h->emu_sm);
@@ -620,7 +620,6 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
         int v = getenv(var) ? atoi(getenv(var)) : (cfg->num_envs >= 16384 * dflt ? dflt : 1);
         return v < 1 ? 1 : (v > kMaxChunks ? kMaxChunks : v);
     };
-    h->host_chain = getenv("MRP_HOST_CHAIN") ? atoi(getenv("MRP_HOST_CHAIN")) : 0;
     h->nchunks = chunks_from("MRP_CHUNKS", 1);
     h->nchunks_host = chunks_from("MRP_CHUNKS_HOST", 4);
     K.seed = cfg->seed;
@@ -640,7 +639,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.trunc, N);
     rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
     rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * 32 * kMaxChunks);
+    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * 32 * (kMaxChunks + 1));
     // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
     rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
     rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * kTaskClasses * N * K.nb);  // classes x at most one island per dynamic body
@@ -696,9 +695,11 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
             if (pr > lo || !use_prio) pr = lo;
             cudaStreamCreateWithPriority(&h->cstream[c], cudaStreamNonBlocking, pr);
             cudaEventCreateWithFlags(&h->cjoin[c], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->cpost[c], cudaEventDisableTiming);
         }
     }
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->cact, cudaEventDisableTiming);
     if (check_launch("mrp_create")) { MRP_API(mrp_destroy)(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
@@ -842,92 +843,134 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
 }
 
 #ifndef MRP_HOST_EMU
-// one chunk's phase pipeline on one stream; `timed` records the phase-boundary events (single-chunk steps only)
-static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
+// One chunk's phase pipeline on one stream, in two halves: the front (collide, constraint setup, solvers) and the back
+// (k_post, TOI events, auto-reset), which may use a different chunking (mrp_step_host: front over the whole batch,
+// back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
+// events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
+static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
-    // persistent / queue kernels: a few CTAs per SM
-    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
     const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
     k_clear<<<1, 32, 0, st>>>(K.cnt);
     if (timed) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
     }
-    if (h->fused) {
-        k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
-        h->launches += 2;
-    } else {
-        k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
-        k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
-        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K);
-        if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
-        k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
-        if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
-        k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
-        if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
-        k_post<<<grid, kBlock, h->smem_post, st>>>(K);
-        if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
-        k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
-        h->launches += 8;
-    }
+    k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
+    k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
+    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
+    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
+    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
+    h->launches += 6;
+}
+static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool clear, cudaEvent_t after_post = nullptr) {
+    const unsigned grid = grid_for(K.nloc, kBlock);
+    if (grid == 0) return;
+    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;  // queue kernels: a few CTAs per SM
+    if (clear) { k_clear<<<1, 32, 0, st>>>(K.cnt); h->launches += 1; }
+    k_post<<<grid, kBlock, h->smem_post, st>>>(K);
+    if (after_post) cudaEventRecord(after_post, st);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+    h->launches += 2;
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
     }
 }
+static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
+    if (h->fused) {  // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
+        const unsigned grid = grid_for(K.nloc, kBlock);
+        if (grid == 0) return;
+        const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+        k_clear<<<1, 32, 0, st>>>(K.cnt);
+        if (timed) {
+            if (h->ev_n == 64) drain_timing(h);
+            cudaEventRecord(h->ev0[h->ev_n], st);
+        }
+        k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
+        if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+        if (K.auto_reset) k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 3;
+        return;
+    }
+    launch_front(h, K, st, timed, nullptr);
+    launch_back(h, K, st, timed, false);
+}
 #else
-static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
+static void run_front_emu(mrp_handle* h, const SimConst& K) {
     for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
     const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
-    if (h->fused) {
-        for (int64_t e = e0; e < e1; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
-    } else {
-        // the same phases the device runs as kernels, executed as loops
-        for (int64_t e = e0; e < e1; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
-        const int nnarrow = K.cnt[CNT_NARROW];
-        for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
-        for (int64_t e = e0; e < e1; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
-        for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
-            const int ntasks = task_count(K, cls);
-            for (int i = 0; i < ntasks; ++i) {
-                Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
-                VelTask vt;
-                Sim::VelReg st1;
-                vel_task_begin(K, s, vt, task_slot(K, cls, i));
-                if (cls == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
-                if (cls == 0) { while (vt.ops += 2, !s.vr_sweep_single<1>(vt.st, 180)) {} }
-                else if (cls == 1) { while (vt.ops += 3, !s.vr_sweep_single<2>(vt.st, 180)) {} }
-                else if (cls == 2) { while (vt.ops += 5, !s.vr_sweep_pair(vt.st, st1, 180)) {} }
-                else { while (++vt.ops, !s.vr_trip(vt.st, 180)) {} }
-                vel_task_end(K, s, vt);
-            }
+    // the same phases the device runs as kernels, executed as loops
+    for (int64_t e = e0; e < e1; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
+    const int nnarrow = K.cnt[CNT_NARROW];
+    for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
+    for (int64_t e = e0; e < e1; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
+    for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
+        const int ntasks = task_count(K, cls);
+        for (int i = 0; i < ntasks; ++i) {
+            Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
+            VelTask vt;
+            Sim::VelReg st1;
+            vel_task_begin(K, s, vt, task_slot(K, cls, i));
+            if (cls == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
+            if (cls == 0) { while (vt.ops += 2, !s.vr_sweep_single<1>(vt.st, 180)) {} }
+            else if (cls == 1) { while (vt.ops += 3, !s.vr_sweep_single<2>(vt.st, 180)) {} }
+            else if (cls == 2) { while (vt.ops += 5, !s.vr_sweep_pair(vt.st, st1, 180)) {} }
+            else { while (++vt.ops, !s.vr_trip(vt.st, 180)) {} }
+            vel_task_end(K, s, vt);
         }
-        {
-            const int ntasks = task_count_all(K);
-            for (int i = 0; i < ntasks; ++i) {
-                Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
-                PosTask pt;
-                pos_task_begin(K, s, pt, task_slot_any(K, i));
-                while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
-                pos_task_end(K, s, pt);
-            }
-        }
-        for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
-        const int ntoi = K.cnt[CNT_TOI];
-        for (int i = 0; i < ntoi; ++i) {
-            const int64_t env = K.toi_list[i];
-            MRP_VC_SCRATCH(K, env);
-            post_lane(K, h->emu_sm, h->ctab_dev, env, true, vc_local);
-        }
+    }
+    const int ntasks = task_count_all(K);
+    for (int i = 0; i < ntasks; ++i) {
+        Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
+        PosTask pt;
+        pos_task_begin(K, s, pt, task_slot_any(K, i));
+        while (!s.pos_trip(pt.st, pt.T, 60, -1, -1)) {}
+        pos_task_end(K, s, pt);
+    }
+}
+static void run_back_emu(mrp_handle* h, const SimConst& K, bool clear) {
+    if (clear) for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
+    const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
+    for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
+    const int ntoi = K.cnt[CNT_TOI];
+    for (int i = 0; i < ntoi; ++i) {
+        const int64_t env = K.toi_list[i];
+        MRP_VC_SCRATCH(K, env);
+        post_lane(K, h->emu_sm, h->ctab_dev, env, true, vc_local);
     }
     if (K.auto_reset) {
         const int nreset = K.cnt[CNT_RESET];
         for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
     }
 }
+static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
+    if (h->fused) {
+        for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
+        for (int64_t e = K.env0; e < K.env0 + K.nloc; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
+        if (K.auto_reset) {
+            const int nreset = K.cnt[CNT_RESET];
+            for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+        }
+        return;
+    }
+    run_front_emu(h, K);
+    run_back_emu(h, K, false);
+}
 #endif
+
+// chunk c of the back half when the front ran over the whole batch: own counters (blocks 1..), own event / reset queues
+static SimConst back_chunk_const(const mrp_handle* h, const SimConst& K0, int c, int nch) {
+    SimConst K = chunk_const(h, K0, c, nch);
+    K.cnt = K0.cnt + 32 * (c + 1);
+    return K;
+}
 
 // chunks of one step call: 1 while the per-phase timers are on (their events live on one stream)
 static int step_chunks(const mrp_handle* h, int wanted) {
@@ -972,38 +1015,74 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     const SimConst& K0 = h->K;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
-    // per chunk: H2D of its action rows, its pipeline, D2H of its result rows, all on the chunk's stream, so the
-    // PCIe copies of one chunk run under the kernels of the others (the host buffers should be pinned)
+    // The front half (collide, setup, solvers) runs over the whole batch on the first chunk stream — the action H2D is
+    // queued beside it on the second and only k_pre waits for it.  The back half (k_post, TOI events, auto-reset) runs
+    // per chunk on prioritised streams, each followed by the D2H of its result rows, so the PCIe copies (the host
+    // buffers should be pinned) run under the remaining chunks' kernels.
     const int nch = step_chunks(h, h->nchunks_host);
+    const size_t N = (size_t)K0.N;
+    static cudaEvent_t tr[32]; static int tr_init = 0; const bool trace = getenv("MRP_TRACE") != nullptr;
+    if (trace && !tr_init) { for (int i = 0; i < 32; ++i) cudaEventCreate(&tr[i]); tr_init = 1; }
+    if (trace) cudaEventRecord(tr[0], 0);
     cudaEventRecord(h->cfork, 0);  // order after whatever the caller queued on the default stream
-    for (int c = 0; c < nch; ++c) {
-        const SimConst K = chunk_const(h, K0, c, nch);
-        if (K.nloc == 0) continue;
-        cudaStream_t st = h->cstream[c];
-        cudaStreamWaitEvent(st, h->cfork, 0);
-        const size_t b = (size_t)K.env0, n = (size_t)K.nloc;
-        if (cudaMemcpyAsync(h->act_dev + b * K.act_dim, actions_host + b * K.act_dim, sizeof(float) * n * K.act_dim,
-                            cudaMemcpyHostToDevice, st) != cudaSuccess)
-            return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
-        // compute runs in chunk order (chunk c+1's kernels queue behind chunk c's): chunk c finishes early and its
-        // D2H overlaps the kernels of chunk c+1, whose H2D already ran under chunk c
-        if (h->host_chain && c > 0) cudaStreamWaitEvent(st, h->cjoin[c - 1], 0);
-        launch_pipeline(h, K, st, nch == 1 && h->timing);
-        cudaEventRecord(h->cjoin[c], st);
-        if (obs_host) cudaMemcpyAsync(obs_host + b * K.obs_dim, K.obs + b * K.obs_dim, sizeof(float) * n * K.obs_dim, cudaMemcpyDeviceToHost, st);
-        if (reward_host) cudaMemcpyAsync(reward_host + b, K.rew + b, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
-        if (done_host) cudaMemcpyAsync(done_host + b, K.done + b, n, cudaMemcpyDeviceToHost, st);
-        if (trunc_host) cudaMemcpyAsync(trunc_host + b, K.trunc + b, n, cudaMemcpyDeviceToHost, st);
+    cudaStream_t s_front = h->cstream[0], s_h2d = h->cstream[kMaxChunks - 1];
+    cudaStreamWaitEvent(s_front, h->cfork, 0);
+    cudaStreamWaitEvent(s_h2d, h->cfork, 0);
+    if (cudaMemcpyAsync(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim, cudaMemcpyHostToDevice, s_h2d) != cudaSuccess)
+        return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
+    cudaEventRecord(h->cact, s_h2d);
+    if (trace) cudaEventRecord(tr[1], s_h2d);
+    auto copy_out = [&](cudaStream_t st, size_t b, size_t n) {
+        if (obs_host) cudaMemcpyAsync(obs_host + b * K0.obs_dim, K0.obs + b * K0.obs_dim, sizeof(float) * n * K0.obs_dim, cudaMemcpyDeviceToHost, st);
+        if (reward_host) cudaMemcpyAsync(reward_host + b, K0.rew + b, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+        if (done_host) cudaMemcpyAsync(done_host + b, K0.done + b, n, cudaMemcpyDeviceToHost, st);
+        if (trunc_host) cudaMemcpyAsync(trunc_host + b, K0.trunc + b, n, cudaMemcpyDeviceToHost, st);
+    };
+    if (nch == 1 || h->fused) {
+        cudaStreamWaitEvent(s_front, h->cact, 0);
+        launch_pipeline(h, chunk_const(h, K0, 0, 1), s_front, h->timing != 0);
+        copy_out(s_front, 0, N);
+    } else {
+        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact);
+        cudaEventRecord(h->cjoin[0], s_front);
+        if (trace) cudaEventRecord(tr[2], s_front);
+        for (int c = 0; c < nch; ++c) {
+            const SimConst K = back_chunk_const(h, K0, c, nch);
+            if (K.nloc == 0) continue;
+            cudaStream_t st = h->cstream[c];
+            // k_post of chunk c starts when k_post of chunk c-1 has finished: at that moment the (higher-priority, large
+            // shared memory) TOI-event and reset kernels of chunk c-1 get the draining SMs first, and chunk c's k_post
+            // fills the rest.  Launched all at once, the k_post CTAs of later chunks would keep re-occupying the SMs and
+            // starve those kernels until every k_post had drained (measured: all chunks finished together).
+            cudaStreamWaitEvent(st, c > 0 ? h->cpost[c - 1] : h->cjoin[0], 0);
+            launch_back(h, K, st, false, true, h->cpost[c]);
+            if (trace) cudaEventRecord(tr[3 + 2 * c], st);
+            copy_out(st, (size_t)K.env0, (size_t)K.nloc);
+            if (trace) cudaEventRecord(tr[4 + 2 * c], st);
+        }
     }
     int rc = check_launch("mrp_step_host");
     for (int c = 0; c < nch; ++c)
         if (cudaStreamSynchronize(h->cstream[c]) != cudaSuccess && !rc) rc = fail(-9, "mrp_step_host: %s", dev_err());
+    if (cudaStreamSynchronize(s_h2d) != cudaSuccess && !rc) rc = fail(-9, "mrp_step_host: %s", dev_err());
+    if (trace && nch > 1) {
+        float ms;
+        cudaEventElapsedTime(&ms, tr[0], tr[1]); printf("h2d_done %.2f", ms);
+        cudaEventElapsedTime(&ms, tr[0], tr[2]); printf(" front_done %.2f", ms);
+        for (int c = 0; c < nch; ++c) { cudaEventElapsedTime(&ms, tr[0], tr[3 + 2 * c]); printf(" | back%d %.2f", c, ms); cudaEventElapsedTime(&ms, tr[0], tr[4 + 2 * c]); printf(" d2h%d %.2f", c, ms); }
+        printf("\n");
+    }
     return rc;
 #else
     const size_t N = (size_t)K0.N;
     memcpy(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim);
     const int nch = step_chunks(h, h->nchunks_host);
-    for (int c = 0; c < nch; ++c) run_pipeline_emu(h, chunk_const(h, K0, c, nch));
+    if (nch == 1 || h->fused) {
+        run_pipeline_emu(h, chunk_const(h, K0, 0, 1));
+    } else {  // front over the whole batch, back per chunk (as the device path)
+        run_front_emu(h, chunk_const(h, K0, 0, 1));
+        for (int c = 0; c < nch; ++c) run_back_emu(h, back_chunk_const(h, K0, c, nch), true);
+    }
     if (obs_host) memcpy(obs_host, K0.obs, sizeof(float) * N * K0.obs_dim);
     if (reward_host) memcpy(reward_host, K0.rew, sizeof(float) * N);
     if (done_host) memcpy(done_host, K0.done, N);
