@@ -277,11 +277,13 @@ __global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimCo
         narrow_item(K, ct, K.narrow_list[i]);
 }
 
-__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K) {
+// envs [loc0, loc1) of the chunk: mrp_step_host launches it in two halves so that the first half starts as soon as
+// its actions have arrived
+__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K, int64_t loc0, int64_t loc1) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
-    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (loc >= K.nloc) return;
+    const int64_t loc = loc0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (loc >= loc1) return;
     const int64_t env = K.env0 + loc;
     pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
 }
@@ -431,7 +433,7 @@ struct mrp_handle {
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cact, cjoin[kMaxChunks], cpost[kMaxChunks];
+    cudaEvent_t cfork, cact, cact0, cjoin[kMaxChunks], cpost[kMaxChunks];
 #endif
     int64_t launches;
     size_t smem_bytes;
@@ -548,6 +550,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); }
         cudaEventDestroy(h->cfork);
         cudaEventDestroy(h->cact);
+        cudaEventDestroy(h->cact0);
     }
 #else
     free(h->emu_sm);
@@ -621,7 +624,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
         return v < 1 ? 1 : (v > kMaxChunks ? kMaxChunks : v);
     };
     h->nchunks = chunks_from("MRP_CHUNKS", 1);
-    h->nchunks_host = chunks_from("MRP_CHUNKS_HOST", 4);
+    h->nchunks_host = chunks_from("MRP_CHUNKS_HOST", 8);
     K.seed = cfg->seed;
     K.env_id_base = cfg->env_id_base;
     K.N = cfg->num_envs;
@@ -700,6 +703,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     }
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cact, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->cact0, cudaEventDisableTiming);
     if (check_launch("mrp_create")) { MRP_API(mrp_destroy)(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
@@ -847,7 +851,8 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
 // (k_post, TOI events, auto-reset), which may use a different chunking (mrp_step_host: front over the whole batch,
 // back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
 // events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
-static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready) {
+static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready,
+                         cudaEvent_t first_half_ready = nullptr, int64_t half = 0) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
     const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
@@ -858,8 +863,16 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     }
     k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
     k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
-    if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
-    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K);
+    if (first_half_ready && half > 0 && half < K.nloc) {
+        cudaStreamWaitEvent(st, first_half_ready, 0);
+        k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half);
+        cudaStreamWaitEvent(st, actions_ready, 0);
+        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, st>>>(K, half, K.nloc);
+        h->launches += 1;
+    } else {
+        if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
+        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
+    }
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
     k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
     if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
@@ -1028,7 +1041,13 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     cudaStream_t s_front = h->cstream[0], s_h2d = h->cstream[kMaxChunks - 1];
     cudaStreamWaitEvent(s_front, h->cfork, 0);
     cudaStreamWaitEvent(s_h2d, h->cfork, 0);
-    if (cudaMemcpyAsync(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim, cudaMemcpyHostToDevice, s_h2d) != cudaSuccess)
+    // the action rows go up in two halves: k_pre of the first half starts while the second is still in flight
+    const size_t half = nch > 1 ? (N / 2 + kBlock - 1) / kBlock * kBlock : 0;
+    const size_t row = sizeof(float) * K0.act_dim;
+    if (half && cudaMemcpyAsync(h->act_dev, actions_host, row * half, cudaMemcpyHostToDevice, s_h2d) != cudaSuccess)
+        return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
+    if (half) cudaEventRecord(h->cact0, s_h2d);
+    if (cudaMemcpyAsync(h->act_dev + half * K0.act_dim, actions_host + half * K0.act_dim, row * (N - half), cudaMemcpyHostToDevice, s_h2d) != cudaSuccess)
         return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
     cudaEventRecord(h->cact, s_h2d);
     if (trace) cudaEventRecord(tr[1], s_h2d);
@@ -1043,7 +1062,7 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
         launch_pipeline(h, chunk_const(h, K0, 0, 1), s_front, h->timing != 0);
         copy_out(s_front, 0, N);
     } else {
-        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact);
+        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half);
         cudaEventRecord(h->cjoin[0], s_front);
         if (trace) cudaEventRecord(tr[2], s_front);
         for (int c = 0; c < nch; ++c) {
