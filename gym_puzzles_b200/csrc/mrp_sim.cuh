@@ -580,7 +580,27 @@ struct Sim {
         int f1 = b == 0 ? 2 : f0 + K.per_agent;
         for (int f = f0; f < f1; ++f) {
             const float* sh = fix_shape(f);
-            Box a1 = shape_aabb(sh, xf1), a2 = shape_aabb(sh, xf2);
+            // both b2PolygonShape::ComputeAABB evaluations (at xf1 and xf2) in one rolled vertex loop: same values as two
+            // shape_aabb() calls, a fraction of the code (k_post is bound by instruction fetch, profiles/)
+            Box a1, a2;
+            {
+                const V2 v0 = sh_v(sh, 0);
+                V2 lo1 = xmul(xf1, v0), hi1 = lo1, lo2 = xmul(xf2, v0), hi2 = lo2;
+                const int cnt = sh_count(sh);
+#pragma unroll 1
+                for (int i = 1; i < cnt; ++i) {
+                    const V2 v = sh_v(sh, i);
+                    const V2 p1 = xmul(xf1, v), p2 = xmul(xf2, v);
+                    lo1 = mk(fmin2(lo1.x, p1.x), fmin2(lo1.y, p1.y));
+                    hi1 = mk(fmax2(hi1.x, p1.x), fmax2(hi1.y, p1.y));
+                    lo2 = mk(fmin2(lo2.x, p2.x), fmin2(lo2.y, p2.y));
+                    hi2 = mk(fmax2(hi2.x, p2.x), fmax2(hi2.y, p2.y));
+                }
+                a1.lx = lo1.x - kPolygonRadius; a1.ly = lo1.y - kPolygonRadius;
+                a1.hx = hi1.x + kPolygonRadius; a1.hy = hi1.y + kPolygonRadius;
+                a2.lx = lo2.x - kPolygonRadius; a2.ly = lo2.y - kPolygonRadius;
+                a2.hx = hi2.x + kPolygonRadius; a2.hy = hi2.y + kPolygonRadius;
+            }
             Box a;
             a.lx = fmin2(a1.lx, a2.lx); a.ly = fmin2(a1.ly, a2.ly);
             a.hx = fmax2(a1.hx, a2.hx); a.hy = fmax2(a1.hy, a2.hy);
@@ -1421,6 +1441,7 @@ struct Sim {
     // to the event kernel, which redoes the scan from the same state)
     MRP_HD bool solve_toi(bool allow_events = true) {
         bool wallc = false;  // contacts with a static body: the only TOI candidates (no bullets)
+#pragma unroll 1
         for (int k = 0; k < nc; ++k) {
             uint32_t m = meta[k];
             if (!is_dyn((m >> 20) & 15) || !is_dyn((m >> 24) & 15)) wallc = true;
@@ -1429,6 +1450,7 @@ struct Sim {
         alpha_none = 0.0f;
         for (int b = 0; fdyn != 11 && b < K.nb; ++b) BX(b, c0f + 3) = 0.0f;
         for (int k = 0; k < 4; ++k) wallAlpha0[k] = 0.0f;
+#pragma unroll 1
         for (int k = 0; k < nc; ++k) { toi[k] = 1.0f; toiCount[k] = 0; }
         CMask toiFlag = cm_none(), enabled = cm_all();
         for (;;) {
