@@ -121,13 +121,16 @@ struct Env : Sim {
         if (!K.v2) {  // _calculate_distance / _calculate_agent_distance with b2Vec2*SCALE in float32
             float s = (float)K.SCALE;
             bd = py_distance((double)(bc.x * s), (double)(bc.y * s), gx, gy);
+#pragma unroll 1
             for (int i = 0; i < n; ++i)
                 ad[i] = py_distance((double)(B(1 + i, 0) * s), (double)(B(1 + i, 1) * s), (double)(bc.x * s), (double)(bc.y * s));
         } else {
             bd = py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, gx, gy);
+#pragma unroll 1
             for (int i = 0; i < n; ++i)
                 ad[i] = py_distance((double)B(1 + i, 0) * K.ratio, (double)B(1 + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio);
         }
+#pragma unroll 1
         for (int i = 0; i < n; ++i) gsd(W_DIST + 2 * i, ad[i]);
         gsd(W_DIST + 2 * n, bd);
 
@@ -137,6 +140,7 @@ struct Env : Sim {
         bool in_place;
         int blks = (int)g(W_INPLACE);
         if (!K.v2) {
+#pragma unroll 1
             for (int i = 0; i < n; ++i) {
                 obs[o++] = (float)((double)B(1 + i, 0) * K.SCALE - (double)bc.x * K.SCALE);
                 obs[o++] = (float)((double)B(1 + i, 1) * K.SCALE - (double)bc.y * K.SCALE);
@@ -151,6 +155,7 @@ struct Env : Sim {
             obs[o++] = (float)(y - gy);
             obs[o++] = (float)a_diff;
             obs[o++] = (float)py_distance(x, y, gx, gy);
+#pragma unroll 1
             for (int k = 0; k < 8; ++k) {
                 V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
                 obs[o++] = (float)((double)p.x * K.SCALE);
@@ -158,6 +163,7 @@ struct Env : Sim {
             }
             reward += (prev_bd - bd) * K.rp.blockDelta * 1.0 / 4.;
             reward -= K.rp.blockDistance * bd * 1.0 / 4.;
+#pragma unroll 1
             for (int i = 0; i < n; ++i) {
                 reward += (prev_ad[i] - ad[i]) * K.rp.agentDelta * 1.0 / 4.;
                 reward -= K.rp.agentDistance * ad[i] * 1.0 / 4.;
@@ -175,6 +181,7 @@ struct Env : Sim {
         const int64_t env_ix = G - K.S;
         const double eps = K.eps_env ? K.eps_env[env_ix] : K.rp.scaled_epsilon;
         const double decay_pow = K.decay_env ? K.decay_env[env_ix] : K.rp.decay_pow;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) {
             int b = 1 + i;
             double aX = (double)B(b, 0) * K.ratio, aY = (double)B(b, 1) * K.ratio;
@@ -200,6 +207,7 @@ struct Env : Sim {
             obs[o++] = (float)(y - gy);
             obs[o++] = (float)a_diff;
             obs[o++] = (float)py_distance(x, y, gx, gy);
+#pragma unroll 1
             for (int k = 0; k < 8; ++k) {
                 V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
                 obs[o++] = (float)((double)p.x * K.ratio);
@@ -209,12 +217,14 @@ struct Env : Sim {
         obs[o++] = (float)eps;
         reward += (prev_bd - bd) * K.rp.blockDelta;
         reward -= K.rp.blockDistance * bd;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) {
             reward += (prev_ad[i] - ad[i]) * K.rp.agentDelta;
             reward -= K.rp.agentDistance * ad[i];
         }
         const double BOUNDS = 0.1;
         bool agt_oob = false;
+#pragma unroll 1
         for (int i = 0; i < n && !agt_oob; ++i) {
             double x = (double)B(1 + i, 0), y = (double)B(1 + i, 1);
             if (x < BOUNDS || x > (K.W - BOUNDS)) agt_oob = true;
@@ -237,6 +247,7 @@ struct Env : Sim {
         int now = in_place ? 1 : 0;
         g(W_INPLACE) = (uint32_t)now;
         int num_in_contact = 0;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) num_in_contact += (goalc >> i) & 1;
         bool done = false;
         if (now == 1) {
