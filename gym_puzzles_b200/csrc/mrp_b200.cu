@@ -292,6 +292,10 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
 // trip; a warp refills its idle lanes from the global task queue once kRefill of them are idle, so the 32 lanes
 // stay busy although islands need anywhere between 2 and ~1000 operations.
 constexpr int kRefill = 8;
+#ifndef MRP_INNER_TRIPS
+#define MRP_INNER_TRIPS 4
+#endif
+constexpr int kInnerTrips = MRP_INNER_TRIPS;
 
 template <int CLS>
 __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
@@ -313,11 +317,16 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
         if (busy) {
-            bool fin;
-            if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
-            else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
-            else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
-            else { vt.ops += 1; fin = s.vr_trip(vt.st, 180); }
+            // a few trips between two refill checks: the warp-wide ballots (reconvergence points) were 17 % of this
+            // kernel's stall samples when taken every trip
+            bool fin = false;
+#pragma unroll 1
+            for (int rep = 0; rep < (CLS == 3 ? kInnerTrips * 2 : kInnerTrips) && !fin; ++rep) {
+                if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
+                else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
+                else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
+                else { vt.ops += 1; fin = s.vr_trip(vt.st, 180); }
+            }
             if (fin) {
                 vel_task_end(K, s, vt);
                 busy = false;
@@ -673,7 +682,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
         free(row);
     }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
-    h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 24 + 4 * K.ndynfix) * kBlock);
+    h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(11 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
