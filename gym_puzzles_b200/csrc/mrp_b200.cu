@@ -361,9 +361,14 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
-        if (busy && s.pos_trip<true>(pt.st, pt.T, 60, -1, -1)) {
-            pos_task_end(K, s, pt);
-            busy = false;
+        if (busy) {
+            bool fin = false;
+#pragma unroll 1
+            for (int rep = 0; rep < kInnerTrips && !fin; ++rep) fin = s.pos_trip<true>(pt.st, pt.T, 60, -1, -1);
+            if (fin) {
+                pos_task_end(K, s, pt);
+                busy = false;
+            }
         }
     }
 }
