@@ -12,7 +12,7 @@ steps applies).  One "step" = one env.step of every env of the batch.
             K steps bracketed by barrier + synchronize, CUDA-event timed, max over ranks.
   e2e       the same through mrp_step_host(): pinned HOST action buffer -> H2D, step, obs/reward/done/trunc D2H,
             every step, copies inside the timed region.
-  roofline  dominant kernel of the step's phase pipeline (k_pre / k_solve_vel / k_solve_pos / k_post / k_post_events):
+  roofline  dominant phase of the step's pipeline (k_broad+k_narrow+k_pre / k_solve_vel / k_solve_pos / k_post / k_post_events):
             algorithmic bytes (513 B per env-step, SURVEY.md §8d / DESIGN.md) over its mean launch time, measured with
             CUDA events recorded between the kernels inside the library (mrp_set_timing / mrp_get_phase_timing).
   cpu_baseline  the oracle ("port": pybox2d is not installable here) on all host cores, bounded sample.
@@ -239,8 +239,10 @@ def run_native(args):
             try:
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture,
                 # scaled from the profiled batch size to this run's
-                rec = json.load(open(tp))[dom]
-                traffic = rec["dram_bytes_per_launch"] * (N / rec["envs"])
+                # the "k_pre" timer spans the three collide / setup launches k_broad + k_narrow + k_pre
+                recs = json.load(open(tp))
+                names = ["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom]
+                traffic = sum(recs[k]["dram_bytes_per_launch"] * (N / recs[k]["envs"]) for k in names)
             except Exception:
                 traffic = None
         line = {
@@ -256,7 +258,7 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / k_mean_ms if k_mean_ms else None,
+                         "kernel": "k_broad+k_narrow+k_pre" if dom == "k_pre" else dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / k_mean_ms if k_mean_ms else None,
                          "kernels_ms": per_kernel, "pipeline_ms": k_mean_ms, "pipeline_achieved": pipeline_gbs,
                          "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
             "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},
