@@ -114,6 +114,8 @@ def load():
     if _default is None:
         # MRP_LIB_PATH: another build of the same library (A/B measurements of two builds on one box); still CUDA-only
         _default = MrpLib(os.environ.get("MRP_LIB_PATH", LIB_PATH))
+        if not _default.backend.startswith("cuda"):
+            raise MrpError(f"{_default.path} is not the CUDA library ({_default.backend}): gym_puzzles_b200 has no CPU fallback")
     return _default
 
 

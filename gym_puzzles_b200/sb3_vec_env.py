@@ -20,8 +20,30 @@ import numpy as np
 from . import abi, spaces
 
 
+def _cuda_buffers(h, term, n_envs, device):
+    """torch views of the library's terminal buffers, a gather of the done rows, pinned host staging buffers"""
+    import torch
+
+    from .vector_env import _wrap
+
+    if not h.lib.backend.startswith("cuda"):
+        raise abi.MrpError("SB3VecEnv needs the CUDA library: gym_puzzles_b200 has no CPU fallback")
+    dev = torch.device("cuda", device)
+    t_obs = _wrap(torch, term.terminal_obs_dev, (n_envs, h.obs_dim), "<f4", h, dev)
+    t_ret = _wrap(torch, term.episode_return_dev, (n_envs,), "<f4", h, dev)
+    t_len = _wrap(torch, term.episode_length_dev, (n_envs,), "<i4", h, dev)
+
+    def gather(idx):
+        sel = torch.from_numpy(idx).to(dev)
+        return t_obs[sel].cpu().numpy(), t_ret[sel].cpu().numpy(), t_len[sel].cpu().numpy()
+
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    return (t_obs, t_ret, t_len, gather, pin((n_envs, h.obs_dim), torch.float32), pin((n_envs,), torch.float32),
+            pin((n_envs,), torch.uint8), pin((n_envs,), torch.uint8), pin((n_envs, h.act_dim), torch.float32))
+
+
 class SB3VecEnv:
-    def __init__(self, env_id, n_envs, device=0, seed=17, n_agents=0, env_id_base=0, max_episode_steps=0, _lib=None):
+    def __init__(self, env_id, n_envs, device=0, seed=17, n_agents=0, env_id_base=0, max_episode_steps=0, _lib=None, _buffers=None):
         self.handle = abi.Handle(env_id, n_envs, device=device, seed=seed, n_agents=n_agents, env_id_base=env_id_base,
                                  auto_reset=True, max_episode_steps=max_episode_steps, lib=_lib)
         h = self.handle
@@ -30,29 +52,11 @@ class SB3VecEnv:
         self.observation_space = spaces.observation_space(env_id, n)
         self.action_space = spaces.action_space(env_id, n)
         self._term = h.enable_terminal_info()
-        self._cuda = h.lib.backend.startswith("cuda")
-        if self._cuda:
-            import torch
-            from .vector_env import _wrap
-
-            dev = torch.device("cuda", device)
-            self._t_obs = _wrap(torch, self._term.terminal_obs_dev, (n_envs, h.obs_dim), "<f4", h, dev)
-            self._t_ret = _wrap(torch, self._term.episode_return_dev, (n_envs,), "<f4", h, dev)
-            self._t_len = _wrap(torch, self._term.episode_length_dev, (n_envs,), "<i4", h, dev)
-            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-            self._obs, self._rew = pin((n_envs, h.obs_dim), torch.float32), pin((n_envs,), torch.float32)
-            self._done, self._trunc = pin((n_envs,), torch.uint8), pin((n_envs,), torch.uint8)
-            self._act = pin((n_envs, h.act_dim), torch.float32)
-        else:   # host build of the kernel source (tests only): "device" pointers are host pointers
-            import ctypes as C
-
-            view = lambda p, shape, ct, dt: np.frombuffer((ct * int(np.prod(shape))).from_address(p), dtype=dt).reshape(shape)  # noqa: E731
-            self._t_obs = view(self._term.terminal_obs_dev, (n_envs, h.obs_dim), C.c_float, np.float32)
-            self._t_ret = view(self._term.episode_return_dev, (n_envs,), C.c_float, np.float32)
-            self._t_len = view(self._term.episode_length_dev, (n_envs,), C.c_int32, np.int32)
-            self._obs, self._rew = np.empty((n_envs, h.obs_dim), np.float32), np.empty(n_envs, np.float32)
-            self._done, self._trunc = np.empty(n_envs, np.uint8), np.empty(n_envs, np.uint8)
-            self._act = np.empty((n_envs, h.act_dim), np.float32)
+        # device views of the terminal buffers + pinned host staging buffers; `_buffers` is a test hook (the CPU test-suite
+        # injects views over the host build of the kernel source together with `_lib`), the product path is CUDA only
+        make = _buffers if _buffers is not None else _cuda_buffers
+        (self._t_obs, self._t_ret, self._t_len, self._gather,
+         self._obs, self._rew, self._done, self._trunc, self._act) = make(h, self._term, n_envs, device)
         self._t0 = time.time()
         self._pending = False
         self.render_mode = None
@@ -73,13 +77,7 @@ class SB3VecEnv:
         infos = [{} for _ in range(self.num_envs)]
         idx = np.nonzero(dones)[0]
         if idx.size:
-            if self._cuda:
-                import torch
-
-                sel = torch.from_numpy(idx).to(self._t_obs.device)
-                t_obs, t_ret, t_len = self._t_obs[sel].cpu().numpy(), self._t_ret[sel].cpu().numpy(), self._t_len[sel].cpu().numpy()
-            else:
-                t_obs, t_ret, t_len = self._t_obs[idx].copy(), self._t_ret[idx].copy(), self._t_len[idx].copy()
+            t_obs, t_ret, t_len = self._gather(idx)
             now = round(time.time() - self._t0, 6)
             for k, i in enumerate(idx):
                 infos[i] = {"terminal_observation": t_obs[k], "TimeLimit.truncated": bool(self._trunc[i]),

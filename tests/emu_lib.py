@@ -17,3 +17,20 @@ def emu_lib():
         _lib = abi.MrpLib(os.path.join(EMU_DIR, "libmrp_emu.so"))
         assert _lib.backend.startswith("host-emu")
     return _lib
+
+
+def host_buffers(h, term, n_envs, device):
+    """`_buffers` hook of gym_puzzles_b200.SB3VecEnv for the host build: its "device" pointers are host pointers."""
+    import ctypes as C
+
+    import numpy as np
+
+    def view(p, shape, ct, dt):
+        return np.frombuffer((ct * int(np.prod(shape))).from_address(p), dtype=dt).reshape(shape)
+
+    t_obs = view(term.terminal_obs_dev, (n_envs, h.obs_dim), C.c_float, np.float32)
+    t_ret = view(term.episode_return_dev, (n_envs,), C.c_float, np.float32)
+    t_len = view(term.episode_length_dev, (n_envs,), C.c_int32, np.int32)
+    gather = lambda idx: (t_obs[idx].copy(), t_ret[idx].copy(), t_len[idx].copy())  # noqa: E731
+    return (t_obs, t_ret, t_len, gather, np.empty((n_envs, h.obs_dim), np.float32), np.empty(n_envs, np.float32),
+            np.empty(n_envs, np.uint8), np.empty(n_envs, np.uint8), np.empty((n_envs, h.act_dim), np.float32))

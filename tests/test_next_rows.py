@@ -19,7 +19,11 @@ def _emu():
 def _check_sb3_adapter(lib, env_id="MultiRobotPuzzleHeavy-v0", n=48, cap=15, steps=50):
     """against the oracle stepped WITHOUT auto-reset semantics visible: the oracle's own obs before reset is what the
     adapter must report as terminal_observation"""
-    venv = gp.SB3VecEnv(env_id, n, seed=7, max_episode_steps=cap, _lib=lib)
+    kw = {}
+    if lib is not None:
+        from emu_lib import host_buffers
+        kw = {"_lib": lib, "_buffers": host_buffers}
+    venv = gp.SB3VecEnv(env_id, n, seed=7, max_episode_steps=cap, **kw)
     o = OracleBatch(env_id, n, seed=7, max_episode_steps=cap)
     o_term = OracleBatch(env_id, n, seed=7, max_episode_steps=cap)   # same rollout with auto-reset off at the done step
     obs = venv.reset()
