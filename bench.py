@@ -245,6 +245,16 @@ def run_native(args):
                 traffic = sum(recs[k]["dram_bytes_per_launch"] * (N / recs[k]["envs"]) for k in names)
             except Exception:
                 traffic = None
+        # FP32-issue view of the same kernels (north star: "fraction of the FP32 and HBM roofline"): issue-slot and FMA-pipe
+        # utilisation, active lanes per instruction and the leading stall reasons from the committed ncu --set full capture
+        issue = None
+        ip = os.path.join(ROOT, "profiles", "kernel_issue.json")
+        if os.path.exists(ip):
+            try:
+                rec = json.load(open(ip))
+                issue = {k: rec[k] for k in (["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom]) if k in rec}
+            except Exception:
+                issue = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -260,6 +270,7 @@ def run_native(args):
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "k_broad+k_narrow+k_pre" if dom == "k_pre" else dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / k_mean_ms if k_mean_ms else None,
                          "kernels_ms": per_kernel, "pipeline_ms": k_mean_ms, "pipeline_achieved": pipeline_gbs,
+                         "fp32_issue_from_ncu": issue,
                          "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
             "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},
         }
