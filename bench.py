@@ -121,7 +121,7 @@ def run_reference(args):
                                    "no Python/SWIG overhead => upper bound on the reference)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    GUARD.emit(json.dumps(line))
 
 
 def run_native(args):
@@ -279,14 +279,35 @@ def run_native(args):
             v, dt = cpu_baseline_run(args.ref_envs, args.cpu_steps, 2, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.ref_envs} envs x {args.cpu_steps} steps of the same workload, {cores} threads, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        GUARD.emit(json.dumps(line))
     env.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class StdoutGuard:
+    """Everything libraries write to fd 1 while the benchmark runs (e.g. NCCL's version banner) goes to stderr, so that
+    stdout carries exactly ONE line: the JSON result printed through emit()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
+GUARD = None
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -98,10 +98,11 @@ MRP_HD void broad_lane(const SimConst& K, float* sm, const float* ct, int64_t en
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
 MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
     Env e(K, sm, ct, env, nullptr, 13);
-    e.load();
+    // the action row is requested first so that it is in flight while the state words are loaded
     float a[3 * MRP_MAX_AGENTS];
     const float* arow = K.act + env * K.act_dim;
     for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+    e.load();
     e.pre_phase(a);
 }
 

@@ -32,6 +32,13 @@ constexpr int kBlock = 128;
 constexpr int kMaxC = MRP_MAXC;  // mrp_layout.max_contacts <= kMaxC
 // fixtures on dynamic bodies: v0 2 + 8 robots, v2 2 + 3 * 2 in the default build; 2 + 3 * 8 in the wide one
 constexpr int kMaxDynFix = MRP_MAXC == 32 ? 12 : 28;
+MRP_HD int clz_u32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
+#endif
+}
 MRP_HD int ctz_u32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __ffs((int)x) - 1;
@@ -1239,6 +1246,53 @@ struct Sim {
             island_of[0] = 0;
             return 1;
         }
+#if MRP_MAXC == 32
+        if (touch) {
+            // per-body sets of touching contacts, so that popping a body visits only its own contacts (newest first)
+            // instead of scanning the whole contact list; same visiting order, hence the same solver order
+            uint32_t bmask[16];
+            for (int b = 0; b < K.nb + 4; ++b) bmask[b] = 0u;
+            for (uint32_t rest = touch; rest; rest &= rest - 1u) {
+                const int k = ctz_u32(rest);
+                const uint32_t m = meta[k];
+                bmask[(m >> 20) & 15] |= 1u << k;
+                bmask[(m >> 24) & 15] |= 1u << k;
+            }
+            uint32_t bflag = 0, cflag = 0;
+            int nisl = 0;
+            for (int seed = K.nb - 1; seed >= 0; --seed) {
+                if ((bflag >> seed) & 1) continue;
+                if (!bmask[seed]) { bflag |= 1u << seed; continue; }  // no touching contact: an island without constraints
+                uint64_t stack = (uint64_t)seed;  // 4 bits per entry
+                int sp = 1;
+                bflag |= 1u << seed;
+                uint32_t statics = 0;
+                const int T0 = T;
+                while (sp > 0) {
+                    --sp;
+                    const int b = (int)((stack >> (4 * sp)) & 15u);
+                    if (!is_dyn(b)) { statics |= 1u << b; continue; }
+                    for (uint32_t cand = bmask[b] & ~cflag; cand;) {
+                        const int k = 31 - clz_u32(cand);
+                        cand &= ~(1u << k);
+                        const uint32_t m = meta[k];
+                        const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+                        order[T] = (uint8_t)k;
+                        island_of[T] = (uint8_t)nisl;
+                        ++T;
+                        cflag |= 1u << k;
+                        const int other = bA == b ? bB : bA;
+                        if ((bflag >> other) & 1) continue;
+                        stack = (stack & ~(15ull << (4 * sp))) | ((uint64_t)other << (4 * sp));
+                        ++sp;
+                        bflag |= 1u << other;
+                    }
+                }
+                bflag &= ~statics;  // static bodies may join later islands
+                if (T > T0) ++nisl;
+            }
+        }
+#else
         if (cm_any(touch)) {
             uint32_t bflag = 0;
             CMask cflag = cm_none();
@@ -1274,6 +1328,7 @@ struct Sim {
                 if (T > T0) ++nisl;
             }
         }
+#endif
         return T;
     }
 
