@@ -322,11 +322,11 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
             // kernel's stall samples when taken every trip
             bool fin = false;
 #pragma unroll 1
-            for (int rep = 0; rep < (CLS == 3 ? kInnerTrips * 2 : kInnerTrips) && !fin; ++rep) {
+            for (int rep = 0; rep < kInnerTrips && !fin; ++rep) {
                 if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
                 else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
                 else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
-                else { vt.ops += 1; fin = s.vr_trip(vt.st, 180); }
+                else { vt.ops += (uint32_t)vt.st.vpc + 1u; fin = s.vr_trip_contact(vt.st, 180); }
             }
             if (fin) {
                 vel_task_end(K, s, vt);
@@ -950,7 +950,7 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
             if (cls == 0) { while (vt.ops += 2, !s.vr_sweep_single<1>(vt.st, 180)) {} }
             else if (cls == 1) { while (vt.ops += 3, !s.vr_sweep_single<2>(vt.st, 180)) {} }
             else if (cls == 2) { while (vt.ops += 5, !s.vr_sweep_pair(vt.st, st1, 180)) {} }
-            else { while (++vt.ops, !s.vr_trip(vt.st, 180)) {} }
+            else { while (vt.ops += (uint32_t)vt.st.vpc + 1u, !s.vr_trip_contact(vt.st, 180)) {} }
             vel_task_end(K, s, vt);
         }
     }

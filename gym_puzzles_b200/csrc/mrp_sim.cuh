@@ -1067,6 +1067,28 @@ struct Sim {
         }
         return false;
     }
+    // generic form for the persistent solver: one whole CONTACT per trip (friction points, then the normal point or the
+    // block solve — the order vr_trip walks), so lanes of a warp only diverge between 1- and 2-point manifolds instead of
+    // between four kinds of point operation, and the per-trip bookkeeping is paid once per contact
+    MRP_HD bool vr_trip_contact(VelReg& r, int iters) {
+        vr_contact_ops(r);
+        bool wrapped = true;
+        if (r.T > 1) {
+            vr_store(r);
+            wrapped = ++r.t == r.T;
+            if (wrapped) r.t = 0;
+            vr_load(r);
+        }
+        if (wrapped) {
+            ++r.sweep;
+            if (!r.changed || r.sweep == iters) {
+                if (r.T == 1) vr_store(r);
+                return true;
+            }
+            r.changed = false;
+        }
+        return false;
+    }
     // two-contact islands: both constraint records stay in registers; only the body velocities travel through the
     // lane's shared-memory slots between the two contacts (they may share one or both bodies)
     MRP_HD void vr_begin_pair(VelReg& r0, VelReg& r1) {
