@@ -1180,13 +1180,15 @@ struct Sim {
         pos_begin(st);
         while (!pos_trip(st, T, maxSweeps, toiA, toiB)) {}
     }
+    // one CONTACT per trip (all its manifold points, in order): the constraint record and the two bodies are read once,
+    // corrected in registers and written back once
     template <bool INL = false>
     MRP_HD bool pos_trip(PosState& st, int T, int maxSweeps, int toiA, int toiB) {
         const bool toi = toiA >= 0;
         const float baum = toi ? kToiBaumgarte : kBaumgarte;
         const float lim = toi ? -1.5f * kLinearSlop : -3.0f * kLinearSlop;
         uint32_t done = st.done, bad = st.bad;
-        int t = st.t, j = st.j;
+        int t = st.t;
         float minSep = st.minSep;
         bool finished = false;
         {
@@ -1203,56 +1205,57 @@ struct Sim {
                 V2 cA = mk(B(bA, 0), B(bA, 1)), cB = mk(B(bB, 0), B(bB, 1));
                 float aA = B(bA, 2), aB = B(bB, 2);
                 const V2 ln = mk(V(t, VC_LNX), V(t, VC_LNY)), lp = mk(V(t, VC_LPX), V(t, VC_LPY));
-                Xf xfA, xfB;
-                xfA.q = body_rot<INL>(bA, aA);
-                xfB.q = body_rot<INL>(bB, aB);
-                xfA.p = cA - rmul(xfA.q, localCenter(bA));
-                xfB.p = cB - rmul(xfB.q, localCenter(bB));
-                const V2 lpj = mk(V(t, VC_LP0X + 2 * j), V(t, VC_LP0X + 2 * j + 1));
-                V2 normal, point;
-                float separation;
-                if (type == 0) {
-                    normal = rmul(xfA.q, ln);
-                    V2 planePoint = xmul(xfA, lp);
-                    V2 clip = xmul(xfB, lpj);
-                    separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
-                    point = clip;
-                } else {
-                    normal = rmul(xfB.q, ln);
-                    V2 planePoint = xmul(xfB, lp);
-                    V2 clip = xmul(xfA, lpj);
-                    separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
-                    point = clip;
-                    normal = -normal;
+                const V2 lp0 = mk(V(t, VC_LP0X), V(t, VC_LP0Y)), lp1 = mk(V(t, VC_LP1X), V(t, VC_LP1Y));
+#pragma unroll 1
+                for (int j = 0; j < ppc; ++j) {
+                    Xf xfA, xfB;
+                    xfA.q = body_rot<INL>(bA, aA);
+                    xfB.q = body_rot<INL>(bB, aB);
+                    xfA.p = cA - rmul(xfA.q, localCenter(bA));
+                    xfB.p = cB - rmul(xfB.q, localCenter(bB));
+                    const V2 lpj = j == 0 ? lp0 : lp1;
+                    V2 normal, point;
+                    float separation;
+                    if (type == 0) {
+                        normal = rmul(xfA.q, ln);
+                        V2 planePoint = xmul(xfA, lp);
+                        V2 clip = xmul(xfB, lpj);
+                        separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
+                        point = clip;
+                    } else {
+                        normal = rmul(xfB.q, ln);
+                        V2 planePoint = xmul(xfB, lp);
+                        V2 clip = xmul(xfA, lpj);
+                        separation = dot(clip - planePoint, normal) - kPolygonRadius - kPolygonRadius;
+                        point = clip;
+                        normal = -normal;
+                    }
+                    const V2 rA = point - cA, rB = point - cB;
+                    minSep = fmin2(minSep, separation);
+                    const float C = clampf(baum * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                    const float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                    const float Kn = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                    const float impulse = Kn > 0.0f ? -C / Kn : 0.0f;
+                    const V2 Pi = impulse * normal;
+                    cA = cA - mA * Pi;
+                    aA -= iA * cross(rA, Pi);
+                    cB = cB + mB * Pi;
+                    aB += iB * cross(rB, Pi);
                 }
-                const V2 rA = point - cA, rB = point - cB;
-                minSep = fmin2(minSep, separation);
-                const float C = clampf(baum * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-                const float rnA = cross(rA, normal), rnB = cross(rB, normal);
-                const float Kn = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                const float impulse = Kn > 0.0f ? -C / Kn : 0.0f;
-                const V2 Pi = impulse * normal;
-                cA = cA - mA * Pi;
-                aA -= iA * cross(rA, Pi);
-                cB = cB + mB * Pi;
-                aB += iB * cross(rB, Pi);
                 B(bA, 0) = cA.x; B(bA, 1) = cA.y; B(bA, 2) = aA;
                 B(bB, 0) = cB.x; B(bB, 1) = cB.y; B(bB, 2) = aB;
             }
-            if (++j >= ppc || ((done >> isl) & 1)) {
-                if (!(minSep >= lim)) bad |= 1u << isl;
-                minSep = 0.0f;
-                j = 0;
-                if (++t == T) {
-                    t = 0;
-                    ++st.sweep;
-                    done = ~bad;
-                    if (!bad || st.sweep == maxSweeps) finished = true;
-                    bad = 0;
-                }
+            if (!(minSep >= lim)) bad |= 1u << isl;
+            minSep = 0.0f;
+            if (++t == T) {
+                t = 0;
+                ++st.sweep;
+                done = ~bad;
+                if (!bad || st.sweep == maxSweeps) finished = true;
+                bad = 0;
             }
         }
-        st.done = done; st.bad = bad; st.t = t; st.j = j; st.minSep = minSep;
+        st.done = done; st.bad = bad; st.t = t; st.j = 0; st.minSep = minSep;
         return finished;
     }
 
