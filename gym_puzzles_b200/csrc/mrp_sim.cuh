@@ -1568,12 +1568,8 @@ struct Sim {
                     uint32_t m = meta[k];
                     int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
                     if (is_dyn(bA) && is_dyn(bB)) continue;
-                    // fixture A is the dynamic one (walls are the last fixtures); cull only untouched sweeps
-                    if (alpha0(bA) == 0.0f && alpha0(bB) == 0.0f && toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) {
-                        toi[k] = 1.0f;
-                        cm_set(toiFlag, k);
-                        continue;
-                    }
+                    // b2World::SolveTOI first aligns the two sweeps to the larger alpha0 (a side effect that later contacts
+                    // of the same bodies see, walls included), then calls b2TimeOfImpact
                     float al0 = alpha0(bA);
                     if (alpha0(bA) < alpha0(bB)) {
                         al0 = alpha0(bB);
@@ -1581,6 +1577,13 @@ struct Sim {
                     } else if (alpha0(bB) < alpha0(bA)) {
                         al0 = alpha0(bA);
                         sweep_advance(bB, al0);
+                    }
+                    // fixture A is the dynamic one (walls are the last fixtures).  The culling bound covers every
+                    // intermediate pose of the sweep swept[] was computed for, hence also an advanced remainder of it
+                    if (toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) {
+                        toi[k] = 1.0f;
+                        cm_set(toiFlag, k);
+                        continue;
                     }
                     float t;
                     int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
