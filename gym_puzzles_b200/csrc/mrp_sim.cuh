@@ -801,11 +801,6 @@ struct Sim {
     // independently, so a warp runs max_lane(total ops) trips instead of 180 x max_lane(contacts) x max(points).
     // The operation order inside an env is exactly Box2D's.  A lane stops after the first sweep that changes
     // nothing: every later sweep would be the identical no-op, so the result equals the full 180 bit for bit.
-    struct VelState {
-        int t, j, sweep;
-        bool changed;
-    };
-    MRP_HD void vel_begin(VelState& st) { st.t = 0; st.j = 0; st.sweep = 0; st.changed = false; }
     MRP_HD void solve_velocity(int T, int iters) {
         if (T == 0) return;
         if (T == 1) {  // register-resident forms (identical arithmetic, see vr_*)
@@ -821,114 +816,14 @@ struct Sim {
             while (!vr_sweep_pair(r0, r1, iters)) {}
             return;
         }
-        VelState st;
-        vel_begin(st);
-        while (!vel_trip(st, T, iters)) {}
-    }
-    // one point operation; returns true when the solve is finished
-    MRP_HD bool vel_trip(VelState& st, int T, int iters) {
-        int t = st.t, j = st.j;
-        bool changed = st.changed;
-        bool finished = false;
-        {
-            const uint32_t vm = vmeta(t);
-            const int bA = vm & 15, bB = (vm >> 4) & 15, vpc = (vm >> 8) & 3;
-            float* const C = &V(t, 0);
-            const float mA = C[VC_MA], mB = C[VC_MB], iA = C[VC_IA], iB = C[VC_IB];
-            float* const pA = bp(bA);
-            float* const pB = bp(bB);
-            V2 vA = mk(pA[3 * MRP_SS], pA[4 * MRP_SS]), vB = mk(pB[3 * MRP_SS], pB[4 * MRP_SS]);
-            float wA = pA[5 * MRP_SS], wB = pB[5 * MRP_SS];
-            const V2 normal = mk(C[VC_NX], C[VC_NY]);
-            if (j < vpc || vpc == 1) {
-                // 1-D op: friction (j < vpc) along the tangent, else the single normal point
-                const bool fr = j < vpc;
-                float* P = &V(t, VC_PT + 8 * (fr ? j : 0));
-                const V2 dir = fr ? crossVS(normal, 1.0f) : normal;
-                const V2 rA = mk(P[0], P[1]), rB = mk(P[2], P[3]);
-                const V2 dv = vB + crossSV(wB, rB) - vA - crossSV(wA, rA);
-                const float vd = dot(dv, dir);
-                const float acc = fr ? P[7] : P[6];
-                float lambda = (fr ? P[5] : P[4]) * (-vd);  // tangentMass*(-vt)  ==  -normalMass*vn (exact sign symmetry)
-                float newImpulse;
-                if (fr) {
-                    const float maxFriction = V(t, VC_FRIC) * P[6];
-                    newImpulse = clampf(acc + lambda, -maxFriction, maxFriction);
-                } else {
-                    newImpulse = fmax2(acc + lambda, 0.0f);
-                }
-                lambda = newImpulse - acc;
-                if (fr) P[7] = newImpulse; else P[6] = newImpulse;
-                changed = changed || (lambda != 0.0f);
-                const V2 Pi = lambda * dir;
-                vA = vA - mA * Pi;
-                wA -= iA * cross(rA, Pi);
-                vB = vB + mB * Pi;
-                wB += iB * cross(rB, Pi);
-            } else {
-                // block solver (2 points)
-                float* P1 = &V(t, VC_PT);
-                float* P2 = &V(t, VC_PT + 8);
-                const V2 rA1 = mk(P1[0], P1[1]), rB1 = mk(P1[2], P1[3]);
-                const V2 rA2 = mk(P2[0], P2[1]), rB2 = mk(P2[2], P2[3]);
-                const float ax = P1[6], ay = P2[6];
-                const V2 dv1 = vB + crossSV(wB, rB1) - vA - crossSV(wA, rA1);
-                const V2 dv2 = vB + crossSV(wB, rB2) - vA - crossSV(wA, rA2);
-                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-                const float k11 = V(t, VC_K11), k12 = V(t, VC_K12), k22 = V(t, VC_K22);
-                float bx = vn1, by = vn2;
-                bx -= k11 * ax + k12 * ay;
-                by -= k12 * ax + k22 * ay;
-                float xx, xy;
-                bool ok = false;
-                xx = -(V(t, VC_M11) * bx + V(t, VC_M12) * by);  // case 1
-                xy = -(V(t, VC_M12) * bx + V(t, VC_M22) * by);
-                if (xx >= 0.0f && xy >= 0.0f) ok = true;
-                if (!ok) {  // case 2
-                    xx = -P1[4] * bx; xy = 0.0f;
-                    vn2 = k12 * xx + by;
-                    if (xx >= 0.0f && vn2 >= 0.0f) ok = true;
-                }
-                if (!ok) {  // case 3
-                    xx = 0.0f; xy = -P2[4] * by;
-                    vn1 = k12 * xy + bx;
-                    if (xy >= 0.0f && vn1 >= 0.0f) ok = true;
-                }
-                if (!ok) {  // case 4
-                    xx = 0.0f; xy = 0.0f;
-                    if (bx >= 0.0f && by >= 0.0f) ok = true;
-                }
-                if (ok) {
-                    const float dx = xx - ax, dy = xy - ay;
-                    const V2 Pa = dx * normal, Pb = dy * normal;
-                    vA = vA - mA * (Pa + Pb);
-                    wA -= iA * (cross(rA1, Pa) + cross(rA2, Pb));
-                    vB = vB + mB * (Pa + Pb);
-                    wB += iB * (cross(rB1, Pa) + cross(rB2, Pb));
-                    P1[6] = xx; P2[6] = xy;
-                    changed = changed || (dx != 0.0f) || (dy != 0.0f);
-                }
-            }
-            pA[3 * MRP_SS] = vA.x; pA[4 * MRP_SS] = vA.y; pA[5 * MRP_SS] = wA;
-            pB[3 * MRP_SS] = vB.x; pB[4 * MRP_SS] = vB.y; pB[5 * MRP_SS] = wB;
-            // advance the (sweep, contact, op) counters
-            if (++j > vpc) {
-                j = 0;
-                if (++t == T) {
-                    t = 0;
-                    ++st.sweep;
-                    if (!changed || st.sweep == iters) finished = true;
-                    changed = false;
-                }
-            }
-        }
-        st.t = t; st.j = j; st.changed = changed;
-        return finished;
+        VelReg r;  // larger islands: one contact per trip, the current constraint record in registers
+        vr_begin(r, T);
+        while (!vr_trip_contact(r, iters)) {}
     }
     // ---- register-resident form of the velocity solve (solver kernel): the current contact's constraint record and
     // the velocities of its two bodies live in registers while its point operations run; they are exchanged with
     // memory only when the lane moves on to another contact.  Islands with one contact (the common case) therefore
-    // iterate entirely in registers.  Arithmetic and operation order are identical to vel_trip().
+    // iterate entirely in registers.  Arithmetic and operation order are Box2D's (friction points, then the normal point / block solve, contact by contact).
     struct VelReg {
         int T, t, j, sweep, bA, bB, vpc;
         bool changed;
@@ -1041,34 +936,8 @@ struct Sim {
             r.changed = r.changed || (dx != 0.0f) || (dy != 0.0f);
         }
     }
-    // generic form: one point operation per trip, any island; returns true when finished (everything written back)
-    MRP_HD bool vr_trip(VelReg& r, int iters) {
-        const int j = r.j;
-        if (j < r.vpc) { if (j == 0) vr_op_1d<0>(r); else vr_op_1d<1>(r); }
-        else if (r.vpc == 1) vr_op_1d<2>(r);
-        else vr_op_block(r);
-        if (++r.j > r.vpc) {
-            r.j = 0;
-            bool wrapped = true;
-            if (r.T > 1) {
-                vr_store(r);
-                wrapped = ++r.t == r.T;
-                if (wrapped) r.t = 0;
-                vr_load(r);
-            }
-            if (wrapped) {
-                ++r.sweep;
-                if (!r.changed || r.sweep == iters) {
-                    if (r.T == 1) vr_store(r);
-                    return true;
-                }
-                r.changed = false;
-            }
-        }
-        return false;
-    }
     // generic form for the persistent solver: one whole CONTACT per trip (friction points, then the normal point or the
-    // block solve — the order vr_trip walks), so lanes of a warp only diverge between 1- and 2-point manifolds instead of
+    // block solve — Box2D's order), so lanes of a warp only diverge between 1- and 2-point manifolds instead of
     // between four kinds of point operation, and the per-trip bookkeeping is paid once per contact
     MRP_HD bool vr_trip_contact(VelReg& r, int iters) {
         vr_contact_ops(r);
