@@ -1388,29 +1388,25 @@ struct Sim {
 
     // returns false when a TOI event must be processed but allow_events is false (the caller then defers this env
     // to the event kernel, which redoes the scan from the same state)
-    // First TOI scan of a step when events are deferred to k_post_events (k_post): every alpha0 is still 0 and no
-    // contact has been advanced, so the scan of solve_toi() reduces to "does any wall contact report e_touching with
-    // alpha <= 1 - 10 eps?"  (alpha = min(0 + (1 - 0) * t, 1) = t).  Same culling, same b2TimeOfImpact calls, no
-    // per-contact TOI cache and no sweep bookkeeping: a fraction of solve_toi()'s code in the hot kernel.
-    MRP_HD bool toi_scan_has_event() {
+    // First TOI scan of a step in k_post, where events are deferred to k_post_events: every alpha0 is still 0 and nothing
+    // has been advanced, so "no event" is certain when every wall contact is culled by the swept-AABB bound.  An env with
+    // a contact the bound cannot clear is handed to the event kernel, which runs the full solve_toi() (b2TimeOfImpact /
+    // GJK included) from the same state: k_post itself never evaluates a TOI — those calls ran with ~1 active lane per
+    // warp and their code (3 k instructions) no longer sits in the hot kernel.
+    MRP_HD bool toi_scan_needs_events() {
 #pragma unroll 1
         for (int k = nc - 1; k >= 0; --k) {
             const uint32_t m = meta[k];
             const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
             if (is_dyn(bA) && is_dyn(bB)) continue;
             // fixture A is the dynamic one (walls are the last fixtures)
-            if (toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) continue;
-            float t;
-            const int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
-            if (st != kToiTouching) continue;
-            const float alpha = fmin2(0.0f + (1.0f - 0.0f) * t, 1.0f);
-            if (alpha < 1.0f && !(1.0f - 10.0f * kEps < alpha)) return true;
+            if (!toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) return true;
         }
         return false;
     }
 
     MRP_HD bool solve_toi(bool allow_events = true) {
-        if (!allow_events) return !toi_scan_has_event();
+        if (!allow_events) return !toi_scan_needs_events();
         bool wallc = false;  // contacts with a static body: the only TOI candidates (no bullets)
 #pragma unroll 1
         for (int k = 0; k < nc; ++k) {
