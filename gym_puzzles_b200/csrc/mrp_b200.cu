@@ -89,10 +89,19 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
 }
 
 // phase 0 (lane per env): broadphase half of Collide — classify every contact, queue the ones that need SAT
-MRP_HD void broad_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+// returns the contacts of this env that need SAT + clipping
+MRP_HD CMask broad_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
     Env e(K, sm, ct, env, nullptr, 10);
     e.load();
-    e.broad_phase(env);
+    return e.broad_phase();
+}
+// queue entries of one env, `base` = the first of its cm_count(need) reserved slots
+MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
+    while (cm_any(need)) {
+        const int k = cm_first(need);
+        cm_clr(need, k);
+        K.narrow_list[base++] = (uint32_t)env * (uint32_t)kMaxC + (uint32_t)k;
+    }
 }
 
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
@@ -263,9 +272,23 @@ __global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimCon
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (loc >= K.nloc) return;
+    const bool valid = loc < K.nloc;   // every lane of the warp stays for the warp-aggregated queue reservation
     const int64_t env = K.env0 + loc;
-    broad_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    CMask need = cm_none();
+    if (valid) need = broad_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    // one atomicAdd per warp instead of one per queued contact (they were 14 % of this kernel's stall samples)
+    const int n = cm_count(need), lane = threadIdx.x & 31;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&K.cnt[CNT_NARROW], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (n) push_narrow(K, env, need, base + incl - n);
 }
 
 // SAT + clipping for the queued contacts: one lane per contact, grid-stride over the queue
@@ -935,7 +958,11 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
     for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
     const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
     // the same phases the device runs as kernels, executed as loops
-    for (int64_t e = e0; e < e1; ++e) broad_lane(K, h->emu_sm, h->ctab_dev, e);
+    for (int64_t e = e0; e < e1; ++e) {
+        const CMask need = broad_lane(K, h->emu_sm, h->ctab_dev, e);
+        const int n = cm_count(need);
+        if (n) push_narrow(K, e, need, atomic_add_i32(&K.cnt[CNT_NARROW], n));
+    }
     const int nnarrow = K.cnt[CNT_NARROW];
     for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
     for (int64_t e = e0; e < e1; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);

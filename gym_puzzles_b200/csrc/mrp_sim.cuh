@@ -46,8 +46,16 @@ MRP_HD int ctz_u32(uint32_t x) {
     return __builtin_ctz(x);
 #endif
 }
+MRP_HD int popc_u32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
 #if MRP_MAXC == 32
 typedef uint32_t CMask;
+MRP_HD int cm_count(const CMask& m) { return popc_u32(m); }
 MRP_HD CMask cm_none() { return 0u; }
 MRP_HD CMask cm_all() { return 0xffffffffu; }
 MRP_HD void cm_set(CMask& m, int k) { m |= 1u << k; }
@@ -74,6 +82,7 @@ MRP_HD int cm_first(const CMask& m) {
     for (int i = 0; i < kMaxC / 32; ++i) if (m.w[i]) return 32 * i + ctz_u32(m.w[i]);
     return -1;
 }
+MRP_HD int cm_count(const CMask& m) { int n = 0; for (int i = 0; i < kMaxC / 32; ++i) n += popc_u32(m.w[i]); return n; }
 #endif
 
 // ---- per-CTA constant table (floats; small ints stored as floats) -----------------
@@ -503,7 +512,9 @@ struct Sim {
     // ---- Collide split over three kernels: k_broad classifies every contact (destroyed / provably empty / needs
     // SAT), k_narrow runs SAT + clipping per queued contact with all lanes busy, k_pre replays the Begin/End events in
     // contact-list order and compacts.  The three together are exactly collide() below.
-    MRP_HD void broad_phase(int64_t env) {
+    // returns the set of contacts that need SAT + clipping (the caller queues them for k_narrow)
+    MRP_HD CMask broad_phase() {
+        CMask need = cm_none();
         for (int k = nc - 1; k >= 0; --k) {
             uint32_t m = meta[k] & 0x0fffffffu;
             if ((m >> 16) & 1) m |= kMetaWas;
@@ -514,10 +525,11 @@ struct Sim {
             } else if (manifold_provably_empty(fa, fb, bA, bB, body_xf(bA), body_xf(bB))) {
                 m &= 0xfff0ffffu | kMetaWas;  // pointCount 0, not touching
             } else {
-                K.narrow_list[atomic_add_i32(&K.cnt[CNT_NARROW], 1)] = (uint32_t)env * (uint32_t)kMaxC + (uint32_t)k;
+                cm_set(need, k);
             }
             g(cw(k, 0)) = m;
         }
+        return need;
     }
     MRP_HD void finish_collide() {
         CMask dead = cm_none();
