@@ -357,11 +357,15 @@ struct Sim {
     MRP_HD void load() {
         nc = (int)g(W_NC);
         goalc = g(W_GOALC);
+        // words a kernel's layout has no use for are not fetched: k_broad (10) needs pose and rotation only, k_pre (13)
+        // writes the pre-step pose words itself
+        const bool want_vel = fdyn != 10, want_c0 = c0f >= 0;
         for (int b = 0; b < K.nb; ++b) {
             const int w = K.w_body + kBodyWords * b;
             float r[kBodyWords];
 #pragma unroll
-            for (int i = 0; i < kBodyWords; ++i) r[i] = gf(w + i);
+            for (int i = 0; i < kBodyWords; ++i)
+                r[i] = ((i >= 3 && i <= 5 && !want_vel) || (i >= 8 && !want_c0)) ? 0.0f : gf(w + i);
             float* p = bp(b);
 #pragma unroll
             for (int f = 0; f < 6; ++f) p[f * MRP_SS] = r[f];
