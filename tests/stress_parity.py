@@ -1,11 +1,11 @@
-"""One-off large parity run on the GPU (not part of the test-suite): rollout of N envs against the oracle.
-  python profiles/stress_parity.py [ENV_ID] [N] [T]"""
+"""One-off large parity run on the GPU (a test tool, not collected by pytest): rollout of N envs against the oracle.
+  python tests/stress_parity.py [ENV_ID] [N] [T]        e.g. 65536 envs x 80 steps = 5.2M env-steps, ~6k TOI events"""
 import os
 import sys
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, HERE)
 from gym_puzzles_b200 import abi
 from parity_util import rollout_compare
 

@@ -139,3 +139,42 @@ def test_vecnormalize_wrapper_over_vector_env():
     sd = env.state_dict()
     np.testing.assert_allclose(sd["obs_rms.mean"], ref.obs_rms.mean, rtol=1e-8, atol=1e-8)
     env.close()
+
+
+def test_vecnorm_rank_sum_equals_global_batch():
+    """Multi-GPU VecNormalize: every rank computes shifted moments of its shard, the accumulator vectors are summed
+    (one NCCL all-reduce on the device; here the sum is done by hand on the host build) and every rank then holds the
+    statistics of ONE VecNormalize over the global batch."""
+    import ctypes as C
+    from emu_lib import emu_lib
+    N, O, R = 1200, 40, 3
+    rng = np.random.default_rng(3)
+    ranks = [VecNormHandle(N // R, O, lib=emu_lib()) for _ in range(R)]
+    whole = VecNormHandle(N, O, lib=emu_lib())
+
+    def accum(vn):
+        p, n = vn.accum()
+        return np.frombuffer((C.c_double * n).from_address(p), dtype=np.float64)
+
+    for t in range(6):
+        obs = (rng.standard_normal((N, O)) * 40 + 7).astype(np.float32)
+        rew = (rng.standard_normal(N) * 3).astype(np.float32)
+        done = (rng.uniform(size=N) < 0.2).astype(np.uint8)
+        out_w, rout_w = np.zeros_like(obs), np.zeros_like(rew)
+        whole.moments(obs.ctypes.data, rew.ctypes.data)
+        whole.apply(obs.ctypes.data, rew.ctypes.data, done.ctypes.data, out_w.ctypes.data, rout_w.ctypes.data)
+        shards = np.split(np.arange(N), R)
+        for vn, ix in zip(ranks, shards):
+            o, r = np.ascontiguousarray(obs[ix]), np.ascontiguousarray(rew[ix])
+            vn.moments(o.ctypes.data, r.ctypes.data)
+        total = sum(accum(vn).copy() for vn in ranks)          # the all-reduce
+        for vn in ranks:
+            accum(vn)[:] = total
+        for vn, ix in zip(ranks, shards):
+            o, r, d = (np.ascontiguousarray(a[ix]) for a in (obs, rew, done))
+            oo, ro = np.zeros_like(o), np.zeros_like(r)
+            vn.apply(o.ctypes.data, r.ctypes.data, d.ctypes.data, oo.ctypes.data, ro.ctypes.data)
+            np.testing.assert_allclose(oo, out_w[ix], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(ro, rout_w[ix], rtol=1e-5, atol=1e-5)
+    for vn in ranks:
+        np.testing.assert_allclose(vn.get_stats(), whole.get_stats(), rtol=1e-10, atol=1e-12)
