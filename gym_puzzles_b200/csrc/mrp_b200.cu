@@ -474,6 +474,7 @@ struct mrp_handle {
     cudaEvent_t cfork, cact, cact0, cjoin[kMaxChunks], cpost[kMaxChunks];
 #endif
     int64_t launches;
+    int64_t steps_done;  // mrp_step / mrp_step_host calls since the statistics were last reset (env_steps = steps_done * N)
     size_t smem_bytes;
     // optional device timing of the step kernel alone (bench.py roofline): ring of event pairs
     int timing;
@@ -1037,6 +1038,7 @@ static int step_chunks(const mrp_handle* h, int wanted) {
 int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
     FWD(mrp_step_wide(h->wide, actions_dev, stream))
     if (!h) return fail(-1, "mrp_step: null handle");
+    h->steps_done += 1;
     SimConst K = h->K;
     if (actions_dev) K.act = actions_dev;
     const int nch = step_chunks(h, h->nchunks);
@@ -1067,6 +1069,7 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
                   uint8_t* trunc_host) {
     FWD(mrp_step_host_wide(h->wide, actions_host, obs_host, reward_host, done_host, trunc_host))
     if (!h || !actions_host) return fail(-1, "mrp_step_host: null argument");
+    h->steps_done += 1;
     const SimConst& K0 = h->K;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
@@ -1380,7 +1383,8 @@ int MRP_API(mrp_get_stats)(mrp_handle* h, double* out_host, int32_t reset_after)
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(-9, "mrp_get_stats: %s", dev_err());
 #endif
     if (D2H(out_host, h->K.stats, sizeof(double) * MRP_N_STATS)) return fail(-9, "mrp_get_stats: D2H failed: %s", dev_err());
-    if (reset_after) DEV_ZERO(h->K.stats, sizeof(double) * MRP_N_STATS);
+    out_host[MRP_STAT_ENV_STEPS] = (double)h->steps_done * (double)h->K.N;  // counted on the host: no per-env atomics
+    if (reset_after) { DEV_ZERO(h->K.stats, sizeof(double) * MRP_N_STATS); h->steps_done = 0; }
     return 0;
 }
 

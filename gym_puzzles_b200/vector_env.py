@@ -58,6 +58,7 @@ class VectorEnv:
         self.truncated = _wrap(torch, b.trunc_dev, (num_envs,), "|b1", h, dev)
         self.stats_tensor = _wrap(torch, b.stats_dev, (abi.N_STATS,), "<f8", h, dev)
         self._step_index = 0
+        self._stats_step0 = 0
         self.terminal_obs = self.episode_return = self.episode_length = None
         self.scaled_epsilon = self.decay_pow = None
 
@@ -191,11 +192,16 @@ class VectorEnv:
     def episode_stats(self, reduce_across_ranks=True, reset=True):
         """Episode statistics accumulated on the device; summed over ranks with one NCCL all-reduce of 8 doubles
         when torch.distributed is initialised (the only collective on this path — SURVEY.md §8e)."""
-        return reduce_stats(self.torch, self.stats_tensor, reduce_across_ranks, reset)
+        out = reduce_stats(self.torch, self.stats_tensor, reduce_across_ranks, reset,
+                           env_steps=(self._step_index - self._stats_step0) * self.num_envs)
+        if reset:
+            self._stats_step0 = self._step_index
+        return out
 
 
-def reduce_stats(torch, stats_tensor, reduce_across_ranks=True, reset=True):
+def reduce_stats(torch, stats_tensor, reduce_across_ranks=True, reset=True, env_steps=0):
     s = stats_tensor.clone()
+    s[abi.STAT_NAMES.index("env_steps")] = float(env_steps)   # counted on the host (no per-env atomics on the device)
     if reset:
         stats_tensor.zero_()
     if reduce_across_ranks:

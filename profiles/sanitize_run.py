@@ -1,0 +1,46 @@
+"""Small program for compute-sanitizer (memcheck) under gpurun: every kernel family once, default and wide build.
+  compute-sanitizer --tool memcheck python profiles/sanitize_run.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+os.environ.setdefault("MRP_CHUNKS_HOST", "3")
+import numpy as np
+import torch
+
+import gym_puzzles_b200 as gp
+from gym_puzzles_b200 import abi
+
+rng = np.random.default_rng(0)
+for env_id, n_agents, N in [("MultiRobotPuzzleHeavy-v0", 0, 1500), ("MultiRobotPuzzle-v0", 0, 700), ("MultiRobotPuzzle-v2", 0, 700),
+                            ("MultiRobotPuzzleHeavy-v2", 5, 300)]:
+    h = abi.Handle(env_id, N, seed=1, n_agents=n_agents, max_episode_steps=12)
+    h.enable_terminal_info()
+    if env_id.endswith("v2"):
+        h.enable_curriculum()
+    h.reset_host()
+    for t in range(30):
+        if t % 2:
+            h.step_host(rng.uniform(-1, 1, (N, h.act_dim)).astype(np.float32))
+        else:
+            h.sample_actions(t)
+            h.step()
+    w = h.get_state()
+    h.set_state(w)
+    h.step()
+    torch.cuda.synchronize()
+    print(env_id, n_agents, h.stats())
+    h.close()
+env = gp.VecNormalize(gp.VectorEnv("MultiRobotPuzzleHeavy-v0", 2000, seed=2, max_episode_steps=10))
+env.venv.enable_terminal_info()
+env.reset()
+for t in range(25):
+    env.venv.sample_actions(t)
+    env.step()
+torch.cuda.synchronize()
+print("vecnorm ok", env.state_dict()["obs_rms.count"])
+venv = gp.SB3VecEnv("MultiRobotPuzzle-v0", 256, seed=3, max_episode_steps=8)
+venv.reset()
+for t in range(20):
+    venv.step(rng.uniform(-1, 1, (256, 6)).astype(np.float32))
+print("sb3 ok")

@@ -150,5 +150,6 @@ def test_chunked_pipeline_is_invariant(monkeypatch):
             assert np.array_equal(x, y)
     assert np.array_equal(ref.get_state(), chk.get_state())
     sr, sc = ref.stats(), chk.stats()
+    assert sr["env_steps"] == 60 * N == sc["env_steps"]
     assert sr["episodes"] > 0 and all(sr[k] == sc[k] for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"))
     assert abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # summation order differs
