@@ -105,14 +105,15 @@ MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
 }
 
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
-MRP_HD void pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+// returns the number of solver constraints of the env (0: no island task was queued for it)
+MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
     Env e(K, sm, ct, env, nullptr, 13);
     // the action row is requested first so that it is in flight while the state words are loaded
     float a[3 * MRP_MAX_AGENTS];
     const float* arow = K.act + env * K.act_dim;
     for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
     e.load();
-    e.pre_phase(a);
+    return e.pre_phase(a);
 }
 
 // phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
@@ -307,9 +308,23 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
     const int64_t loc = loc0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (loc >= loc1) return;
+    const bool valid = loc < loc1;   // every lane of the warp stays for the warp-aggregated list reservation
     const int64_t env = K.env0 + loc;
-    pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    int T = -1;
+    if (valid) T = pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    // envs without solver tasks are final already: k_post handles them while the solver kernels run (post_list)
+    const unsigned free_m = __ballot_sync(0xffffffffu, T == 0), busy_m = __ballot_sync(0xffffffffu, T > 0);
+    const int lane = threadIdx.x & 31;
+    int base_f = 0, base_b = 0;
+    if (lane == 0) {
+        if (free_m) base_f = atomicAdd(&K.cnt[CNT_FREE], __popc(free_m));
+        if (busy_m) base_b = atomicAdd(&K.cnt[CNT_BUSY], __popc(busy_m));
+    }
+    base_f = __shfl_sync(0xffffffffu, base_f, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (T == 0) K.post_list[base_f + __popc(free_m & below)] = (int32_t)env;
+    else if (T > 0) K.post_list[K.nloc - 1 - (base_b + __popc(busy_m & below))] = (int32_t)env;
 }
 
 // Persistent solver kernels.  Every lane owns one task at a time and advances it by one point operation per loop
@@ -397,12 +412,16 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
     }
 }
 
-__global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimConst K) {
+// which = 2: envs [env0, env0 + nloc) in order.  which = 0 / 1: the envs k_pre listed as free of / owning solver tasks
+// (post_list): the free ones do not depend on the solver kernels and run beside them on a second stream.
+__global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimConst K, int which) {
     extern __shared__ float smem[];
-    const float* ct = load_ctab(K, smem);
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (loc >= K.nloc) return;
-    const int64_t env = K.env0 + loc;
+    const int64_t count = which == 2 ? (int64_t)K.nloc : (int64_t)K.cnt[which == 0 ? CNT_FREE : CNT_BUSY];
+    if ((int64_t)blockIdx.x * kBlock >= count) return;
+    const float* ct = load_ctab(K, smem);
+    if (loc >= count) return;
+    const int64_t env = which == 2 ? K.env0 + loc : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
     post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr);
 }
 
@@ -471,7 +490,8 @@ struct mrp_handle {
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cact, cact0, cjoin[kMaxChunks], cpost[kMaxChunks];
+    cudaEvent_t cfork, cact, cact0, cpre, cfree, cjoin[kMaxChunks], cpost[kMaxChunks];
+    int overlap_post;  // mrp_step: k_post of envs without solver tasks runs beside the solver kernels
 #endif
     int64_t launches;
     int64_t steps_done;  // mrp_step / mrp_step_host calls since the statistics were last reset (env_steps = steps_done * N)
@@ -590,6 +610,8 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
         cudaEventDestroy(h->cfork);
         cudaEventDestroy(h->cact);
         cudaEventDestroy(h->cact0);
+        cudaEventDestroy(h->cpre);
+        cudaEventDestroy(h->cfree);
     }
 #else
     free(h->emu_sm);
@@ -609,6 +631,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.task_T);
     DEV_FREE(h->K.task_off);
     DEV_FREE(h->K.toi_list);
+    DEV_FREE(h->K.post_list);
     DEV_FREE(h->K.narrow_list);
     DEV_FREE((void*)h->K.eps_env);
     DEV_FREE((void*)h->K.decay_env);
@@ -688,6 +711,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.task_T, sizeof(int32_t) * kTaskClasses * N * K.nb);
     rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * kTaskClasses * N * K.nb);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.post_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
@@ -743,6 +767,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cact, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cact0, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->cpre, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->cfree, cudaEventDisableTiming);
+    h->overlap_post = getenv("MRP_OVERLAP_POST") ? atoi(getenv("MRP_OVERLAP_POST")) : (cfg->num_envs >= 65536 ? 1 : 0);
     if (check_launch("mrp_create")) { MRP_API(mrp_destroy)(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
@@ -881,6 +908,7 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
     K.toi_list = K0.toi_list + b;
     K.narrow_list = K0.narrow_list + (size_t)b * K0.maxc;
     K.reset_list = K0.reset_list + b;
+    K.post_list = K0.post_list + b;
     (void)h;
     return K;
 }
@@ -919,17 +947,55 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
     h->launches += 6;
 }
+static void launch_front_head(mrp_handle* h, const SimConst& K, cudaStream_t st) {
+    const unsigned grid = grid_for(K.nloc, kBlock);
+    k_clear<<<1, 32, 0, st>>>(K.cnt);
+    k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
+    k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
+    h->launches += 4;
+}
+static void launch_front_solvers(mrp_handle* h, const SimConst& K, cudaStream_t st) {
+    const unsigned grid = grid_for(K.nloc, kBlock);
+    const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
+    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
+    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
+    h->launches += 2;
+}
 static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool clear, cudaEvent_t after_post = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
     const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;  // queue kernels: a few CTAs per SM
     if (clear) { k_clear<<<1, 32, 0, st>>>(K.cnt); h->launches += 1; }
-    k_post<<<grid, kBlock, h->smem_post, st>>>(K);
+    k_post<<<grid, kBlock, h->smem_post, st>>>(K, 2);
     if (after_post) cudaEventRecord(after_post, st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
     k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
     h->launches += 2;
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+    if (K.auto_reset) {
+        k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        h->launches += 1;
+    }
+}
+// Whole-batch step with k_post split by k_pre's lists: envs without solver tasks (~60 %) are final after k_pre, so their
+// k_post runs on a second, low-priority stream beside k_solve_vel / k_solve_pos — kernels whose duration is set by the
+// serial tail of the longest islands, not by throughput — and only the envs with tasks are post-processed afterwards.
+static void launch_overlapped(mrp_handle* h, const SimConst& K, cudaStream_t st) {
+    const unsigned grid = grid_for(K.nloc, kBlock);
+    if (grid == 0) return;
+    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+    cudaStream_t side = h->cstream[kMaxChunks - 1];
+    launch_front_head(h, K, st);
+    cudaEventRecord(h->cpre, st);
+    cudaStreamWaitEvent(side, h->cpre, 0);
+    k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
+    cudaEventRecord(h->cfree, side);
+    launch_front_solvers(h, K, st);
+    k_post<<<grid, kBlock, h->smem_post, st>>>(K, 1);
+    cudaStreamWaitEvent(st, h->cfree, 0);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+    h->launches += 3;
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
@@ -966,7 +1032,11 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
     }
     const int nnarrow = K.cnt[CNT_NARROW];
     for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
-    for (int64_t e = e0; e < e1; ++e) pre_lane(K, h->emu_sm, h->ctab_dev, e);
+    for (int64_t e = e0; e < e1; ++e) {
+        const int T = pre_lane(K, h->emu_sm, h->ctab_dev, e);
+        if (T == 0) K.post_list[K.cnt[CNT_FREE]++] = (int32_t)e;
+        else K.post_list[K.nloc - 1 - K.cnt[CNT_BUSY]++] = (int32_t)e;
+    }
     for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
         const int ntasks = task_count(K, cls);
         for (int i = 0; i < ntasks; ++i) {
@@ -991,10 +1061,15 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
         pos_task_end(K, s, pt);
     }
 }
-static void run_back_emu(mrp_handle* h, const SimConst& K, bool clear) {
+static void run_back_emu(mrp_handle* h, const SimConst& K, bool clear, bool by_lists = false) {
     if (clear) for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
     const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
-    for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
+    if (by_lists) {  // the order of the device's overlapped step: envs without solver tasks first, then the others
+        for (int i = 0; i < K.cnt[CNT_FREE]; ++i) post_lane(K, h->emu_sm, h->ctab_dev, K.post_list[i], false, nullptr);
+        for (int i = 0; i < K.cnt[CNT_BUSY]; ++i) post_lane(K, h->emu_sm, h->ctab_dev, K.post_list[K.nloc - 1 - i], false, nullptr);
+    } else {
+        for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
+    }
     const int ntoi = K.cnt[CNT_TOI];
     for (int i = 0; i < ntoi; ++i) {
         const int64_t env = K.toi_list[i];
@@ -1017,7 +1092,7 @@ static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
         return;
     }
     run_front_emu(h, K);
-    run_back_emu(h, K, false);
+    run_back_emu(h, K, false, true);
 }
 #endif
 
@@ -1045,7 +1120,9 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (nch == 1) {
+    if (nch == 1 && h->overlap_post && !h->timing && !h->fused) {
+        launch_overlapped(h, chunk_const(h, K, 0, 1), st);
+    } else if (nch == 1) {
         launch_pipeline(h, chunk_const(h, K, 0, 1), st, h->timing != 0);
     } else {
         // fork the chunk pipelines off the caller's stream and join them back: stream-ordered like one kernel

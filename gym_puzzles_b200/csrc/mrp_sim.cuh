@@ -146,6 +146,8 @@ struct SimConst {
     int32_t* task_off;    // [..] index of task i's first record in pool
     int32_t* toi_list;    // [N] envs whose TOI scan found an event (handled by k_post_events)
     uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * kMaxC + slot
+    int32_t* post_list;    // [N] envs without solver tasks from slot 0 up, envs with tasks from the last slot down (k_pre):
+                           // k_post of the former runs beside the solver kernels
     // optional per-env curriculum vectors (NULL: the scalar mrp_params apply): update_goal / update_params per env
     const double* eps_env;       // [N] scaled_epsilon   (mrp02:232-233)
     const double* decay_env;     // [N] decay**(-timestep) (mrp02:227-230)
@@ -161,7 +163,7 @@ struct SimConst {
 // Class c owns slots [c*cap, (c+1)*cap), cap = N * nb.
 constexpr int kTaskClasses = 4;
 enum { CNT_RESET = 0, CNT_POOL = 1, CNT_TOI = 2, CNT_NARROW = 3, CNT_HEAD_P = 4, CNT_TASKS = 8 /*[4] heavy*/, CNT_TASKS_LIGHT = 12 /*[4]*/,
-       CNT_HEAD_V = 16 /*[4]*/, CNT_N = 20 };
+       CNT_HEAD_V = 16 /*[4]*/, CNT_FREE = 20 /* envs without solver tasks */, CNT_BUSY = 21 /* envs with tasks */, CNT_N = 22 };
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
