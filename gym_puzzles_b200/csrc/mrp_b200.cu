@@ -189,13 +189,17 @@ MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
 
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
 // false an env whose TOI scan finds an event is queued for the event pass and left untouched.
-MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local) {
+MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local,
+                      bool free_group = false) {
     Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 11);
     e.load();
     double r;
     bool d;
     if (!e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events)) {
-        K.toi_list[atomic_add_i32(&K.cnt[CNT_TOI], 1)] = (int32_t)env;
+        // deferred to the event pass; the task-free group has its own queue (end of toi_list, downwards) so that its
+        // events can be processed beside the solver kernels as well
+        if (free_group) K.toi_list[K.nloc - 1 - atomic_add_i32(&K.cnt[CNT_TOI_F], 1)] = (int32_t)env;
+        else K.toi_list[atomic_add_i32(&K.cnt[CNT_TOI], 1)] = (int32_t)env;
         return;
     }
     finish_step(K, e, env, d, r);
@@ -422,17 +426,17 @@ __global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimC
     const float* ct = load_ctab(K, smem);
     if (loc >= count) return;
     const int64_t env = which == 2 ? K.env0 + loc : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
-    post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr);
+    post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr, which == 0);
 }
 
 // rare paths, grid-stride over their queues: envs with a TOI event this step; envs to auto-reset
-__global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ SimConst K) {
+__global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ SimConst K, int free_group) {
     extern __shared__ float smem[];
-    const int count = K.cnt[CNT_TOI];
+    const int count = K.cnt[free_group ? CNT_TOI_F : CNT_TOI];
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock) {
-        const int64_t env = K.toi_list[i];
+        const int64_t env = K.toi_list[free_group ? K.nloc - 1 - i : i];
         MRP_VC_SCRATCH(K, env);
         post_lane(K, smem + kCtPad + threadIdx.x, ct, env, true, vc_local);
     }
@@ -745,8 +749,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
     cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
-    for (auto fn : {k_step, k_post_events, k_reset_list})
+    for (auto fn : {k_step, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_post_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
     cudaFuncSetAttribute(k_reset_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
@@ -970,7 +975,7 @@ static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 2);
     if (after_post) cudaEventRecord(after_post, st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
-    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
     h->launches += 2;
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     if (K.auto_reset) {
@@ -990,12 +995,13 @@ static void launch_overlapped(mrp_handle* h, const SimConst& K, cudaStream_t st)
     cudaEventRecord(h->cpre, st);
     cudaStreamWaitEvent(side, h->cpre, 0);
     k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, side>>>(K, 1);
     cudaEventRecord(h->cfree, side);
     launch_front_solvers(h, K, st);
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 1);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
     cudaStreamWaitEvent(st, h->cfree, 0);
-    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
-    h->launches += 3;
+    h->launches += 4;
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
@@ -1065,16 +1071,18 @@ static void run_back_emu(mrp_handle* h, const SimConst& K, bool clear, bool by_l
     if (clear) for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
     const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
     if (by_lists) {  // the order of the device's overlapped step: envs without solver tasks first, then the others
-        for (int i = 0; i < K.cnt[CNT_FREE]; ++i) post_lane(K, h->emu_sm, h->ctab_dev, K.post_list[i], false, nullptr);
+        for (int i = 0; i < K.cnt[CNT_FREE]; ++i) post_lane(K, h->emu_sm, h->ctab_dev, K.post_list[i], false, nullptr, true);
         for (int i = 0; i < K.cnt[CNT_BUSY]; ++i) post_lane(K, h->emu_sm, h->ctab_dev, K.post_list[K.nloc - 1 - i], false, nullptr);
     } else {
         for (int64_t e = e0; e < e1; ++e) post_lane(K, h->emu_sm, h->ctab_dev, e, false, nullptr);
     }
-    const int ntoi = K.cnt[CNT_TOI];
-    for (int i = 0; i < ntoi; ++i) {
-        const int64_t env = K.toi_list[i];
-        MRP_VC_SCRATCH(K, env);
-        post_lane(K, h->emu_sm, h->ctab_dev, env, true, vc_local);
+    for (int grp = 1; grp >= 0; --grp) {   // the task-free group's queue first, as on the device
+        const int ntoi = K.cnt[grp ? CNT_TOI_F : CNT_TOI];
+        for (int i = 0; i < ntoi; ++i) {
+            const int64_t env = K.toi_list[grp ? K.nloc - 1 - i : i];
+            MRP_VC_SCRATCH(K, env);
+            post_lane(K, h->emu_sm, h->ctab_dev, env, true, vc_local);
+        }
     }
     if (K.auto_reset) {
         const int nreset = K.cnt[CNT_RESET];

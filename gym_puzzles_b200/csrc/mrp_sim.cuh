@@ -163,7 +163,8 @@ struct SimConst {
 // Class c owns slots [c*cap, (c+1)*cap), cap = N * nb.
 constexpr int kTaskClasses = 4;
 enum { CNT_RESET = 0, CNT_POOL = 1, CNT_TOI = 2, CNT_NARROW = 3, CNT_HEAD_P = 4, CNT_TASKS = 8 /*[4] heavy*/, CNT_TASKS_LIGHT = 12 /*[4]*/,
-       CNT_HEAD_V = 16 /*[4]*/, CNT_FREE = 20 /* envs without solver tasks */, CNT_BUSY = 21 /* envs with tasks */, CNT_N = 22 };
+       CNT_HEAD_V = 16 /*[4]*/, CNT_FREE = 20 /* envs without solver tasks */, CNT_BUSY = 21 /* envs with tasks */,
+       CNT_TOI_F = 22 /* TOI-event queue of the task-free group (filled from the end of toi_list) */, CNT_N = 23 };
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
