@@ -241,8 +241,8 @@ def run_native(args):
                 # scaled from the profiled batch size to this run's
                 # the "k_pre" timer spans the three collide / setup launches k_broad + k_narrow + k_pre
                 recs = json.load(open(tp))
-                names = ["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom]
-                traffic = sum(recs[k]["dram_bytes_per_launch"] * (N / recs[k]["envs"]) for k in names)
+                names = ["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom, dom + "#2"]
+                traffic = sum(recs[k]["dram_bytes_per_launch"] * (N / recs[k]["envs"]) for k in names if k in recs)
             except Exception:
                 traffic = None
         # FP32-issue view of the same kernels (north star: "fraction of the FP32 and HBM roofline"): issue-slot and FMA-pipe
@@ -252,7 +252,7 @@ def run_native(args):
         if os.path.exists(ip):
             try:
                 rec = json.load(open(ip))
-                issue = {k: rec[k] for k in (["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom]) if k in rec}
+                issue = {k: rec[k] for k in (["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom, dom + "#2"]) if k in rec}
             except Exception:
                 issue = None
         line = {

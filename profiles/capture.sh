@@ -6,7 +6,8 @@ TAG=${1:-rX}
 CMD="python profiles/profile_step.py"
 KERNELS='regex:^k_(broad|narrow|pre|solve_vel|solve_pos|post|post_events|reset_list)$'
 $CMD > gpurun_out/plain_$TAG.log 2>&1
-# 1 reset + 64 steps x 8 matching kernels: skip 61 steps
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 488 -c 24 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 504 -c 8 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
+# 64 steps x 10 matching kernels (k_post and k_post_events launch twice per step: the task-free group on the side stream,
+# then the envs with solver tasks): skip 61 steps for the launch list, 63 for the full capture
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 610 -c 30 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 630 -c 10 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
 tail -2 gpurun_out/ncu2_$TAG.log

@@ -28,6 +28,11 @@ def main():
     head, units, data = rows[0], rows[1], rows[2:]
     ki = head.index("Kernel Name")
     names = [r[ki].split("(")[0] for r in data]
+    seen = {}
+    for i, n in enumerate(names):   # k_post / k_post_events launch twice per step: task-free group, then envs with tasks
+        seen[n] = seen.get(n, 0) + 1
+        if seen[n] > 1:
+            names[i] = n + "#%d" % seen[n]
     out = ["| metric | unit | " + " | ".join(names) + " |", "|---|---|" + "---|" * len(names)]
     traffic = {}
     for m in METRICS:
