@@ -11,3 +11,7 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 610 -c 30 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k "$KERNELS" -s 630 -c 10 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
 tail -2 gpurun_out/ncu2_$TAG.log
+# 3) launch list of the bench command itself (short form: 524288 envs, 60 settle + 3 warm-up + 3 timed steps), every launch
+BCMD="python bench.py --steps 3 --warmup 3 --settle 60 --envs 524288 --no-cpu-baseline --e2e-steps 2"
+$BCMD > gpurun_out/plain_bench_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" --csv --log-file gpurun_out/launches_bench_$TAG.csv $BCMD > gpurun_out/ncu3_$TAG.log 2>&1
