@@ -9,12 +9,14 @@ U(-1,1) from the Philox ACTION stream, auto-reset on (BASELINE.json configs[2]; 
 steps applies).  One "step" = one env.step of every env of the batch.
 
   value     whole-job env-steps/s with actions already resident in HBM (pre-generated ring of action buffers),
-            K steps bracketed by barrier + synchronize, CUDA-event timed, max over ranks.
+            K steps bracketed by barrier + synchronize, CUDA-event timed, max over ranks.  Production configuration of
+            mrp_step: library timers off, k_post of the envs without solver tasks on a side stream beside the solvers.
   e2e       the same through mrp_step_host(): pinned HOST action buffer -> H2D, step, obs/reward/done/trunc D2H,
             every step, copies inside the timed region.
   roofline  dominant phase of the step's pipeline (k_broad+k_narrow+k_pre / k_solve_vel / k_solve_pos / k_post / k_post_events):
             algorithmic bytes (513 B per env-step, SURVEY.md §8d / DESIGN.md) over its mean launch time, measured with
-            CUDA events recorded between the kernels inside the library (mrp_set_timing / mrp_get_phase_timing).
+            CUDA events recorded between the kernels inside the library (mrp_set_timing / mrp_get_phase_timing) in a
+            separate pass of K steps (the timers keep every kernel on the launching stream, one after the other).
   cpu_baseline  the oracle ("port": pybox2d is not installable here) on all host cores, bounded sample.
 """
 import argparse

@@ -43,8 +43,35 @@ def compare_states(layout, wa, wb):
     return int_bad, tol_bad, bit_bad, max_rel
 
 
-def rollout_compare(handle, variant, N, T, seed, max_episode_steps=0, n_agents=0, env_id_base=0, nthreads=8, state_every=25):
-    """handle: gym_puzzles_b200.abi.Handle built with the same (variant, N, seed, ...)."""
+def device_stepper(handle):
+    """step(actions) through the device-resident entry point mrp_step (actions uploaded into the library's action
+    buffer, results read back from its device buffers): the path VectorEnv.step and bench.py's `value` use."""
+    import torch
+
+    from gym_puzzles_b200.vector_env import _wrap
+
+    dev = torch.device("cuda", 0)
+    b, N = handle.buffers, handle.num_envs
+    act = _wrap(torch, b.action_dev, (N, handle.act_dim), "<f4", handle, dev)
+    obs = _wrap(torch, b.obs_dev, (N, handle.obs_dim), "<f4", handle, dev)
+    rew = _wrap(torch, b.reward_dev, (N,), "<f4", handle, dev)
+    done = _wrap(torch, b.done_dev, (N,), "|u1", handle, dev)
+    trunc = _wrap(torch, b.trunc_dev, (N,), "|u1", handle, dev)
+
+    def step(a):
+        act.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+        handle.step(None, torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+        return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), trunc.cpu().numpy()
+
+    return step
+
+
+def rollout_compare(handle, variant, N, T, seed, max_episode_steps=0, n_agents=0, env_id_base=0, nthreads=8, state_every=25,
+                    device_path=False):
+    """handle: gym_puzzles_b200.abi.Handle built with the same (variant, N, seed, ...).  device_path: step through
+    mrp_step (device-resident) instead of mrp_step_host."""
+    step_fn = device_stepper(handle) if device_path else handle.step_host
     o = OracleBatch(variant, N, seed=seed, nthreads=nthreads, max_episode_steps=max_episode_steps, n_agents=n_agents,
                     env_id_base=env_id_base)
     rep = dict(steps=0, flag_mismatch=0, done_mismatch=0, obs_not_close=0, obs_not_exact=0, rew_not_close=0,
@@ -54,7 +81,7 @@ def rollout_compare(handle, variant, N, T, seed, max_episode_steps=0, n_agents=0
     for t in range(T):
         a = o.sample_actions(t)
         obs_o, r_o, d_o, t_o = o.step(a)
-        obs_h, r_h, d_h, t_h = handle.step_host(a)
+        obs_h, r_h, d_h, t_h = step_fn(a)
         rep["steps"] += N
         rep["dones"] += int(d_o.sum())
         rep["done_mismatch"] += int((d_o != d_h).sum() + (t_o != t_h).sum())

@@ -110,3 +110,28 @@ def test_v2_more_agents_parity(env_id, n_agents):
     _assert_parity(rep)
     assert rep["dones"] >= N and h.stats()["overflow"] == 0
     h.close()
+
+
+@pytest.mark.parametrize("N", [1, 37, 3001])
+def test_overlapped_post_ragged_sizes(monkeypatch, N):
+    """mrp_step's split k_post (envs without solver tasks beside the solver kernels, lists built by k_pre) with batch
+    sizes that leave partial warps / CTAs; forced on (it is the default only from 65,536 envs)."""
+    monkeypatch.setenv("MRP_OVERLAP_POST", "1")
+    env_id = "MultiRobotPuzzleHeavy-v0"
+    h = abi.Handle(env_id, N, seed=8, max_episode_steps=30)
+    rep = rollout_compare(h, env_id, N, 70, seed=8, max_episode_steps=30, device_path=True)
+    _assert_parity(rep)
+    assert rep["dones"] >= 2 * N
+    h.close()
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_rollout_parity_device_path(env_id):
+    """the same rollout parity through mrp_step (device-resident; what VectorEnv.step and bench.py's `value` run),
+    large enough for the default overlapped k_post"""
+    N, T = 65536 + 777, 45
+    h = abi.Handle(env_id, N, seed=19, max_episode_steps=20)
+    rep = rollout_compare(h, env_id, N, T, seed=19, max_episode_steps=20, device_path=True, nthreads=16)
+    _assert_parity(rep)
+    assert rep["dones"] >= 2 * N
+    h.close()
