@@ -334,9 +334,12 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
 // Persistent solver kernels.  Every lane owns one task at a time and advances it by one point operation per loop
 // trip; a warp refills its idle lanes from the global task queue once kRefill of them are idle, so the 32 lanes
 // stay busy although islands need anywhere between 2 and ~1000 operations.
-constexpr int kRefill = 8;
+#ifndef MRP_REFILL
+#define MRP_REFILL 8
+#endif
+constexpr int kRefill = MRP_REFILL;
 #ifndef MRP_INNER_TRIPS
-#define MRP_INNER_TRIPS 4
+#define MRP_INNER_TRIPS 8
 #endif
 constexpr int kInnerTrips = MRP_INNER_TRIPS;
 
