@@ -34,3 +34,29 @@ def host_buffers(h, term, n_envs, device):
     gather = lambda idx: (t_obs[idx].copy(), t_ret[idx].copy(), t_len[idx].copy())  # noqa: E731
     return (t_obs, t_ret, t_len, gather, np.empty((n_envs, h.obs_dim), np.float32), np.empty(n_envs, np.float32),
             np.empty(n_envs, np.uint8), np.empty(n_envs, np.uint8), np.empty((n_envs, h.act_dim), np.float32))
+
+
+def emu_device_stepper(handle):
+    """step(actions) through mrp_step of the host build (its "device" buffers are host memory): exercises the code path of
+    the device-resident entry point (task-free / task-owning k_post groups and their TOI queues) on the CPU."""
+    import ctypes as C
+
+    import numpy as np
+
+    b, N = handle.buffers, handle.num_envs
+
+    def view(p, shape, ct, dt):
+        return np.frombuffer((ct * int(np.prod(shape))).from_address(p), dtype=dt).reshape(shape)
+
+    act = view(b.action_dev, (N, handle.act_dim), C.c_float, np.float32)
+    obs = view(b.obs_dev, (N, handle.obs_dim), C.c_float, np.float32)
+    rew = view(b.reward_dev, (N,), C.c_float, np.float32)
+    done = view(b.done_dev, (N,), C.c_uint8, np.uint8)
+    trunc = view(b.trunc_dev, (N,), C.c_uint8, np.uint8)
+
+    def step(a):
+        act[...] = a
+        handle.step()
+        return obs.copy(), rew.copy(), done.copy(), trunc.copy()
+
+    return step

@@ -68,10 +68,11 @@ def device_stepper(handle):
 
 
 def rollout_compare(handle, variant, N, T, seed, max_episode_steps=0, n_agents=0, env_id_base=0, nthreads=8, state_every=25,
-                    device_path=False):
+                    device_path=False, step_fn=None):
     """handle: gym_puzzles_b200.abi.Handle built with the same (variant, N, seed, ...).  device_path: step through
     mrp_step (device-resident) instead of mrp_step_host."""
-    step_fn = device_stepper(handle) if device_path else handle.step_host
+    if step_fn is None:
+        step_fn = device_stepper(handle) if device_path else handle.step_host
     o = OracleBatch(variant, N, seed=seed, nthreads=nthreads, max_episode_steps=max_episode_steps, n_agents=n_agents,
                     env_id_base=env_id_base)
     rep = dict(steps=0, flag_mismatch=0, done_mismatch=0, obs_not_close=0, obs_not_exact=0, rew_not_close=0,

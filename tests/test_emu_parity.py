@@ -6,7 +6,7 @@ bit for bit; the `-m gpu` tests repeat this on the real device through the produ
 import numpy as np
 import pytest
 
-from emu_lib import emu_lib
+from emu_lib import emu_device_stepper, emu_lib
 from gym_puzzles_b200 import abi
 from oracle_lib import OracleBatch
 from parity_util import rollout_compare, single_step_compare
@@ -153,3 +153,14 @@ def test_chunked_pipeline_is_invariant(monkeypatch):
     assert sr["env_steps"] == 60 * N == sc["env_steps"]
     assert sr["episodes"] > 0 and all(sr[k] == sc[k] for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"))
     assert abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # summation order differs
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_rollout_bit_exact_through_mrp_step(variant):
+    """the device-resident entry point: k_post in two groups (envs without / with solver tasks), separate TOI queues"""
+    N, T, cap = 200, 90, 30
+    h = abi.Handle(variant, N, seed=41, max_episode_steps=cap, lib=emu_lib())
+    rep = rollout_compare(h, variant, N, T, seed=41, max_episode_steps=cap, nthreads=4, step_fn=emu_device_stepper(h))
+    _exact(rep)
+    assert rep["dones"] >= 2 * N
+    h.close()
