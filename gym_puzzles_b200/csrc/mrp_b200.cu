@@ -348,6 +348,8 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
     const int ntasks = task_count(K, CLS);
     VelTask vt;
     Sim::VelReg st1;  // second contact (class 2 only)
+    float imp3[CLS == 3 ? 4 * kMaxC : 4];   // class 3: the island's accumulated impulses while it iterates
+    float* const imp = CLS == 3 ? imp3 : nullptr;
     bool busy = false, exhausted = false;
     for (;;) {
         const unsigned bm = __ballot_sync(0xffffffffu, busy);
@@ -356,7 +358,7 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_V + CLS], 1);
                 if (task < ntasks) {
                     vel_task_begin(K, s, vt, task_slot(K, CLS, task));
-                    if (CLS == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
+                    if (CLS == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T, imp);
                     busy = true;
                 } else exhausted = true;
             }
@@ -371,7 +373,7 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
                 if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
                 else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
                 else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
-                else { vt.ops += (uint32_t)vt.st.vpc + 1u; fin = s.vr_trip_contact(vt.st, 180); }
+                else { vt.ops += (uint32_t)vt.st.vpc + 1u; fin = s.vr_trip_contact(vt.st, 180, imp); }
             }
             if (fin) {
                 vel_task_end(K, s, vt);
@@ -1053,11 +1055,13 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
             VelTask vt;
             Sim::VelReg st1;
             vel_task_begin(K, s, vt, task_slot(K, cls, i));
-            if (cls == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T);
+            float imp3[4 * kMaxC];
+            float* const imp = cls == 3 ? imp3 : nullptr;
+            if (cls == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T, imp);
             if (cls == 0) { while (vt.ops += 2, !s.vr_sweep_single<1>(vt.st, 180)) {} }
             else if (cls == 1) { while (vt.ops += 3, !s.vr_sweep_single<2>(vt.st, 180)) {} }
             else if (cls == 2) { while (vt.ops += 5, !s.vr_sweep_pair(vt.st, st1, 180)) {} }
-            else { while (vt.ops += (uint32_t)vt.st.vpc + 1u, !s.vr_trip_contact(vt.st, 180)) {} }
+            else { while (vt.ops += (uint32_t)vt.st.vpc + 1u, !s.vr_trip_contact(vt.st, 180, imp)) {} }
             vel_task_end(K, s, vt);
         }
     }

@@ -836,8 +836,9 @@ struct Sim {
             return;
         }
         VelReg r;  // larger islands: one contact per trip, the current constraint record in registers
-        vr_begin(r, T);
-        while (!vr_trip_contact(r, iters)) {}
+        float imp[4 * kMaxC];
+        vr_begin(r, T, imp);
+        while (!vr_trip_contact(r, iters, imp)) {}
     }
     // ---- register-resident form of the velocity solve (solver kernel): the current contact's constraint record and
     // the velocities of its two bodies live in registers while its point operations run; they are exchanged with
@@ -853,7 +854,9 @@ struct Sim {
         V2 vA, vB;
         float wA, wB;
     };
-    MRP_HD void vr_load(VelReg& r) {
+    // imp != NULL: the accumulated impulses of the island live in a lane-local array during the sweeps (vr_imp_*), so the
+    // constraint records are read-only while the island iterates and stay resident in L1
+    MRP_HD void vr_load(VelReg& r, const float* imp = nullptr) {
         const float* C = &V(r.t, 0);
         const uint32_t vm = __float_as_uint_(C[VC_META]);
         r.bA = vm & 15; r.bB = (vm >> 4) & 15; r.vpc = (vm >> 8) & 3;
@@ -861,9 +864,11 @@ struct Sim {
         r.fric = C[VC_FRIC];
         r.n = mk(C[VC_NX], C[VC_NY]);
         r.rA0 = mk(C[VC_PT + 0], C[VC_PT + 1]); r.rB0 = mk(C[VC_PT + 2], C[VC_PT + 3]);
-        r.nM0 = C[VC_PT + 4]; r.tM0 = C[VC_PT + 5]; r.nI0 = C[VC_PT + 6]; r.tI0 = C[VC_PT + 7];
+        r.nM0 = C[VC_PT + 4]; r.tM0 = C[VC_PT + 5];
         r.rA1 = mk(C[VC_PT + 8], C[VC_PT + 9]); r.rB1 = mk(C[VC_PT + 10], C[VC_PT + 11]);
-        r.nM1 = C[VC_PT + 12]; r.tM1 = C[VC_PT + 13]; r.nI1 = C[VC_PT + 14]; r.tI1 = C[VC_PT + 15];
+        r.nM1 = C[VC_PT + 12]; r.tM1 = C[VC_PT + 13];
+        if (imp) { const float* I = imp + 4 * r.t; r.nI0 = I[0]; r.tI0 = I[1]; r.nI1 = I[2]; r.tI1 = I[3]; }
+        else { r.nI0 = C[VC_PT + 6]; r.tI0 = C[VC_PT + 7]; r.nI1 = C[VC_PT + 14]; r.tI1 = C[VC_PT + 15]; }
         r.k11 = C[VC_K11]; r.k12 = C[VC_K12]; r.k22 = C[VC_K22];
         r.m11 = C[VC_M11]; r.m12 = C[VC_M12]; r.m22 = C[VC_M22];
         vr_load_vel(r);
@@ -880,17 +885,28 @@ struct Sim {
         pA[3 * MRP_SS] = r.vA.x; pA[4 * MRP_SS] = r.vA.y; pA[5 * MRP_SS] = r.wA;
         pB[3 * MRP_SS] = r.vB.x; pB[4 * MRP_SS] = r.vB.y; pB[5 * MRP_SS] = r.wB;
     }
-    MRP_HD void vr_store(const VelReg& r) {
-        float* C = &V(r.t, 0);
-        C[VC_PT + 6] = r.nI0; C[VC_PT + 7] = r.tI0; C[VC_PT + 14] = r.nI1; C[VC_PT + 15] = r.tI1;
+    MRP_HD void vr_store(const VelReg& r, float* imp = nullptr) {
+        if (imp) { float* I = imp + 4 * r.t; I[0] = r.nI0; I[1] = r.tI0; I[2] = r.nI1; I[3] = r.tI1; }
+        else { float* C = &V(r.t, 0); C[VC_PT + 6] = r.nI0; C[VC_PT + 7] = r.tI0; C[VC_PT + 14] = r.nI1; C[VC_PT + 15] = r.tI1; }
         float* pA = bp(r.bA);
         float* pB = bp(r.bB);
         pA[3 * MRP_SS] = r.vA.x; pA[4 * MRP_SS] = r.vA.y; pA[5 * MRP_SS] = r.wA;
         pB[3 * MRP_SS] = r.vB.x; pB[4 * MRP_SS] = r.vB.y; pB[5 * MRP_SS] = r.wB;
     }
-    MRP_HD void vr_begin(VelReg& r, int T) {
+    MRP_HD void vr_begin(VelReg& r, int T, float* imp = nullptr) {
         r.T = T; r.t = 0; r.j = 0; r.sweep = 0; r.changed = false;
-        vr_load(r);
+        if (imp)   // records -> lane-local impulses
+            for (int t = 0; t < T; ++t) {
+                const float* C = &V(t, 0);
+                imp[4 * t] = C[VC_PT + 6]; imp[4 * t + 1] = C[VC_PT + 7]; imp[4 * t + 2] = C[VC_PT + 14]; imp[4 * t + 3] = C[VC_PT + 15];
+            }
+        vr_load(r, imp);
+    }
+    MRP_HD void vr_imp_flush(const float* imp, int T) {  // lane-local impulses -> records (StoreImpulses reads them there)
+        for (int t = 0; t < T; ++t) {
+            float* C = &V(t, 0);
+            C[VC_PT + 6] = imp[4 * t]; C[VC_PT + 7] = imp[4 * t + 1]; C[VC_PT + 14] = imp[4 * t + 2]; C[VC_PT + 15] = imp[4 * t + 3];
+        }
     }
     // one point operation; returns true when the solve is finished (everything written back)
     // the two kinds of point operation on the register-resident contact
@@ -958,19 +974,20 @@ struct Sim {
     // generic form for the persistent solver: one whole CONTACT per trip (friction points, then the normal point or the
     // block solve — Box2D's order), so lanes of a warp only diverge between 1- and 2-point manifolds instead of
     // between four kinds of point operation, and the per-trip bookkeeping is paid once per contact
-    MRP_HD bool vr_trip_contact(VelReg& r, int iters) {
+    MRP_HD bool vr_trip_contact(VelReg& r, int iters, float* imp = nullptr) {
         vr_contact_ops(r);
         bool wrapped = true;
         if (r.T > 1) {
-            vr_store(r);
+            vr_store(r, imp);
             wrapped = ++r.t == r.T;
             if (wrapped) r.t = 0;
-            vr_load(r);
+            vr_load(r, imp);
         }
         if (wrapped) {
             ++r.sweep;
             if (!r.changed || r.sweep == iters) {
                 if (r.T == 1) vr_store(r);
+                else if (imp) vr_imp_flush(imp, r.T);
                 return true;
             }
             r.changed = false;
