@@ -1,6 +1,8 @@
 // Micro-benchmark (run under gpurun): how fast can a kernel write scattered 160-byte result rows straight into pinned
 // host memory (zero-copy stores over PCIe), compared with cudaMemcpyAsync of the same rows as one contiguous range?
 // Decides whether mrp_step_host can stream the rows of task-free envs out while the solver kernels still run.
+// Outcome (B200 box, PCIe gen5): memcpy 53.9 GB/s, zero-copy 52.6 GB/s contiguous / 47 GB/s for a random 60 % of the rows;
+// inside the step it lost all the same (measured dead ends).
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/zc profiles/micro/zerocopy_rows.cu && /tmp/zc
 #include <cstdio>
 #include <cstdlib>
