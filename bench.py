@@ -257,6 +257,20 @@ def run_native(args):
                 issue = {k: rec[k] for k in (["k_broad", "k_narrow", "k_pre"] if dom == "k_pre" else [dom, dom + "#2"]) if k in rec}
             except Exception:
                 issue = None
+        # Lane-issue roofline of the whole step: thread-level instructions per env-step (warp instructions x active lanes per
+        # instruction of every kernel, from the committed ncu capture) x this run's env-steps/s, against
+        # 148 SMs x 4 schedulers x 32 lanes x the SM clock sampled during the timed region.
+        lane_issue = None
+        try:
+            rec = json.load(open(ip))
+            tinst = sum(r["warp_inst_per_launch"] * r["active_lanes_per_inst"] / r["envs"] for r in rec.values())
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_ti = 148 * 4 * 32 * mhz * 1e6
+            ach_ti = tinst * N / (k_mean_ms / 1e3) if k_mean_ms > 0 else None
+            lane_issue = {"thread_inst_per_env_step": tinst, "achieved": ach_ti, "peak": peak_ti, "unit": "thread-inst/s",
+                          "frac": ach_ti / peak_ti if ach_ti else None, "sm_mhz": mhz}
+        except Exception:
+            lane_issue = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,7 +286,7 @@ def run_native(args):
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "k_broad+k_narrow+k_pre" if dom == "k_pre" else dom, "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / k_mean_ms if k_mean_ms else None,
                          "kernels_ms": per_kernel, "pipeline_ms": k_mean_ms, "pipeline_achieved": pipeline_gbs,
-                         "fp32_issue_from_ncu": issue,
+                         "fp32_issue_from_ncu": issue, "lane_issue": lane_issue,
                          "note": "path is FP32-issue/latency bound by nature (SURVEY.md §8d): HBM fraction is expected << 1"},
             "episode_stats": {k: stats[k] for k in ("episodes", "done_by_env", "truncated", "mean_return", "mean_length", "overflow")},
         }

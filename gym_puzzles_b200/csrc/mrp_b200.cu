@@ -929,7 +929,7 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
 // back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
 // events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
 static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready,
-                         cudaEvent_t first_half_ready = nullptr, int64_t half = 0) {
+                         cudaEvent_t first_half_ready = nullptr, int64_t half = 0, cudaEvent_t* tr = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
     const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
@@ -940,9 +940,11 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     }
     k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
     k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    if (tr) cudaEventRecord(tr[20], st);
     if (first_half_ready && half > 0 && half < K.nloc) {
         cudaStreamWaitEvent(st, first_half_ready, 0);
         k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half);
+        if (tr) cudaEventRecord(tr[21], st);
         cudaStreamWaitEvent(st, actions_ready, 0);
         k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, st>>>(K, half, K.nloc);
         h->launches += 1;
@@ -950,6 +952,7 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
         if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
         k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
     }
+    if (tr) cudaEventRecord(tr[22], st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
     k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
     if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
@@ -1199,7 +1202,7 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
         launch_pipeline(h, chunk_const(h, K0, 0, 1), s_front, h->timing != 0);
         copy_out(s_front, 0, N);
     } else {
-        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half);
+        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half, trace ? tr : nullptr);
         cudaEventRecord(h->cjoin[0], s_front);
         if (trace) cudaEventRecord(tr[2], s_front);
         for (int c = 0; c < nch; ++c) {
@@ -1224,6 +1227,9 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     if (trace && nch > 1) {
         float ms;
         cudaEventElapsedTime(&ms, tr[0], tr[1]); printf("h2d_done %.2f", ms);
+        cudaEventElapsedTime(&ms, tr[0], tr[20]); printf(" narrow_done %.2f", ms);
+        cudaEventElapsedTime(&ms, tr[0], tr[21]); printf(" pre0_done %.2f", ms);
+        cudaEventElapsedTime(&ms, tr[0], tr[22]); printf(" pre_done %.2f", ms);
         cudaEventElapsedTime(&ms, tr[0], tr[2]); printf(" front_done %.2f", ms);
         for (int c = 0; c < nch; ++c) { cudaEventElapsedTime(&ms, tr[0], tr[3 + 2 * c]); printf(" | back%d %.2f", c, ms); cudaEventElapsedTime(&ms, tr[0], tr[4 + 2 * c]); printf(" d2h%d %.2f", c, ms); }
         printf("\n");

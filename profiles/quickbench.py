@@ -42,8 +42,9 @@ def run(env_id, N, settle=100, K=20, n_agents=0):
         A, O = h.act_dim, h.obs_dim
         pin = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt).pin_memory().numpy()
         acts = [pin(N, A) for _ in range(4)]
+        rng = np.random.default_rng(0)   # a different batch per buffer: constant actions would be a heavier workload (steady pushing)
         for a in acts:
-            a[:] = np.random.default_rng(0).uniform(-1, 1, a.shape)
+            a[:] = rng.uniform(-1, 1, a.shape)
         out = (pin(N, O), pin(N), pin(N, dt=torch.uint8), pin(N, dt=torch.uint8))
         h.step_host(acts[0], *out)
         torch.cuda.synchronize()
