@@ -456,6 +456,25 @@ __global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ S
         reset_lane(K, smem + kCtPad + threadIdx.x, ct, K.reset_list[i]);
 }
 
+// mrp_step_host with a pinned, device-visible obs buffer: the rows of a chunk leave by cudaMemcpyAsync as soon as its k_post
+// has finished, i.e. before the chunk's TOI-event and auto-reset passes (a serial tail of ~0.4 ms that touches ~3 % of the
+// envs); the rows those two passes rewrite are then stored straight into the host buffer by this kernel (zero-copy stores
+// over PCIe: 47 GB/s for scattered rows, profiles/micro/zerocopy_rows.cu), ordered after the bulk copy of the same range.
+// which 0: the chunk's TOI-event queue, 1: its auto-reset queue.  V = float4 when the row length allows it, else float.
+template <typename V>
+__global__ void __launch_bounds__(256) k_out_rows(const __grid_constant__ SimConst K, int which, V* __restrict__ obs_host) {
+    const int64_t count = K.cnt[which == 0 ? CNT_TOI : CNT_RESET];
+    const int32_t* list = which == 0 ? K.toi_list : K.reset_list;
+    const int q = K.obs_dim / (int)(sizeof(V) / sizeof(float));   // elements per row
+    const int64_t total = count * q;
+    const V* src = reinterpret_cast<const V*>(K.obs);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q;
+        const int64_t at = (int64_t)list[r] * q + (i - r * q);
+        obs_host[at] = src[at];
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
@@ -499,7 +518,11 @@ struct mrp_handle {
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cact, cact0, cpre, cfree, cjoin[kMaxChunks], cpost[kMaxChunks];
+    cudaEvent_t cfork, cact, cact0, cpre, cfree, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks];
+    cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
+    int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
+    const void* zc_host;       // last obs_host pointer checked for device visibility ...
+    float* zc_dev;             // ... and its device alias (nullptr: not pinned / not mapped -> rows leave after the passes)
     int overlap_post;  // mrp_step: k_post of envs without solver tasks runs beside the solver kernels
 #endif
     int64_t launches;
@@ -615,7 +638,8 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     cudaSetDevice(h->device);
     if (h->timing) MRP_API(mrp_set_timing)(h, 0);
     if (h->cfork) {
-        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); }
+        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); }
+        cudaStreamDestroy(h->copy_stream);
         cudaEventDestroy(h->cfork);
         cudaEventDestroy(h->cact);
         cudaEventDestroy(h->cact0);
@@ -772,7 +796,10 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
             cudaStreamCreateWithPriority(&h->cstream[c], cudaStreamNonBlocking, pr);
             cudaEventCreateWithFlags(&h->cjoin[c], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&h->cpost[c], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->cd2h[c], cudaEventDisableTiming);
         }
+        cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi);
+        h->host_early_copy = getenv("MRP_HOST_EARLY_COPY") ? atoi(getenv("MRP_HOST_EARLY_COPY")) : 1;
     }
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cact, cudaEventDisableTiming);
@@ -1205,10 +1232,44 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
         launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half, trace ? tr : nullptr);
         cudaEventRecord(h->cjoin[0], s_front);
         if (trace) cudaEventRecord(tr[2], s_front);
+        // pinned obs buffer the device can address: early bulk copy + zero-copy fix-up of the rewritten rows
+        float* obs_zc = nullptr;
+        if (obs_host && h->host_early_copy) {
+            if (h->zc_host != (const void*)obs_host) {
+                cudaPointerAttributes pa;
+                h->zc_host = obs_host;
+                h->zc_dev = nullptr;
+                if (cudaPointerGetAttributes(&pa, obs_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+                    ((uintptr_t)pa.devicePointer & 15) == 0)
+                    h->zc_dev = (float*)pa.devicePointer;
+                cudaGetLastError();
+            }
+            obs_zc = h->zc_dev;
+        }
         for (int c = 0; c < nch; ++c) {
             const SimConst K = back_chunk_const(h, K0, c, nch);
             if (K.nloc == 0) continue;
             cudaStream_t st = h->cstream[c];
+            if (obs_zc) {
+                cudaStreamWaitEvent(st, c > 0 ? h->cpost[c - 1] : h->cjoin[0], 0);
+                launch_back(h, K, st, false, true, h->cpost[c]);
+                if (trace) cudaEventRecord(tr[3 + 2 * c], st);
+                const size_t b = (size_t)K.env0, n = (size_t)K.nloc;
+                cudaStreamWaitEvent(h->copy_stream, h->cpost[c], 0);
+                cudaMemcpyAsync(obs_host + b * K0.obs_dim, K0.obs + b * K0.obs_dim, sizeof(float) * n * K0.obs_dim, cudaMemcpyDeviceToHost, h->copy_stream);
+                cudaEventRecord(h->cd2h[c], h->copy_stream);
+                cudaStreamWaitEvent(st, h->cd2h[c], 0);
+                for (int which = 0; which < (K.auto_reset ? 2 : 1); ++which) {
+                    if (K0.obs_dim % 4 == 0) k_out_rows<float4><<<16, 256, 0, st>>>(K, which, reinterpret_cast<float4*>(obs_zc));
+                    else k_out_rows<float><<<16, 256, 0, st>>>(K, which, obs_zc);
+                    h->launches += 1;
+                }
+                if (reward_host) cudaMemcpyAsync(reward_host + b, K0.rew + b, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+                if (done_host) cudaMemcpyAsync(done_host + b, K0.done + b, n, cudaMemcpyDeviceToHost, st);
+                if (trunc_host) cudaMemcpyAsync(trunc_host + b, K0.trunc + b, n, cudaMemcpyDeviceToHost, st);
+                if (trace) cudaEventRecord(tr[4 + 2 * c], st);
+                continue;
+            }
             // k_post of chunk c starts when k_post of chunk c-1 has finished: at that moment the (higher-priority, large
             // shared memory) TOI-event and reset kernels of chunk c-1 get the draining SMs first, and chunk c's k_post
             // fills the rest.  Launched all at once, the k_post CTAs of later chunks would keep re-occupying the SMs and

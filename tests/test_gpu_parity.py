@@ -125,6 +125,39 @@ def test_overlapped_post_ragged_sizes(monkeypatch, N):
     h.close()
 
 
+@pytest.mark.parametrize("env_id,N", [("MultiRobotPuzzleHeavy-v0", 8192 + 300), ("MultiRobotPuzzleHeavy-v0", 1100),
+                                      ("MultiRobotPuzzle-v0", 3001), ("MultiRobotPuzzleHeavy-v2", 3001)])
+def test_host_step_early_copy_with_pinned_buffers(monkeypatch, env_id, N):
+    """mrp_step_host with a pinned obs buffer copies a chunk's rows before its TOI-event / auto-reset passes and lets a
+    kernel store the rows those passes rewrite straight into the host buffer: same results as the plain order (pageable
+    buffers, or MRP_HOST_EARLY_COPY=0)."""
+    import torch
+
+    monkeypatch.setenv("MRP_CHUNKS_HOST", "8")
+    monkeypatch.setenv("MRP_HOST_EARLY_COPY", "0")
+    ref = abi.Handle(env_id, N, seed=4, max_episode_steps=25)
+    monkeypatch.setenv("MRP_HOST_EARLY_COPY", "1")
+    chk = abi.Handle(env_id, N, seed=4, max_episode_steps=25)
+    assert np.array_equal(ref.reset_host(), chk.reset_host())
+    pin = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt).pin_memory().numpy()  # noqa: E731
+    out = (pin(N, ref.obs_dim), pin(N), pin(N, dt=torch.uint8), pin(N, dt=torch.uint8))
+    rng = np.random.default_rng(2)
+    l_ref, l_chk = ref.launch_count, chk.launch_count
+    dones = 0
+    for t in range(80):
+        act = rng.uniform(-1, 1, (N, ref.act_dim)).astype(np.float32)
+        out[0][:] = np.nan   # every row must be rewritten by this step
+        r = ref.step_host(act, *[np.empty_like(o) for o in out]) if t % 2 else ref.step_host(act)
+        chk.step_host(act, *out)
+        for x, y in zip(r, out):
+            assert np.array_equal(x, y)
+        dones += int(r[2].sum())
+    assert dones >= 2 * N   # auto-reset rows were exercised
+    assert np.array_equal(ref.get_state(), chk.get_state())
+    assert (chk.launch_count - l_chk) > (ref.launch_count - l_ref)   # the row fix-up kernels ran
+    ref.close(); chk.close()
+
+
 @pytest.mark.parametrize("env_id", IDS)
 def test_rollout_parity_device_path(env_id):
     """the same rollout parity through mrp_step (device-resident; what VectorEnv.step and bench.py's `value` run),
