@@ -92,7 +92,9 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream);
 
 /* Host-buffer convenience forms (what a non-CUDA-aware caller of the reference would use):
  * H2D copy of actions, step, D2H copies of the results, then a stream synchronise.
- * Any output pointer may be NULL. */
+ * Any output pointer may be NULL.  Pinned (page-locked, device-visible) buffers make the copies overlap the kernels;
+ * with a pinned obs buffer the rows of a chunk of envs leave before that chunk's TOI-event / auto-reset passes and the
+ * few rows those passes rewrite are stored into the buffer by a kernel.  Pageable buffers work, more slowly. */
 int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host,
                   uint8_t* done_host, uint8_t* trunc_host);
 int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host);
