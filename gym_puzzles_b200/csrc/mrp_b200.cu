@@ -969,11 +969,18 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
     if (tr) cudaEventRecord(tr[20], st);
     if (first_half_ready && half > 0 && half < K.nloc) {
+        // the second half runs on another stream, beside the draining CTAs of the first (two launches in a row on one
+        // stream would pay the partial last wave twice)
+        cudaStream_t s2 = h->cstream[1];
+        cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(st, first_half_ready, 0);
         k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half);
         if (tr) cudaEventRecord(tr[21], st);
-        cudaStreamWaitEvent(st, actions_ready, 0);
-        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, st>>>(K, half, K.nloc);
+        cudaStreamWaitEvent(s2, h->cpre, 0);
+        cudaStreamWaitEvent(s2, actions_ready, 0);
+        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, s2>>>(K, half, K.nloc);
+        cudaEventRecord(h->cfree, s2);
+        cudaStreamWaitEvent(st, h->cfree, 0);
         h->launches += 1;
     } else {
         if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
