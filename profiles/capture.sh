@@ -4,6 +4,8 @@
 set -e
 TAG=${1:-rX}
 CMD="python profiles/profile_step.py"
+# k_out_rows (row fix-up of mrp_step_host with pinned buffers, a few microseconds) is left out so that the per-step skip counts
+# below stay aligned with the 10 kernels of a device-resident step
 KERNELS='regex:^k_(broad|narrow|pre|solve_vel|solve_pos|post|post_events|reset_list)$'
 $CMD > gpurun_out/plain_$TAG.log 2>&1
 # 64 steps x 10 matching kernels (k_post and k_post_events launch twice per step: the task-free group on the side stream,
