@@ -1,0 +1,58 @@
+"""Error behaviour of the C-ABI (include/mrp_b200.h: "no exceptions across the ABI", status < 0 + mrp_last_error), checked
+through the host build of the same source.  The reference raises Python exceptions / Box2D asserts in these situations
+("Ownership / errors")."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from emu_lib import emu_lib
+
+from gym_puzzles_b200 import abi
+
+
+@pytest.mark.parametrize("n", [0, -3])
+def test_create_rejects_empty_batches(n):
+    with pytest.raises(abi.MrpError, match="num_envs must be > 0"):
+        abi.Handle("MultiRobotPuzzle-v0", n, seed=1, lib=emu_lib())
+
+
+def test_create_rejects_unsupported_robot_counts():
+    with pytest.raises(abi.MrpError, match="n_agents"):
+        abi.Handle("MultiRobotPuzzle-v2", 4, seed=1, lib=emu_lib(), n_agents=9)
+
+
+def test_create_rejects_unknown_variant_and_null_arguments():
+    lib = emu_lib()
+    cfg = abi.Config()
+    cfg.variant, cfg.num_envs = 17, 4
+    out = C.c_void_p()
+    assert lib.lib.mrp_create(C.byref(cfg), C.byref(out)) < 0 and not out.value
+    assert b"variant" in lib.lib.mrp_last_error()
+    assert lib.lib.mrp_create(None, C.byref(out)) < 0
+    assert lib.lib.mrp_step(None, None, None) < 0 and b"null" in lib.lib.mrp_last_error()
+    assert lib.lib.mrp_step_host(None, None, None, None, None, None) < 0
+
+
+def test_step_host_checks_the_action_shape_and_accepts_missing_outputs():
+    h = abi.Handle("MultiRobotPuzzle-v0", 3, seed=1, lib=emu_lib())
+    h.reset_host()
+    with pytest.raises(ValueError):
+        h.step_host(np.zeros((2, 6), np.float32))
+    # any output pointer may be NULL (header): only the action pointer is required
+    a = np.zeros((3, 6), np.float32)
+    assert h.lib.lib.mrp_step_host(h.h, a.ctypes.data_as(C.c_void_p), None, None, None, None) == 0
+    assert h.lib.lib.mrp_step_host(h.h, None, None, None, None, None) < 0
+    h.close()
+
+
+def test_actions_outside_the_box_are_not_clipped():
+    """the reference does not clip actions: a larger action gives a larger commanded velocity"""
+    h1 = abi.Handle("MultiRobotPuzzle-v0", 1, seed=3, lib=emu_lib())
+    h2 = abi.Handle("MultiRobotPuzzle-v0", 1, seed=3, lib=emu_lib())
+    assert np.array_equal(h1.reset_host(), h2.reset_host())
+    a = np.zeros((1, 6), np.float32)
+    a[0, 0] = 1.0
+    o1 = h1.step_host(a)[0]
+    o2 = h2.step_host(3.0 * a)[0]
+    assert not np.array_equal(o1, o2) and np.isfinite(o2).all()
+    h1.close(); h2.close()
