@@ -10,11 +10,15 @@ Public surface:
 """
 from .abi import MrpError, VARIANTS  # noqa: F401
 from .envs import MultiRobotPuzzle, MultiRobotPuzzle2, MultiRobotPuzzleHeavy, MultiRobotPuzzleHeavy2  # noqa: F401
-from .registry import make, registry, spec  # noqa: F401
+from .registry import make, register_with_gym, registry, spec  # noqa: F401
 from .vector_env import VectorEnv, shard_range  # noqa: F401
 from .sb3_vec_env import SB3VecEnv  # noqa: F401
 from .vec_normalize import VecNormalize  # noqa: F401
 from . import render  # noqa: F401
 
-__all__ = ["make", "spec", "registry", "VectorEnv", "shard_range", "MultiRobotPuzzle", "MultiRobotPuzzleHeavy",
+# the reference registers its ids with gym on import (gym_puzzles/__init__.py:3-29): do the same where gym / gymnasium
+# is installed, so that gym.make("MultiRobotPuzzleHeavy-v0") resolves to this package after `import gym_puzzles_b200`
+GYM_REGISTERED = register_with_gym()
+
+__all__ = ["make", "spec", "registry", "register_with_gym", "VectorEnv", "shard_range", "MultiRobotPuzzle", "MultiRobotPuzzleHeavy",
            "MultiRobotPuzzle2", "MultiRobotPuzzleHeavy2", "MrpError", "VARIANTS", "SB3VecEnv", "VecNormalize", "render"]

@@ -207,8 +207,9 @@ MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env
 
 // fused single-lane step (used by the host emulation's reference path and kept for debugging)
 // Constraint records of the fused per-env paths (fused step, TOI event pass, reset): a lane-local array in the default
-// build; the wide build (192 x 38 words) borrows the env's own slice of the task pool, which no solver kernel of the
-// same chunk touches while these paths run.
+// build; the wide build (192 x 38 words) borrows the env's own slice of the task pool.  The solver records of a step are
+// bump-allocated from the start of the same pool (k_pre), so these paths must not run concurrently with k_solve_vel /
+// k_solve_pos of the same chunk: launch_overlapped() orders the wide build's event passes after the solver kernels.
 #ifdef MRP_WIDE
 #define MRP_VC_SCRATCH(K, env) float* vc_local = (K).pool + (size_t)((env) - (K).env0) * (K).maxc * VC_WORDS
 #else
@@ -511,9 +512,11 @@ struct mrp_handle {
     int device;
     float* ctab_dev;
     float* act_dev;
+    uint8_t* mask_dev;  // mrp_reset_host: staging buffer of the host mask (allocated on first use)
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
     size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post;
     int solver_ctas;  // persistent solver CTAs per SM
+    int num_sms;      // multiprocessors of the handle's device (148 on B200); persistent / queue grids are sized from it
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
@@ -521,6 +524,8 @@ struct mrp_handle {
     cudaEvent_t cfork, cact, cact0, cpre, cfree, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks];
     cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
     int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
+    cudaEvent_t tr[32];        // MRP_TRACE=1: timeline of one mrp_step_host call (created on first use)
+    int tr_init;
     const void* zc_host;       // last obs_host pointer checked for device visibility ...
     float* zc_dev;             // ... and its device alias (nullptr: not pinned / not mapped -> rows leave after the passes)
     int overlap_post;  // mrp_step: k_post of envs without solver tasks runs beside the solver kernels
@@ -640,6 +645,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     if (h->cfork) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); }
         cudaStreamDestroy(h->copy_stream);
+        if (h->tr_init) for (int i = 0; i < 32; ++i) cudaEventDestroy(h->tr[i]);
         cudaEventDestroy(h->cfork);
         cudaEventDestroy(h->cact);
         cudaEventDestroy(h->cact0);
@@ -652,6 +658,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.S);
     DEV_FREE(h->ctab_dev);
     DEV_FREE(h->act_dev);
+    DEV_FREE(h->mask_dev);
     DEV_FREE(h->K.obs);
     DEV_FREE(h->K.rew);
     DEV_FREE(h->K.done);
@@ -726,6 +733,10 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     K.env0 = 0;
     K.nloc = cfg->num_envs;
     h->device = cfg->device;
+    h->num_sms = 148;
+#ifndef MRP_HOST_EMU
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
+#endif
     const size_t N = (size_t)cfg->num_envs;
     int rc = 0;
     rc |= DEV_ALLOC(K.S, sizeof(uint32_t) * N * K.w_total);
@@ -964,14 +975,14 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
                          cudaEvent_t first_half_ready = nullptr, int64_t half = 0, cudaEvent_t* tr = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
-    const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
+    const unsigned sgrid = grid < (unsigned)h->num_sms * (unsigned)h->solver_ctas ? grid : (unsigned)h->num_sms * (unsigned)h->solver_ctas;
     k_clear<<<1, 32, 0, st>>>(K.cnt);
     if (timed) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
     }
     k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
-    k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    k_narrow<<<grid < (unsigned)h->num_sms * 16u ? grid : (unsigned)h->num_sms * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
     if (tr) cudaEventRecord(tr[20], st);
     if (first_half_ready && half > 0 && half < K.nloc) {
         // the second half runs on another stream, beside the draining CTAs of the first (two launches in a row on one
@@ -1003,13 +1014,13 @@ static void launch_front_head(mrp_handle* h, const SimConst& K, cudaStream_t st)
     const unsigned grid = grid_for(K.nloc, kBlock);
     k_clear<<<1, 32, 0, st>>>(K.cnt);
     k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
-    k_narrow<<<grid < 148u * 16u ? grid : 148u * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    k_narrow<<<grid < (unsigned)h->num_sms * 16u ? grid : (unsigned)h->num_sms * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
     k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
     h->launches += 4;
 }
 static void launch_front_solvers(mrp_handle* h, const SimConst& K, cudaStream_t st) {
     const unsigned grid = grid_for(K.nloc, kBlock);
-    const unsigned sgrid = grid < 148u * (unsigned)h->solver_ctas ? grid : 148u * (unsigned)h->solver_ctas;
+    const unsigned sgrid = grid < (unsigned)h->num_sms * (unsigned)h->solver_ctas ? grid : (unsigned)h->num_sms * (unsigned)h->solver_ctas;
     k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
     k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
     h->launches += 2;
@@ -1017,7 +1028,7 @@ static void launch_front_solvers(mrp_handle* h, const SimConst& K, cudaStream_t 
 static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool clear, cudaEvent_t after_post = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
-    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;  // queue kernels: a few CTAs per SM
+    const unsigned pgrid = grid < (unsigned)h->num_sms * 8u ? grid : (unsigned)h->num_sms * 8u;  // queue kernels: a few CTAs per SM
     if (clear) { k_clear<<<1, 32, 0, st>>>(K.cnt); h->launches += 1; }
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 2);
     if (after_post) cudaEventRecord(after_post, st);
@@ -1036,18 +1047,26 @@ static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
 static void launch_overlapped(mrp_handle* h, const SimConst& K, cudaStream_t st) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
-    const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+    const unsigned pgrid = grid < (unsigned)h->num_sms * 8u ? grid : (unsigned)h->num_sms * 8u;
     cudaStream_t side = h->cstream[kMaxChunks - 1];
     launch_front_head(h, K, st);
     cudaEventRecord(h->cpre, st);
     cudaStreamWaitEvent(side, h->cpre, 0);
     k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
+#ifndef MRP_WIDE
     k_post_events<<<pgrid, kBlock, h->smem_bytes, side>>>(K, 1);
+#endif
     cudaEventRecord(h->cfree, side);
     launch_front_solvers(h, K, st);
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 1);
     k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
     cudaStreamWaitEvent(st, h->cfree, 0);
+#ifdef MRP_WIDE
+    // wide build: the event pass borrows the env's slice of the task pool as constraint scratch (MRP_VC_SCRATCH), and
+    // k_pre bump-allocates the solver records of ALL envs from the start of that pool — so the task-free group's event
+    // pass may only run once the solver kernels have finished with the records (beside them it corrupted live records)
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 1);
+#endif
     h->launches += 4;
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
@@ -1058,7 +1077,7 @@ static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, b
     if (h->fused) {  // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
         const unsigned grid = grid_for(K.nloc, kBlock);
         if (grid == 0) return;
-        const unsigned pgrid = grid < 148u * 8u ? grid : 148u * 8u;
+        const unsigned pgrid = grid < (unsigned)h->num_sms * 8u ? grid : (unsigned)h->num_sms * 8u;
         k_clear<<<1, 32, 0, st>>>(K.cnt);
         if (timed) {
             if (h->ev_n == 64) drain_timing(h);
@@ -1213,8 +1232,9 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     // buffers should be pinned) run under the remaining chunks' kernels.
     const int nch = step_chunks(h, h->nchunks_host);
     const size_t N = (size_t)K0.N;
-    static cudaEvent_t tr[32]; static int tr_init = 0; const bool trace = getenv("MRP_TRACE") != nullptr;
-    if (trace && !tr_init) { for (int i = 0; i < 32; ++i) cudaEventCreate(&tr[i]); tr_init = 1; }
+    cudaEvent_t* const tr = h->tr;
+    const bool trace = getenv("MRP_TRACE") != nullptr;
+    if (trace && !h->tr_init) { for (int i = 0; i < 32; ++i) cudaEventCreate(&tr[i]); h->tr_init = 1; }
     if (trace) cudaEventRecord(tr[0], 0);
     cudaEventRecord(h->cfork, 0);  // order after whatever the caller queued on the default stream
     cudaStream_t s_front = h->cstream[0], s_h2d = h->cstream[kMaxChunks - 1];
@@ -1331,9 +1351,13 @@ int MRP_API(mrp_reset_host)(mrp_handle* h, const uint8_t* mask_host, float* obs_
     if (!h) return fail(-1, "mrp_reset_host: null handle");
     const size_t N = (size_t)h->K.N;
     uint8_t* mask_dev = nullptr;
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(-9, "mrp_reset_host: %s", dev_err());   // order after steps queued on any stream
+#endif
     if (mask_host) {
-        // done_dev doubles as the staging buffer for the mask; it is rewritten by the next step
-        mask_dev = h->K.done;
+        if (!h->mask_dev && DEV_ALLOC_RAW(h->mask_dev, N)) return fail(-7, "mrp_reset_host: device allocation failed: %s", dev_err());
+        mask_dev = h->mask_dev;
         if (H2D(mask_dev, mask_host, N)) return fail(-8, "mrp_reset_host: H2D failed: %s", dev_err());
     }
     int rc = MRP_API(mrp_reset)(h, mask_dev, nullptr);
@@ -1379,6 +1403,7 @@ static int push_internal(mrp_handle* h, int64_t begin, int64_t count, const uint
     const SimConst& K = h->K;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;   // steps queued on any stream finish before the state is replaced
     if (cudaMemcpy2D(K.S + begin, sizeof(uint32_t) * K.N, buf, sizeof(uint32_t) * count, sizeof(uint32_t) * count, K.w_total,
                      cudaMemcpyHostToDevice) != cudaSuccess)
         return -1;

@@ -192,9 +192,11 @@ __device__ __forceinline__ float vn_norm(float x, float m, float is, float clip)
     return fminf(fmaxf(y, -clip), clip);
 }
 
-__global__ void __launch_bounds__(kVnBlock) k_vn_apply(const __grid_constant__ VnConst V, const float* __restrict__ obs,
-                                                        const float* __restrict__ rew, const uint8_t* __restrict__ done,
-                                                        float* __restrict__ obs_out, float* __restrict__ rew_out, float* term_obs) {
+// obs_out may alias obs (in-place normalisation, include/mrp_vecnorm.h): neither is __restrict__ nor read through the
+// non-coherent path; every thread reads its elements before it writes them
+__global__ void __launch_bounds__(kVnBlock) k_vn_apply(const __grid_constant__ VnConst V, const float* obs,
+                                                        const float* rew, const uint8_t* __restrict__ done,
+                                                        float* obs_out, float* rew_out, float* term_obs) {
     __shared__ float sm[kVnMaxObs + 1], si[kVnMaxObs + 1];
     const int O = V.O;
     for (int c = threadIdx.x; c <= O; c += kVnBlock) { sm[c] = V.meanf[c]; si[c] = V.istdf[c]; }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kVnBlock) k_vn_apply(const __grid_constant__ V
         const float4* in4 = reinterpret_cast<const float4*>(obs);
         float4* out4 = reinterpret_cast<float4*>(obs_out);
         for (int64_t i = tid; i < n4; i += stride) {
-            float4 v = __ldg(in4 + i);
+            float4 v = in4[i];
             if (V.norm_obs) {
                 int c0 = (int)((i * 4) % O);
                 int c1 = c0 + 1 == O ? 0 : c0 + 1;

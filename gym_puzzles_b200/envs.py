@@ -18,13 +18,14 @@ class MultiRobotPuzzle:
     spec = None
 
     def __init__(self, obs_depth=3, frameskip=4, num_agents=0, seed=17, device=0, _lib=None):
-        # obs_depth / frameskip are accepted for signature compatibility (reference mrp00:152-162: the low-dim
-        # env forces frameskip to 1); v2's ctor is (frameskip=1, num_agents=2) (reference mrp02:139)
+        # obs_depth / frameskip are accepted for signature compatibility: the v0 classes force frameskip to 1 for the
+        # low-dim observation (reference mrp00:161-162), whatever is passed
         self._seed_value = seed
         self._device = device
         self._lib = _lib
         self._num_agents = num_agents
         self._episode_base = 0
+        self._reward_kw, self._knob_kw = None, {}   # knob state survives seed() (which rebuilds the handle)
         self._make_handle()
         self.observation_space = spaces.observation_space(self.env_id, self.num_agents)
         self.action_space = spaces.action_space(self.env_id, self.num_agents)
@@ -35,6 +36,10 @@ class MultiRobotPuzzle:
         self._h = abi.Handle(self.env_id, 1, device=self._device, seed=self._seed_value, n_agents=self._num_agents,
                              auto_reset=False, lib=self._lib)
         self.num_agents = self._h.layout.n_agents
+        if self._reward_kw:
+            self._h.set_params(**self._reward_kw)
+        if self._knob_kw:
+            self._h.set_params(**self._knob_kw)
 
     # ---- gym API
     def seed(self, seed=None):
@@ -80,19 +85,18 @@ class MultiRobotPuzzle:
         self._h.close()
 
     # ---- knobs (reference mrp00:231-258 / mrp02:216-245)
-    def set_reward_params(self, agentDelta=None, agentDistance=None, blockDelta=None, blockDistance=None, puzzleComp=10000,
-                          outOfBounds=1000, blkOutOfBounds=100):
-        cur = self._h.get_params()
-        kw = dict(puzzleComp=puzzleComp, outOfBounds=outOfBounds, blkOutOfBounds=blkOutOfBounds)
-        for k, v in (("agentDelta", agentDelta), ("agentDistance", agentDistance), ("blockDelta", blockDelta), ("blockDistance", blockDistance)):
-            kw[k] = cur[k] if v is None else v
-        self._h.set_params(**kw)
+    def set_reward_params(self, *args, **kwargs):
+        """reference mrp00:231-239 / mrp02:216-225; arguments not given return to the family's defaults, as there"""
+        self._reward_kw = spaces.reward_params(self.env_id, *args, **kwargs)
+        self._h.set_params(**self._reward_kw)
 
     def update_params(self, timestep, decay):
-        self._h.set_params(decay_pow=float(decay) ** (-float(timestep)))
+        self._knob_kw["decay_pow"] = float(decay) ** (-float(timestep))
+        self._h.set_params(decay_pow=self._knob_kw["decay_pow"])
 
     def update_goal(self, epoch, nb_epochs):
-        self._h.set_params(scaled_epsilon=0.1 * (2 - epoch / nb_epochs))
+        self._knob_kw["scaled_epsilon"] = 0.1 * (2 - epoch / nb_epochs)
+        self._h.set_params(scaled_epsilon=self._knob_kw["scaled_epsilon"])
 
     def get_deltaAgent(self):
         return self._h.get_params()["agentDelta"]
@@ -129,6 +133,9 @@ class MultiRobotPuzzle2(MultiRobotPuzzle):
     env_id = "MultiRobotPuzzle-v2"
 
     def __init__(self, frameskip=1, num_agents=2, seed=17, device=0, _lib=None):
+        # reference mrp02:477-478 runs world.Step `frameskip` times per env.step; the kernels run it once
+        if frameskip != 1:
+            raise NotImplementedError("MultiRobotPuzzle2(frameskip != 1) is not provided: one world.Step per env.step (the registered default)")
         super().__init__(frameskip=frameskip, num_agents=num_agents, seed=seed, device=device, _lib=_lib)
 
 

@@ -102,10 +102,7 @@ class SB3VecEnv:
     # the reference's runtime knobs, addressed the way SB3 does it: venv.env_method("set_reward_params", ...)
     def env_method(self, method_name, *args, indices=None, **kwargs):
         if method_name == "set_reward_params":
-            names = ("agentDelta", "agentDistance", "blockDelta", "blockDistance", "puzzleComp", "outOfBounds", "blkOutOfBounds")
-            kw = dict(zip(names, args))
-            kw.update(kwargs)
-            self.handle.set_params(**kw)
+            self.handle.set_params(**spaces.reward_params(self.env_id, *args, **kwargs))
         elif method_name == "update_params":
             timestep, decay = args
             self.handle.set_params(decay_pow=float(decay) ** (-float(timestep)))

@@ -57,3 +57,30 @@ def action_space(env_id, n_agents):
     k = 3 if env_id.endswith("-v0") else 2
     high = np.ones(k * n_agents, dtype=np.float32)
     return make_box(-high, high)
+
+
+def reward_defaults(env_id):
+    """keyword defaults of set_reward_params (reference mrp00:231-232 / mrp02:216-217): an argument that is not given is
+    RESET to its default by the reference, not kept"""
+    if env_id.endswith("-v2"):
+        return dict(agentDelta=10, agentDistance=0.25, blockDelta=25, blockDistance=0.1, puzzleComp=10000, outOfBounds=1000, blkOutOfBounds=100)
+    return dict(agentDelta=10, agentDistance=0.1, blockDelta=50, blockDistance=0.025, puzzleComp=10000, outOfBounds=1000, blkOutOfBounds=100)
+
+
+REWARD_PARAM_NAMES = ("agentDelta", "agentDistance", "blockDelta", "blockDistance", "puzzleComp", "outOfBounds", "blkOutOfBounds")
+
+
+def reward_params(env_id, *args, **kwargs):
+    """positional / keyword arguments of a set_reward_params call -> the full parameter set the reference would end up with"""
+    if len(args) > len(REWARD_PARAM_NAMES):
+        raise TypeError("set_reward_params takes at most %d arguments" % len(REWARD_PARAM_NAMES))
+    kw = reward_defaults(env_id)
+    given = dict(zip(REWARD_PARAM_NAMES, args))
+    for k, v in kwargs.items():
+        if k not in kw:
+            raise TypeError(f"set_reward_params() got an unexpected keyword argument {k!r}")
+        if k in given:
+            raise TypeError(f"set_reward_params() got multiple values for argument {k!r}")
+        given[k] = v
+    kw.update(given)
+    return kw

@@ -129,14 +129,9 @@ class VectorEnv:
         return self.handle.reset_host(mask)
 
     # ------------------------------------------------------------------ knobs of the reference env classes
-    def set_reward_params(self, agentDelta=None, agentDistance=None, blockDelta=None, blockDistance=None, puzzleComp=10000,
-                          outOfBounds=1000, blkOutOfBounds=100):
-        """reference mrp00:231-239 / mrp02:216-225 (defaults differ per family and are kept when None)."""
-        cur = self.handle.get_params()
-        kw = dict(puzzleComp=puzzleComp, outOfBounds=outOfBounds, blkOutOfBounds=blkOutOfBounds)
-        for k, v in (("agentDelta", agentDelta), ("agentDistance", agentDistance), ("blockDelta", blockDelta), ("blockDistance", blockDistance)):
-            kw[k] = cur[k] if v is None else v
-        self.handle.set_params(**kw)
+    def set_reward_params(self, *args, **kwargs):
+        """reference mrp00:231-239 / mrp02:216-225; arguments not given return to the family's defaults, as there"""
+        self.handle.set_params(**spaces.reward_params(self.env_id, *args, **kwargs))
 
     def _per_env(self, x):
         t = self.torch

@@ -94,7 +94,10 @@ int mrp_step(mrp_handle* h, const float* actions_dev, void* stream);
  * H2D copy of actions, step, D2H copies of the results, then a stream synchronise.
  * Any output pointer may be NULL.  Pinned (page-locked, device-visible) buffers make the copies overlap the kernels;
  * with a pinned obs buffer the rows of a chunk of envs leave before that chunk's TOI-event / auto-reset passes and the
- * few rows those passes rewrite are stored into the buffer by a kernel.  Pageable buffers work, more slowly. */
+ * few rows those passes rewrite are stored into the buffer by a kernel.  Pageable buffers work, more slowly.
+ * Ordering: mrp_step_host orders its work after what the caller queued on the legacy default stream only; a caller
+ * that mixes it with mrp_step / mrp_reset on another stream synchronises that stream first.  mrp_reset_host,
+ * mrp_get_state, mrp_set_state and mrp_get_stats synchronise the device on entry. */
 int mrp_step_host(mrp_handle* h, const float* actions_host, float* obs_host, float* reward_host,
                   uint8_t* done_host, uint8_t* trunc_host);
 int mrp_reset_host(mrp_handle* h, const uint8_t* mask_host, float* obs_host);

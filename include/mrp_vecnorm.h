@@ -44,7 +44,7 @@ int mrp_vecnorm_accum(mrp_vecnorm* vn, double** accum_dev, int32_t* count);
 /* pass 2: fold the batch moments into the running statistics (Chan's parallel update), then
  * obs_out = clip((obs - mean) / sqrt(var + eps)), reward_out = clip(reward / sqrt(var_ret + eps)),
  * returns[done] = 0, terminal-observation rows of done envs normalised in place.
- * obs_out_dev may alias obs_dev; reward_dev, reward_out_dev, done_dev, terminal_obs_dev may be NULL. */
+ * obs_out_dev may alias obs_dev and reward_out_dev may alias reward_dev (in place); reward_dev, reward_out_dev, done_dev, terminal_obs_dev may be NULL. */
 int mrp_vecnorm_apply(mrp_vecnorm* vn, const float* obs_dev, const float* reward_dev, const uint8_t* done_dev,
                       float* obs_out_dev, float* reward_out_dev, float* terminal_obs_dev, void* stream);
 /* VecNormalize.reset(): returns <- 0 */

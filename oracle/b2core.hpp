@@ -1122,6 +1122,59 @@ struct World {
         }
     }
 
+    // Harness entry (not a Box2D function): put the dynamic bodies, their proxies' fat AABBs and the contact list into
+    // a given between-steps state.  Bodies [0, nDyn) and fixtures [0, nDynFix) are the dynamic ones (creation order:
+    // the env builders create them before the walls).  bodies6 = (c.x, c.y, a, v.x, v.y, w) per body; contact records
+    // are include/mrp_state.h's 14 words, list head first.  The move buffer is empty between two steps.
+    void LoadState(int nDyn, const float* bodies6, int nDynFix, const float* fat4, int nc, const uint32_t* cwords) {
+        for (Contact* c : contactList) delete c;
+        contactList.clear();
+        for (Body& b : bodies) b.contacts.clear();
+        for (int b = 0; b < nDyn; ++b) {
+            Body& B = bodies[b];
+            B.sweep.c = Vec2(bodies6[6 * b + 0], bodies6[6 * b + 1]);
+            B.sweep.a = bodies6[6 * b + 2];
+            B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
+            B.v = Vec2(bodies6[6 * b + 3], bodies6[6 * b + 4]);
+            B.w = bodies6[6 * b + 5];
+            B.force = Vec2(0, 0); B.torque = 0.0f;
+            B.SynchronizeTransform();
+        }
+        for (int f = 0; f < nDynFix; ++f) {
+            fat[f].lo = Vec2(fat4[4 * f + 0], fat4[4 * f + 1]);
+            fat[f].hi = Vec2(fat4[4 * f + 2], fat4[4 * f + 3]);
+        }
+        moveBuffer.clear();
+        newFixture = false;
+        inv_dt0 = 50.0f;
+        // record k is list position k (head first): rebuild tail -> head
+        for (int k = nc - 1; k >= 0; --k) {
+            const uint32_t* cw = cwords + 14 * k;
+            const float* cf = (const float*)cw;
+            Contact* c = new Contact();
+            c->fA = cw[0] & 0xff; c->fB = (cw[0] >> 8) & 0xff;
+            c->bA = fixtures[c->fA].body; c->bB = fixtures[c->fB].body;
+            c->touching = ((cw[0] >> 16) & 1) != 0;
+            c->manifold.type = (cw[0] >> 17) & 1;
+            c->manifold.pointCount = (cw[0] >> 18) & 3;
+            c->friction = std::sqrt(fixtures[c->fA].friction * fixtures[c->fB].friction);
+            c->restitution = 0.0f;
+            c->manifold.localNormal = Vec2(cf[2], cf[3]);
+            c->manifold.localPoint = Vec2(cf[4], cf[5]);
+            for (int j = 0; j < 2; ++j) {
+                uint32_t k16 = (cw[1] >> (16 * j)) & 0xffff;
+                ManifoldPoint& p = c->manifold.points[j];
+                p.id.indexA = k16 & 15; p.id.indexB = (k16 >> 4) & 15; p.id.typeA = (k16 >> 8) & 1; p.id.typeB = (k16 >> 9) & 1;
+                p.localPoint = Vec2(cf[6 + 4 * j], cf[7 + 4 * j]);
+                p.normalImpulse = cf[8 + 4 * j];
+                p.tangentImpulse = cf[9 + 4 * j];
+            }
+            contactList.insert(contactList.begin(), c);
+            bodies[c->bA].contacts.insert(bodies[c->bA].contacts.begin(), c);
+            bodies[c->bB].contacts.insert(bodies[c->bB].contacts.begin(), c);
+        }
+    }
+
     void Step(float dt, int velocityIterations, int positionIterations);
     void Solve(const TimeStep& step);
     void SolveTOI(const TimeStep& step);

@@ -118,6 +118,18 @@ int b2s_step(void* h, float dt, int vel_iters, int pos_iters, int* events5, int 
     }
     return (int)s->events.size();
 }
+// Harness entry (no pybox2d counterpart): load a between-steps state — dynamic bodies (c, a, v, w), fat AABBs of their
+// proxies, contact list in include/mrp_state.h's record format — so that the reference's Python can be stepped from
+// the very state the oracle and the CUDA library are stepped from (BASELINE.json north_star: "from identical states").
+// The env modules create the dynamic bodies (block, robots) before the walls, so canonical body / fixture ids are the
+// world's creation-order ids.
+int b2s_load_state(void* h, int n_dyn, const float* bodies6, int n_dynfix, const float* fat4, int nc, const uint32_t* contacts14) {
+    World* w = S(h)->w;
+    if (n_dyn > (int)w->bodies.size() || n_dynfix > (int)w->fixtures.size()) return -1;
+    for (int b = 0; b < n_dyn; ++b) if (w->bodies[b].type != kDynamic) return -2;
+    w->LoadState(n_dyn, bodies6, n_dynfix, fat4, nc, contacts14);
+    return 0;
+}
 long b2s_toi_events(void* h) { return S(h)->w->stat_toi_events; }
 
 // the Philox stream the oracle / product spawn from, so the harness can feed the reference's np.random.uniform and

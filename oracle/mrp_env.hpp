@@ -499,15 +499,8 @@ struct Env : ContactListener {
         double blk[3] = {0, 0, 0}, ag[2 * MRP_MAX_AGENTS];
         for (int i = 0; i < 2 * MRP_MAX_AGENTS; ++i) ag[i] = 0;
         build_world(blk, ag);  // shapes/masses; poses overwritten below
-        for (int b = 0; b <= n; ++b) {
-            Body& B = world->bodies[b == 0 ? block_body : agent_body[b - 1]];
-            B.sweep.c = Vec2(fb[6 * b + 0], fb[6 * b + 1]);
-            B.sweep.a = fb[6 * b + 2];
-            B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
-            B.v = Vec2(fb[6 * b + 3], fb[6 * b + 4]);
-            B.w = fb[6 * b + 5];
-            B.SynchronizeTransform();
-        }
+        // canonical body b is world body b (block, then the robots; walls are created last)
+        world->LoadState(n + 1, fb, L.n_dyn_fixtures, (const float*)(w + L.off_aabb), nc, w + L.off_contacts);
         for (int i = 0; i < n; ++i) goal_contact[i] = w[L.off_goal_contact + i] != 0;
         double dd[MRP_MAX_AGENTS + 1];
         std::memcpy(dd, w + L.off_dists, sizeof(double) * (n + 1));
@@ -518,40 +511,6 @@ struct Env : ContactListener {
         goal_x = g[0]; goal_y = g[1];
         std::memcpy(&ep_return, w + L.off_episode_acc, sizeof(double));
         ep_len = (int)w[L.off_episode_acc + 2];
-        const float* fa = (const float*)(w + L.off_aabb);
-        for (int f = 0; f < L.n_dyn_fixtures; ++f) {
-            world->fat[f].lo = Vec2(fa[4 * f + 0], fa[4 * f + 1]);
-            world->fat[f].hi = Vec2(fa[4 * f + 2], fa[4 * f + 3]);
-        }
-        world->moveBuffer.clear();
-        world->newFixture = false;
-        world->inv_dt0 = 50.0f;
-        // contacts: record k is list position k (head first); rebuild tail -> head
-        for (int k = nc - 1; k >= 0; --k) {
-            const uint32_t* cw = w + L.off_contacts + MRP_CONTACT_WORDS * k;
-            const float* cf = (const float*)cw;
-            Contact* c = new Contact();
-            c->fA = cw[0] & 0xff; c->fB = (cw[0] >> 8) & 0xff;
-            c->bA = world->fixtures[c->fA].body; c->bB = world->fixtures[c->fB].body;
-            c->touching = ((cw[0] >> 16) & 1) != 0;
-            c->manifold.type = (cw[0] >> 17) & 1;
-            c->manifold.pointCount = (cw[0] >> 18) & 3;
-            c->friction = std::sqrt(world->fixtures[c->fA].friction * world->fixtures[c->fB].friction);
-            c->restitution = 0.0f;
-            c->manifold.localNormal = Vec2(cf[2], cf[3]);
-            c->manifold.localPoint = Vec2(cf[4], cf[5]);
-            for (int j = 0; j < 2; ++j) {
-                uint32_t k16 = (cw[1] >> (16 * j)) & 0xffff;
-                ManifoldPoint& p = c->manifold.points[j];
-                p.id.indexA = k16 & 15; p.id.indexB = (k16 >> 4) & 15; p.id.typeA = (k16 >> 8) & 1; p.id.typeB = (k16 >> 9) & 1;
-                p.localPoint = Vec2(cf[6 + 4 * j], cf[7 + 4 * j]);
-                p.normalImpulse = cf[8 + 4 * j];
-                p.tangentImpulse = cf[9 + 4 * j];
-            }
-            world->contactList.insert(world->contactList.begin(), c);
-            world->bodies[c->bA].contacts.insert(world->bodies[c->bA].contacts.begin(), c);
-            world->bodies[c->bB].contacts.insert(world->bodies[c->bB].contacts.begin(), c);
-        }
     }
 };
 

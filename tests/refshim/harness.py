@@ -123,6 +123,29 @@ class ReferenceEnv:
             obs = self.reset()
         return obs, float(rew), bool(done), bool(trunc)
 
+    def set_state(self, layout, words):
+        """Put the reference env into the between-steps state of one canonical record (include/mrp_state.h): Box2D side
+        through the stand-in's load_state, Python side by assigning the attributes step() reads (goal_contact flags,
+        previous distances, goal, blks_in_place).  v0's goal is a module constant and must agree with the record."""
+        from oracle_lib import StateView
+        sv = StateView(layout, np.asarray(words, dtype=np.uint32).reshape(1, -1))
+        w, l, env = sv.w[0], layout, self.env
+        nc = int(w[3])
+        env.world.load_state(sv.bodies[0], sv.aabbs[0], sv.contacts[0][:nc])
+        self.elapsed, self.episode = int(w[0]), int(np.int32(w[1]))
+        env.blks_in_place = int(w[2])
+        d = sv.dists[0]
+        for i, a in enumerate(env.agents):
+            a.goal_contact = bool(w[l.off_goal_contact + i])
+            env.agent_dist[a.userData] = float(d[i])
+        env.block_distance[env.goal_block.userData] = float(d[l.n_agents])
+        gx, gy = np.ascontiguousarray(w[l.off_goal:l.off_goal + 4]).view(np.float64)
+        if self.v2:
+            env.block_final_pos = {env.goal_block.userData: (float(gx), float(gy), 0)}
+        else:
+            fx, fy, _ = env.block_final_pos[env.goal_block.userData]
+            assert (fx, fy) == (gx, gy), "v0 goal is fixed (mrp00:115-128)"
+
     @property
     def goal_contacts(self):
         return [bool(a.goal_contact) for a in self.env.agents]

@@ -33,6 +33,7 @@ _L.b2s_world_point.argtypes = [_p, _i, _f, _f, _p]
 _L.b2s_world_vector.argtypes = [_p, _i, _f, _f, _p]
 _L.b2s_step.argtypes = [_p, _f, _i, _i, _p, _i]
 _L.b2s_toi_events.argtypes = [_p]
+_L.b2s_load_state.argtypes = [_p, _i, _p, _i, _p, _i, _p]
 _L.b2s_toi_events.restype = C.c_long
 _L.b2s_uniform53.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
 _L.b2s_uniform53.restype = C.c_double
@@ -291,6 +292,14 @@ class b2World:
     @property
     def toi_events(self):
         return int(_L.b2s_toi_events(self._h))
+
+    def load_state(self, bodies6, fat4, contacts14):
+        """harness only (no pybox2d counterpart): see b2s_load_state in oracle/b2shim_capi.cpp"""
+        b = np.ascontiguousarray(bodies6, dtype=np.float32)
+        f = np.ascontiguousarray(fat4, dtype=np.float32)
+        c = np.ascontiguousarray(contacts14, dtype=np.uint32).reshape(-1, 14)
+        rc = _L.b2s_load_state(self._h, b.shape[0], b.ctypes.data, f.shape[0], f.ctypes.data, c.shape[0], c.ctypes.data)
+        assert rc == 0, rc
 
 
 def uniform53(seed, stream, env, epoch, d):

@@ -81,6 +81,72 @@ def _replay_through_abi(env_id, lib=None):
 
 
 @pytest.mark.parametrize("env_id", IDS)
+def test_oracle_reproduces_reference_single_steps(env_id):
+    """ss_* fixtures: one reference env.step from a given state (incl. the v2 out-of-bounds branches, mrp02:552-563)."""
+    g = _load(env_id)
+    S = len(g["ss_states"])
+    if env_id.endswith("v2"):
+        k = g["ss_kind"]
+        assert (k == 1).sum() >= 2 and (k == 2).sum() >= 2 and (g["ss_decay_pow"][k > 0] != 1.0).any()
+        assert g["ss_done"][k > 0].all() and (g["ss_rew"][k == 2] > -400).all() and (g["ss_rew"][(k == 1) | (k == 3)] < -900).all()
+    for i in range(S):
+        o = OracleBatch(env_id, 1, seed=int(g["seed"]))
+        o.set_auto_reset(False)
+        p = o.get_params()
+        p[8] = g["ss_decay_pow"][i]
+        o.set_params(p)
+        o.set_state(g["ss_states"][i][None])
+        obs, rew, done, trunc = o.step(g["ss_actions"][i][None])
+        assert _close64(obs[0], g["ss_obs"][i]) and _close64(rew[0], g["ss_rew"][i], amplify=1e3), (env_id, i)
+        assert done[0] == g["ss_done"][i] and trunc[0] == 0, (env_id, i)
+        sv = StateView(o.layout, o.get_state())
+        assert np.array_equal(sv.goal_contact[0], g["ss_contact"][i]), (env_id, i)
+        assert np.array_equal(sv.bodies[0].view(np.uint32), g["ss_bodies"][i].view(np.uint32)), (env_id, i)
+
+
+def _single_steps_through_abi(env_id, lib=None, device_path=False):
+    """the same fixtures through the C-ABI: one batch per decay value (mrp_set_params is per handle)"""
+    g = _load(env_id)
+    kw = {} if lib is None else {"lib": lib}
+    checked = 0
+    for dp in np.unique(g["ss_decay_pow"]):
+        idx = np.nonzero(g["ss_decay_pow"] == dp)[0]
+        h = abi.Handle(env_id, len(idx), seed=int(g["seed"]), auto_reset=False, **kw)
+        h.reset_host()
+        h.set_params(decay_pow=float(dp))
+        h.set_state(g["ss_states"][idx])
+        if device_path:
+            from parity_util import device_stepper
+            obs, rew, done, trunc = device_stepper(h)(g["ss_actions"][idx])
+        else:
+            obs, rew, done, trunc = h.step_host(g["ss_actions"][idx])
+        assert np.array_equal(done, g["ss_done"][idx]) and not trunc.any(), env_id
+        assert np.allclose(obs, g["ss_obs"][idx], rtol=1e-5, atol=1e-5), (env_id, np.abs(obs - g["ss_obs"][idx]).max())
+        assert np.allclose(rew, g["ss_rew"][idx], rtol=1e-5, atol=1e-3), env_id
+        sv = StateView(h.layout, h.get_state())
+        assert np.array_equal(sv.goal_contact, g["ss_contact"][idx]), env_id
+        assert np.allclose(sv.bodies, g["ss_bodies"][idx], rtol=1e-5, atol=1e-6), env_id
+        checked += len(idx)
+        h.close()
+    return checked
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_kernel_source_reproduces_reference_single_steps(env_id):
+    from emu_lib import emu_lib
+    assert _single_steps_through_abi(env_id, lib=emu_lib()) == len(_load(env_id)["ss_states"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", IDS)
+@pytest.mark.parametrize("device_path", [False, True])
+def test_gpu_reproduces_reference_single_steps(env_id, device_path):
+    """reference Python vs the sm_100a library from identical states, incl. mrp02:552-563 (robot / block out of bounds)"""
+    n = _single_steps_through_abi(env_id, device_path=device_path)
+    print(env_id, "single steps from given states:", n)
+
+
+@pytest.mark.parametrize("env_id", IDS)
 def test_kernel_source_reproduces_reference_python(env_id):
     from emu_lib import emu_lib
     _replay_through_abi(env_id, lib=emu_lib())

@@ -100,15 +100,30 @@ def test_chunked_streams_are_invariant(monkeypatch):
     assert sr["episodes"] > 0 and abs(sr["sum_return"] - sc["sum_return"]) <= 1e-9 * abs(sr["sum_return"])   # atomics order
 
 
+@pytest.mark.parametrize("device_path", [False, True])
 @pytest.mark.parametrize("env_id,n_agents", [("MultiRobotPuzzle-v2", 5), ("MultiRobotPuzzleHeavy-v2", 3)])
-def test_v2_more_agents_parity(env_id, n_agents):
-    """BASELINE.json configs[3] with the num_agents ctor kw (mrp02:139): wide-capacity build of the kernels."""
+def test_v2_more_agents_parity(env_id, n_agents, device_path):
+    """BASELINE.json configs[3] with the num_agents ctor kw (mrp02:139): wide-capacity build of the kernels, through
+    mrp_step_host and through the device-resident mrp_step."""
     N, T = 512, 100
     h = abi.Handle(env_id, N, seed=17, max_episode_steps=50, n_agents=n_agents)
     assert h.layout.max_contacts > 32
-    rep = rollout_compare(h, env_id, N, T, seed=17, max_episode_steps=50, n_agents=n_agents)
+    rep = rollout_compare(h, env_id, N, T, seed=17, max_episode_steps=50, n_agents=n_agents, device_path=device_path)
     _assert_parity(rep)
     assert rep["dones"] >= N and h.stats()["overflow"] == 0
+    h.close()
+
+
+def test_v2_more_agents_overlapped_post(monkeypatch):
+    """Wide build with the overlapped k_post (the default from 65,536 envs): the event pass of the task-free group uses
+    the env's slice of the task pool as scratch and must not run beside the solver kernels, whose records start at the
+    pool's base (round-1 ADVICE: data race).  Low env indices with many live records are the ones at risk."""
+    monkeypatch.setenv("MRP_OVERLAP_POST", "1")
+    env_id, n_agents, N, T = "MultiRobotPuzzle-v2", 5, 4096, 80
+    h = abi.Handle(env_id, N, seed=23, max_episode_steps=40, n_agents=n_agents)
+    rep = rollout_compare(h, env_id, N, T, seed=23, max_episode_steps=40, n_agents=n_agents, device_path=True, nthreads=16)
+    _assert_parity(rep)
+    assert rep["dones"] >= N
     h.close()
 
 
