@@ -18,8 +18,9 @@ VARIANTS = {
     "MultiRobotPuzzleHeavy-v2": 3,
 }
 
-N_STATS = 8
-STAT_NAMES = ("episodes", "done_by_env", "truncated", "sum_return", "sum_return_sq", "sum_length", "env_steps", "overflow")
+N_STATS = 16
+STAT_NAMES = ("episodes", "done_by_env", "truncated", "sum_return", "sum_return_sq", "sum_length", "env_steps", "overflow",
+              "nan_resets", "pairs", "m1", "m2", "vel_flops", "pos_points", "toi_calls", "reserved")
 
 EXPORTS = (
     "mrp_last_error", "mrp_backend", "mrp_create", "mrp_destroy", "mrp_get_layout", "mrp_get_buffers", "mrp_reset",
@@ -143,6 +144,7 @@ class Handle:
         self.num_envs = num_envs
         self.obs_dim, self.act_dim = self.layout.obs_dim, self.layout.act_dim
         self.state_words = self.layout.state_words
+        self.state_bytes = 4 * self.state_words   # canonical record; the device-resident [word][env] state is about as large
         self.variant = variant
 
     def close(self):

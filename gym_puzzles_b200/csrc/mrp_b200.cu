@@ -55,11 +55,28 @@ MRP_HD void stat_add(double* stats, int slot, double v) {
 #endif
 }
 
+// workload counters: one atomic per warp (every lane of the warp calls)
+#ifndef MRP_HOST_EMU
+__device__ __forceinline__ void stat_add_warp(double* stats, int slot, uint32_t v) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + slot, (double)v);
+}
+#endif
+
 // TimeLimit, episode accounting, auto-reset queue: the tail of every env.step
 MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r) {
     uint32_t elapsed = e.g(W_ELAPSED) + 1u;
     e.g(W_ELAPSED) = elapsed;
+    // NaN / inf guard: a dynamic body whose pose or velocity is not finite ends the episode by force —
+    // reported like a TimeLimit truncation with reward 0, counted in MRP_STAT_NAN_RESETS, respawned by the auto-reset
+    uint32_t expo = 0u;
+    for (int b = 0; b < K.nb; ++b)
+        for (int f = 0; f < 6; ++f) expo |= ((Sim::__float_as_uint_(e.B(b, f)) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
     bool limit = (int)elapsed >= K.max_steps;
+    if (expo) {
+        d = false; limit = true; r = 0.0;
+        stat_add(K.stats, MRP_STAT_NAN_RESETS, 1.0);
+    }
     bool done = d || limit;
     K.rew[env] = (float)r;
     K.done[env] = done ? 1 : 0;
@@ -106,14 +123,16 @@ MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
 
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
 // returns the number of solver constraints of the env (0: no island task was queued for it)
-MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
+MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, uint32_t* m12) {
     Env e(K, sm, ct, env, nullptr, 13);
     // the action row is requested first so that it is in flight while the state words are loaded
     float a[3 * MRP_MAX_AGENTS];
     const float* arow = K.act + env * K.act_dim;
     for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
     e.load();
-    return e.pre_phase(a);
+    const int T = e.pre_phase(a);
+    m12[0] += e.stat_m1; m12[1] += e.stat_m2;
+    return T;
 }
 
 // phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
@@ -259,6 +278,27 @@ __device__ __forceinline__ const float* load_ctab(const SimConst& K, float* smem
     return smem;
 }
 
+// -DMRP_TAILPROBE (profiling builds only, profiles/tailprobe.py): when does each warp of the tail-dominated kernels finish,
+// and which single task ran longest?  Times are globaltimer nanoseconds.
+#ifdef MRP_TAILPROBE
+constexpr int kTpKernels = 8, kTpWarps = 8192;   // ids: 0 k_solve_vel, 1 k_solve_pos, 2 k_post_events, 3 k_post_events (free), 4..7 vel classes 0..3
+__device__ unsigned long long g_tp_start[kTpKernels];
+__device__ unsigned long long g_tp_end[kTpKernels][kTpWarps];
+__device__ unsigned long long g_tp_maxtask[kTpKernels];
+__device__ __forceinline__ unsigned long long tp_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tp_begin(int id) { if ((threadIdx.x & 31) == 0) atomicMin(&g_tp_start[id], tp_now()); }
+__device__ __forceinline__ void tp_end(int id) {
+    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if ((threadIdx.x & 31) == 0 && w < kTpWarps) g_tp_end[id][w] = tp_now();
+}
+__device__ __forceinline__ void tp_task(int id, unsigned long long t0, uint32_t info) {
+    atomicMax(&g_tp_maxtask[id], ((tp_now() - t0) << 24) | (unsigned long long)(info & 0xffffffu));
+}
+#define TP(x) x
+#else
+#define TP(x)
+#endif
+
 __global__ void k_clear(int32_t* cnt) {
     if (threadIdx.x < CNT_N) cnt[threadIdx.x] = 0;
 }
@@ -302,6 +342,7 @@ __global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimCo
     extern __shared__ float smem[];
     const int count = K.cnt[CNT_NARROW];
     if ((int64_t)blockIdx.x * kBlock >= count) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(K.stats + MRP_STAT_PAIRS, (double)count);
     const float* ct = load_ctab(K, smem);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock)
         narrow_item(K, ct, K.narrow_list[i]);
@@ -316,7 +357,10 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
     const bool valid = loc < loc1;   // every lane of the warp stays for the warp-aggregated list reservation
     const int64_t env = K.env0 + loc;
     int T = -1;
-    if (valid) T = pre_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    uint32_t m12[2] = {0u, 0u};
+    if (valid) T = pre_lane(K, smem + kCtPad + threadIdx.x, ct, env, m12);
+    stat_add_warp(K.stats, MRP_STAT_M1, m12[0]);
+    stat_add_warp(K.stats, MRP_STAT_M2, m12[1]);
     // envs without solver tasks are final already: k_post handles them while the solver kernels run (post_list)
     const unsigned free_m = __ballot_sync(0xffffffffu, T == 0), busy_m = __ballot_sync(0xffffffffu, T > 0);
     const int lane = threadIdx.x & 31;
@@ -345,19 +389,21 @@ constexpr int kRefill = MRP_REFILL;
 constexpr int kInnerTrips = MRP_INNER_TRIPS;
 
 template <int CLS>
-__device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
+__device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s, uint32_t& flops) {
     const int ntasks = task_count(K, CLS);
     VelTask vt;
     Sim::VelReg st1;  // second contact (class 2 only)
     float imp3[CLS == 3 ? 4 * kMaxC : 4];   // class 3: the island's accumulated impulses while it iterates
     float* const imp = CLS == 3 ? imp3 : nullptr;
     bool busy = false, exhausted = false;
+    TP(unsigned long long tp_t0 = 0;)
     for (;;) {
         const unsigned bm = __ballot_sync(0xffffffffu, busy);
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_V + CLS], 1);
                 if (task < ntasks) {
+                    TP(tp_t0 = tp_now();)
                     vel_task_begin(K, s, vt, task_slot(K, CLS, task));
                     if (CLS == 2) s.vr_begin_pair(vt.st, st1); else s.vr_begin(vt.st, vt.T, imp);
                     busy = true;
@@ -371,27 +417,34 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s) {
             bool fin = false;
 #pragma unroll 1
             for (int rep = 0; rep < kInnerTrips && !fin; ++rep) {
-                if (CLS == 0) { vt.ops += 2; fin = s.vr_sweep_single<1>(vt.st, 180); }
-                else if (CLS == 1) { vt.ops += 3; fin = s.vr_sweep_single<2>(vt.st, 180); }
-                else if (CLS == 2) { vt.ops += 5; fin = s.vr_sweep_pair(vt.st, st1, 180); }
-                else { vt.ops += (uint32_t)vt.st.vpc + 1u; fin = s.vr_trip_contact(vt.st, 180, imp); }
+                // flops by the cost model of SURVEY.md Appendix D: 81 per 1-point contact and sweep, 160 per 2-point contact
+                if (CLS == 0) { vt.ops += 2; flops += 81u; fin = s.vr_sweep_single<1>(vt.st, 180); }
+                else if (CLS == 1) { vt.ops += 3; flops += 160u; fin = s.vr_sweep_single<2>(vt.st, 180); }
+                else if (CLS == 2) { vt.ops += 5; flops += (vt.st.vpc == 2 ? 160u : 81u) + (st1.vpc == 2 ? 160u : 81u); fin = s.vr_sweep_pair(vt.st, st1, 180); }
+                else { vt.ops += (uint32_t)vt.st.vpc + 1u; flops += vt.st.vpc == 2 ? 160u : 81u; fin = s.vr_trip_contact(vt.st, 180, imp); }
             }
             if (fin) {
+                TP(tp_task(0, tp_t0, ((uint32_t)vt.T << 16) | (uint32_t)(CLS == 2 ? vt.st.sweep : vt.st.sweep));)
                 vel_task_end(K, s, vt);
                 busy = false;
             }
         }
     }
+    TP(tp_end(4 + CLS);)
 }
 
 __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
     Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
     // every warp serves one class at a time (uniform instruction stream); multi-contact islands first, they run longest
-    solve_vel_class<3>(K, s);
-    solve_vel_class<2>(K, s);
-    solve_vel_class<1>(K, s);
-    solve_vel_class<0>(K, s);
+    uint32_t flops = 0u;
+    TP(tp_begin(0); tp_begin(4); tp_begin(5); tp_begin(6); tp_begin(7);)
+    solve_vel_class<3>(K, s, flops);
+    solve_vel_class<2>(K, s, flops);
+    solve_vel_class<1>(K, s, flops);
+    solve_vel_class<0>(K, s, flops);
+    stat_add_warp(K.stats, MRP_STAT_VEL_FLOPS, flops);
+    TP(tp_end(0);)
 }
 
 __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ SimConst K) {
@@ -400,12 +453,13 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
     const int ntasks = task_count_all(K);
     PosTask pt;
     bool busy = false, exhausted = false;
+    TP(unsigned long long tp_t0 = 0; tp_begin(1);)
     for (;;) {
         const unsigned bm = __ballot_sync(0xffffffffu, busy);
         if (32 - __popc(bm) >= kRefill || bm == 0u) {
             if (!busy && !exhausted) {
                 const int task = atomicAdd(&K.cnt[CNT_HEAD_P], 1);
-                if (task < ntasks) { pos_task_begin(K, s, pt, task_slot_any(K, task)); busy = true; }
+                if (task < ntasks) { TP(tp_t0 = tp_now();) pos_task_begin(K, s, pt, task_slot_any(K, task)); busy = true; }
                 else exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
@@ -415,11 +469,14 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
 #pragma unroll 1
             for (int rep = 0; rep < kInnerTrips && !fin; ++rep) fin = s.pos_trip<true>(pt.st, pt.T, 60, -1, -1);
             if (fin) {
+                TP(tp_task(1, tp_t0, ((uint32_t)pt.T << 16) | (uint32_t)pt.st.sweep);)
                 pos_task_end(K, s, pt);
                 busy = false;
             }
         }
     }
+    stat_add_warp(K.stats, MRP_STAT_POS_POINTS, s.stat_pos_pts);
+    TP(tp_end(1);)
 }
 
 // which = 2: envs [env0, env0 + nloc) in order.  which = 0 / 1: the envs k_pre listed as free of / owning solver tasks
@@ -441,11 +498,15 @@ __global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ 
     const int count = K.cnt[free_group ? CNT_TOI_F : CNT_TOI];
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
+    TP(tp_begin(2 + (free_group ? 1 : 0));)
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock) {
         const int64_t env = K.toi_list[free_group ? K.nloc - 1 - i : i];
         MRP_VC_SCRATCH(K, env);
+        TP(const unsigned long long tp_t0 = tp_now();)
         post_lane(K, smem + kCtPad + threadIdx.x, ct, env, true, vc_local);
+        TP(tp_task(2 + (free_group ? 1 : 0), tp_t0, 0u);)
     }
+    TP(tp_end(2 + (free_group ? 1 : 0));)
 }
 
 __global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K) {
@@ -1103,9 +1164,12 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
         if (n) push_narrow(K, e, need, atomic_add_i32(&K.cnt[CNT_NARROW], n));
     }
     const int nnarrow = K.cnt[CNT_NARROW];
+    K.stats[MRP_STAT_PAIRS] += nnarrow;
     for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
     for (int64_t e = e0; e < e1; ++e) {
-        const int T = pre_lane(K, h->emu_sm, h->ctab_dev, e);
+        uint32_t m12[2] = {0u, 0u};
+        const int T = pre_lane(K, h->emu_sm, h->ctab_dev, e, m12);
+        K.stats[MRP_STAT_M1] += m12[0]; K.stats[MRP_STAT_M2] += m12[1];
         if (T == 0) K.post_list[K.cnt[CNT_FREE]++] = (int32_t)e;
         else K.post_list[K.nloc - 1 - K.cnt[CNT_BUSY]++] = (int32_t)e;
     }
@@ -1583,6 +1647,35 @@ int MRP_API(mrp_get_stats)(mrp_handle* h, double* out_host, int32_t reset_after)
     if (reset_after) { DEV_ZERO(h->K.stats, sizeof(double) * MRP_N_STATS); h->steps_done = 0; }
     return 0;
 }
+
+#if defined(MRP_TAILPROBE) && !defined(MRP_WIDE) && !defined(MRP_HOST_EMU)
+// profiling builds only: reset (what = 0) or read (what = 1) the tail probe.  out: [kernel][0] start, [kernel][1] longest task
+// (ns << 24 | info), [kernel][2 ...] end time of every warp (0 = did not run); row length 2 + kTpWarps
+int mrp_debug_tailprobe(int what, unsigned long long* out) {
+    if (what == 0) {
+        static unsigned long long ones[kTpKernels];
+        for (int i = 0; i < kTpKernels; ++i) ones[i] = ~0ull;
+        cudaMemcpyToSymbol(g_tp_start, ones, sizeof(ones));
+        unsigned long long* p = nullptr;
+        cudaGetSymbolAddress((void**)&p, g_tp_end);
+        cudaMemset(p, 0, sizeof(unsigned long long) * kTpKernels * kTpWarps);
+        cudaGetSymbolAddress((void**)&p, g_tp_maxtask);
+        cudaMemset(p, 0, sizeof(unsigned long long) * kTpKernels);
+        return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+    }
+    cudaDeviceSynchronize();
+    static unsigned long long st[kTpKernels], mx[kTpKernels];
+    cudaMemcpyFromSymbol(st, g_tp_start, sizeof(st));
+    cudaMemcpyFromSymbol(mx, g_tp_maxtask, sizeof(mx));
+    for (int k = 0; k < kTpKernels; ++k) {
+        out[(size_t)k * (2 + kTpWarps)] = st[k];
+        out[(size_t)k * (2 + kTpWarps) + 1] = mx[k];
+        cudaMemcpyFromSymbol(out + (size_t)k * (2 + kTpWarps) + 2, g_tp_end, sizeof(unsigned long long) * kTpWarps,
+                             sizeof(unsigned long long) * kTpWarps * k);
+    }
+    return 0;
+}
+#endif
 
 int64_t MRP_API(mrp_launch_count)(mrp_handle* h) {
 #ifndef MRP_WIDE

@@ -359,6 +359,7 @@ struct Env : Sim {
             vcp = K.pool + (size_t)off * VC_WORDS;
             init_constraints(T, island_of, true);
             warm_start(T);
+            for (int t = 0; t < T; ++t) { if (((vmeta(t) >> 8) & 3) == 2) ++stat_m2; else ++stat_m1; }
             // one solver task per island (its constraint records are contiguous in solver order)
             const bool heavy = g(W_HINT) >= kHeavyHint;
             const int cap = K.nloc * K.nb;

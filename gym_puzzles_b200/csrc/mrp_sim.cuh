@@ -233,6 +233,8 @@ struct Sim {
     int nc;
     uint32_t goalc;
     uint32_t overflow;
+    // workload counters of this lane (MRP_STAT_M1 / M2 / POS_POINTS / TOI_CALLS): summed per warp by the kernels
+    uint32_t stat_m1, stat_m2, stat_pos_pts, stat_toi;
 
     // layouts (words per dynamic body):
     //   17 full: pose/vel 0-5, q 6-7, p 8-9, cache 10-12, c0/a0/alpha0 13-16, walls, fat AABBs   (fused step, reset, k_post_events)
@@ -245,7 +247,7 @@ struct Sim {
           qoff(fdyn_ == 17 || fdyn_ == 13 ? 10 : (fdyn_ == 9 ? 6 : -1)),
           fa_off(fdyn_ == 17 ? k.nb * 17 + 24 : (fdyn_ == 11 ? k.nb * 11 : (fdyn_ == 10 ? k.nb * 10 : -1))),
           c0f(fdyn_ == 17 ? 13 : (fdyn_ == 11 ? 8 : -1)), wall_off(fdyn_ == 11 || fdyn_ == 10 ? -1 : k.nb * fdyn_), nc(0), goalc(0),
-          overflow(0) {}
+          overflow(0), stat_m1(0), stat_m2(0), stat_pos_pts(0), stat_toi(0) {}
 
     // ------------------------------------------------------------ memory helpers
     MRP_HD uint32_t& g(int w) { return G[(int64_t)w * N]; }
@@ -1101,6 +1103,7 @@ struct Sim {
             const int isl = (vm >> 16) & 0xff;
             const int ppc = (vm >> 10) & 3;
             if (!((done >> isl) & 1)) {
+                stat_pos_pts += (uint32_t)ppc;
                 const int bA = vm & 15, bB = (vm >> 4) & 15, type = (vm >> 12) & 1;
                 float mA = V(t, VC_MA), mB = V(t, VC_MB), iA = V(t, VC_IA), iB = V(t, VC_IB);
                 if (toi) {
@@ -1487,6 +1490,7 @@ struct Sim {
                         continue;
                     }
                     float t;
+                    ++stat_toi;
                     int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
                     if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
                     else alpha = 1.0f;

@@ -185,7 +185,7 @@ class VectorEnv:
         self.handle.set_state(words, begin)
 
     def episode_stats(self, reduce_across_ranks=True, reset=True):
-        """Episode statistics accumulated on the device; summed over ranks with one NCCL all-reduce of 8 doubles
+        """Episode statistics accumulated on the device; summed over ranks with one NCCL all-reduce of 16 doubles
         when torch.distributed is initialised (the only collective on this path — SURVEY.md §8e)."""
         out = reduce_stats(self.torch, self.stats_tensor, reduce_across_ranks, reset,
                            env_steps=(self._step_index - self._stats_step0) * self.num_envs)

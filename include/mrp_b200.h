@@ -55,11 +55,22 @@ typedef struct mrp_buffers {
     int32_t num_envs, obs_dim, act_dim, reserved;
 } mrp_buffers;
 
-/* stats_dev slots */
+/* stats_dev slots.  0-7: episode statistics.  8: envs whose body state became NaN / inf and were reset by force
+ * (SURVEY.md §5 / §8b "NaN guard counter"; such a step reports done = trunc = 1, reward 0).  9-14: workload counters
+ * of the steps since the last reset of the statistics, for the FLOP roofline of SURVEY.md §8d
+ * (F = F_fix + 700 P + 180 (81 m1 + 160 m2) + 64 sum(position points) + F_toi): */
 enum {
     MRP_STAT_EPISODES = 0, MRP_STAT_DONE_BY_ENV = 1, MRP_STAT_TRUNCATED = 2, MRP_STAT_SUM_RETURN = 3,
     MRP_STAT_SUM_RETURN_SQ = 4, MRP_STAT_SUM_LENGTH = 5, MRP_STAT_ENV_STEPS = 6, MRP_STAT_OVERFLOW = 7,
-    MRP_N_STATS = 8
+    MRP_STAT_NAN_RESETS = 8,
+    MRP_STAT_PAIRS = 9,        /* P: narrowphase (SAT + clip) evaluations actually run (culled pairs not counted) */
+    MRP_STAT_M1 = 10,          /* touching manifolds handed to the solver with one point ... */
+    MRP_STAT_M2 = 11,          /* ... and with two points (block solver): Box2D runs 180 sweeps over each */
+    MRP_STAT_VEL_FLOPS = 12,   /* velocity-sweep flops actually executed (81 / 160 per contact and sweep; early exit) */
+    MRP_STAT_POS_POINTS = 13,  /* manifold-point corrections executed by the position solver (64 flops each) */
+    MRP_STAT_TOI_CALLS = 14,   /* b2TimeOfImpact evaluations (culled sweeps not counted) */
+    MRP_STAT_RESERVED = 15,
+    MRP_N_STATS = 16
 };
 
 /* replaces: set_reward_params (mrp00:231-239, mrp02:216-225), update_goal (mrp02:232-233),

@@ -934,7 +934,11 @@ struct World {
     // workload probes (used to size the CUDA design; do not alter results)
     bool probe = false;
     long stat_islands = 0, stat_islands_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // histogram by #contacts (7 = 7+)
-    long stat_period[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long stat_period[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [p] = islands whose velocity sweeps enter a cycle of period p <= 8; [0]: 9..32
+    // position solver: islands, islands that use all iterations, and of those: state cycle of period 1 / 2 / 3..8 found, sum of
+    // the iteration at which it was found; iterations spent by all islands
+    long stat_pos_islands = 0, stat_pos_full = 0, stat_pos_cyc[3] = {0, 0, 0}, stat_pos_cyc_at = 0, stat_pos_iter_sum = 0;
+    long stat_vel_cyc_at = 0;   // sum over islands with a velocity cycle of period >= 2 of the sweep that closed it
     long stat_fix_iters = 0, stat_fix_never = 0, stat_contact_sum = 0, stat_touch_sum = 0, stat_steps = 0;
 
     ~World() { for (Contact* c : contactList) delete c; }
@@ -1562,8 +1566,8 @@ inline void World::SolveIsland(std::vector<int>& ibodies, std::vector<Contact*>&
         for (int i = 0; i < step.velocityIterations && fixed < 0; ++i) {
             s2.SolveVelocityConstraints();
             std::vector<char> cur = snap();
-            for (int p = 1; p <= 8 && p <= (int)hist.size(); ++p)
-                if (hist[hist.size() - p] == cur) { fixed = i + 1; ++stat_period[p]; break; }
+            for (int p = 1; p <= 32 && p <= (int)hist.size(); ++p)
+                if (hist[hist.size() - p] == cur) { fixed = i + 1; ++stat_period[p <= 8 ? p : 0]; if (p > 1) stat_vel_cyc_at += i + 1; break; }
             hist.push_back(cur);
         }
         if (fixed < 0) { ++stat_fix_never; stat_fix_iters += step.velocityIterations; } else stat_fix_iters += fixed;
@@ -1587,6 +1591,32 @@ inline void World::SolveIsland(std::vector<int>& ibodies, std::vector<Contact*>&
         a += h * w;
         positions[i].c = c; positions[i].a = a;
         velocities[i].v = v; velocities[i].w = w;
+    }
+    if (probe && !icontacts.empty()) {   // would the position iterations enter a bitwise cycle before they run out?
+        std::vector<Position> p2 = positions;
+        ContactSolver s2 = solver;
+        s2.positions = &p2;
+        std::vector<std::vector<char>> hist;
+        auto snap = [&]() { std::vector<char> b(sizeof(Position) * p2.size()); std::memcpy(b.data(), p2.data(), b.size()); return b; };
+        hist.push_back(snap());
+        int used = 0, cyc_p = 0, cyc_at = 0;
+        bool okay = false;
+        for (int i = 0; i < step.positionIterations; ++i) {
+            ++used;
+            okay = s2.SolvePositionConstraints();
+            if (okay) break;
+            std::vector<char> cur = snap();
+            if (!cyc_p)
+                for (int p = 1; p <= 8 && p <= (int)hist.size(); ++p)
+                    if (hist[hist.size() - p] == cur) { cyc_p = p; cyc_at = i + 1; break; }
+            hist.push_back(cur);
+        }
+        ++stat_pos_islands;
+        stat_pos_iter_sum += used;
+        if (!okay) {
+            ++stat_pos_full;
+            if (cyc_p) { ++stat_pos_cyc[cyc_p == 1 ? 0 : (cyc_p == 2 ? 1 : 2)]; stat_pos_cyc_at += cyc_at; }
+        }
     }
     for (int i = 0; i < step.positionIterations; ++i) {
         ++stat_pos_iters;

@@ -165,6 +165,20 @@ int orc_probe(void* h, int enable, double* out14, double* period9) {
     return 0;
 }
 
+// position-solver / long-cycle part of the workload probe: {pos islands, pos islands using all iterations, of those: cycle of
+// period 1, 2, 3..8 found, sum of the iteration it was found at, iterations of all islands, sum of closing sweeps of velocity cycles}
+int orc_probe_pos(void* h, double* out8) {
+    OrcBatch* b = (OrcBatch*)h;
+    for (int k = 0; k < 8; ++k) out8[k] = 0;
+    for (Env* e : b->envs) {
+        b2o::World* w = e->world;
+        out8[0] += w->stat_pos_islands; out8[1] += w->stat_pos_full;
+        out8[2] += w->stat_pos_cyc[0]; out8[3] += w->stat_pos_cyc[1]; out8[4] += w->stat_pos_cyc[2];
+        out8[5] += w->stat_pos_cyc_at; out8[6] += w->stat_pos_iter_sum; out8[7] += w->stat_vel_cyc_at;
+    }
+    return 0;
+}
+
 // ---- primitive-level probes for known-answer tests ---------------------------------
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
     orc::Philox4 r = orc::philox4x32_10(c0, c1, c2, c3, k0, k1);
