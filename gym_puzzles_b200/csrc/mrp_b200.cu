@@ -135,6 +135,22 @@ MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, 
     return T;
 }
 
+// phase 0+ (lane per env): k_front — broad classification of every contact; quiet envs (no contact needs SAT) run their
+// whole step here.  Returns Env::front_phase's code; *need = contacts to queue for k_narrow (code 2).
+MRP_HD int front_lane(const SimConst& K, float* sm, const float* ct, int64_t env, CMask* need) {
+    Env e(K, sm, ct, env, nullptr, 11);
+    float a[3 * MRP_MAX_AGENTS];
+    const float* arow = K.act + env * K.act_dim;
+    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+    e.load(false);
+    double r;
+    bool d;
+    const int code = e.front_phase(a, K.obs + env * K.obs_dim, &r, &d, need);
+    if (code == 0) finish_step(K, e, env, d, r);
+    else if (code == 1) K.toi_list[K.nloc - 1 - atomic_add_i32(&K.cnt[CNT_TOI_F], 1)] = (int32_t)env;
+    return code;
+}
+
 // phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
 struct VelTask {
     Sim::VelReg st;
@@ -153,7 +169,7 @@ MRP_HD uint32_t task_body_mask(const SimConst& K, Sim& s, int T) {
 MRP_HD void vel_task_begin(const SimConst& K, Sim& s, VelTask& vt, int task) {
     const int64_t env = K.task_env[task];
     vt.T = K.task_T[task];
-    s.G = K.S + env;
+    s.set_env(env);
     s.vcp = K.pool + (size_t)K.task_off[task] * VC_WORDS;
     vt.bodies = task_body_mask(K, s, vt.T);
     for (int b = 0; b < K.nb; ++b)
@@ -184,7 +200,7 @@ struct PosTask {
 MRP_HD void pos_task_begin(const SimConst& K, Sim& s, PosTask& pt, int task) {
     const int64_t env = K.task_env[task];
     pt.T = K.task_T[task];
-    s.G = K.S + env;
+    s.set_env(env);
     s.vcp = K.pool + (size_t)K.task_off[task] * VC_WORDS;
     pt.bodies = task_body_mask(K, s, pt.T);
     const float nan = s.__uint_as_float_(0x7fc00000u);
@@ -204,6 +220,54 @@ MRP_HD void pos_task_end(const SimConst& K, Sim& s, PosTask& pt) {
     for (int b = 0; b < K.nb; ++b)
         if ((pt.bodies >> b) & 1)
             for (int f = 0; f < 3; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
+}
+
+// Big islands (class 3: more than two contacts; 1.7 % of the islands of a Heavy-v0 rollout, but the longest dependent
+// chains of the step: up to T x 180 velocity trips and T x 60 position trips) are solved velocity AND position in one
+// go by k_solve_big, a small kernel that runs beside the bulk solver kernels.  The island's constraint records are
+// copied into the lane's block of shared memory first (T <= kBigT), so a trip costs shared-memory latency instead of an
+// L2 round trip for records the bulk kernels keep evicting from L1, and the bodies never leave shared memory between
+// the two solves.  Arithmetic and order are those of vel_task_* / pos_task_* (same Sim member functions).
+constexpr int kBigT = 6;                                // contact records kept in shared memory per lane
+constexpr int kBigLanes = 64;                           // lanes per CTA of k_solve_big
+constexpr int kBigRecWords = kBigT * VC_WORDS + 1;      // odd: the lanes' blocks start in different banks
+MRP_HD void big_task_lane(const SimConst& K, Sim& s, int task, float* rec, uint32_t& flops) {
+    VelTask vt;
+    vel_task_begin(K, s, vt, task);
+    if (vt.T <= kBigT) {
+        const float* src = s.vcp;
+        for (int i = 0; i < vt.T * VC_WORDS; ++i) rec[i] = src[i];
+        s.vcp = rec;
+    }
+    s.vr_begin(vt.st, vt.T, nullptr);
+    for (;;) {
+        vt.ops += (uint32_t)vt.st.vpc + 1u;
+        flops += vt.st.vpc == 2 ? 160u : 81u;
+        if (s.vr_trip_contact(vt.st, 180, nullptr)) break;
+    }
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&s.g(W_HINT), vt.ops);
+#else
+    s.g(W_HINT) += vt.ops;
+#endif
+    s.store_impulses(vt.T);
+    const float nan = s.__uint_as_float_(0x7fc00000u);
+    for (int b = 0; b < K.nb; ++b) {
+        if (!((vt.bodies >> b) & 1)) continue;
+        s.integrate_position(b, K.h);
+        s.set_rot_cache(b, Rot{0.0f, 1.0f}, nan);  // no rotation known for the freshly integrated angle
+    }
+    for (int k = 0; k < 4; ++k) {
+        s.B(K.nb + k, 0) = K.ctab[CT_WALLPOS + 2 * k];
+        s.B(K.nb + k, 1) = K.ctab[CT_WALLPOS + 2 * k + 1];
+        s.B(K.nb + k, 2) = 0.0f;
+    }
+    Sim::PosState ps;
+    s.pos_begin(ps);
+    while (!s.pos_trip<true>(ps, vt.T, 60, -1, -1)) {}
+    for (int b = 0; b < K.nb; ++b)
+        if ((vt.bodies >> b) & 1)
+            for (int f = 0; f < 6; ++f) s.gsf(K.w_body + kBodyWords * b + f, s.B(b, f));
 }
 
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
@@ -228,7 +292,7 @@ MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env
 // Constraint records of the fused per-env paths (fused step, TOI event pass, reset): a lane-local array in the default
 // build; the wide build (192 x 38 words) borrows the env's own slice of the task pool.  The solver records of a step are
 // bump-allocated from the start of the same pool (k_pre), so these paths must not run concurrently with k_solve_vel /
-// k_solve_pos of the same chunk: launch_overlapped() orders the wide build's event passes after the solver kernels.
+// k_solve_pos of the same chunk: launch_step() orders the wide build's event passes after the solver kernels.
 #ifdef MRP_WIDE
 #define MRP_VC_SCRATCH(K, env) float* vc_local = (K).pool + (size_t)((env) - (K).env0) * (K).maxc * VC_WORDS
 #else
@@ -262,12 +326,12 @@ MRP_HD void sample_actions_lane(const SimConst& K, float* dst, uint64_t step_ind
 
 MRP_HD void fix_rot_lane(const SimConst& K, int64_t env) {  // q = Rot(a) after a state upload
     for (int b = 0; b < K.nb; ++b) {
-        uint32_t* G = K.S + env;
+        uint32_t* G = env_words(K, env);
         union { uint32_t u; float f; } c;
-        c.u = G[(int64_t)(K.w_body + kBodyWords * b + 2) * K.N];
+        c.u = G[(K.w_body + kBodyWords * b + 2) << kTileShift];
         Rot q = rot_set(c.f);
-        c.f = q.s; G[(int64_t)(K.w_body + kBodyWords * b + 6) * K.N] = c.u;
-        c.f = q.c; G[(int64_t)(K.w_body + kBodyWords * b + 7) * K.N] = c.u;
+        c.f = q.s; G[(K.w_body + kBodyWords * b + 6) << kTileShift] = c.u;
+        c.f = q.c; G[(K.w_body + kBodyWords * b + 7) << kTileShift] = c.u;
     }
 }
 
@@ -299,6 +363,11 @@ __device__ __forceinline__ void tp_task(int id, unsigned long long t0, uint32_t 
 #define TP(x)
 #endif
 
+// this lane's column of the CTA's per-lane shared memory: every warp owns words_per_lane x 32 floats
+__device__ __forceinline__ float* lane_sm(float* base, int words_per_lane) {
+    return base + (threadIdx.x >> 5) * (words_per_lane * 32) + (threadIdx.x & 31);
+}
+
 __global__ void k_clear(int32_t* cnt) {
     if (threadIdx.x < CNT_N) cnt[threadIdx.x] = 0;
 }
@@ -311,7 +380,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ SimCons
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (loc >= K.nloc) return;
     const int64_t env = K.env0 + loc;
-    step_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    step_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, env);
 }
 
 __global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimConst K) {
@@ -321,7 +390,7 @@ __global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimCon
     const bool valid = loc < K.nloc;   // every lane of the warp stays for the warp-aggregated queue reservation
     const int64_t env = K.env0 + loc;
     CMask need = cm_none();
-    if (valid) need = broad_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    if (valid) need = broad_lane(K, lane_sm(smem + kCtPad, 10 * K.nb + 4 * K.ndynfix), ct, env);
     // one atomicAdd per warp instead of one per queued contact (they were 14 % of this kernel's stall samples)
     const int n = cm_count(need), lane = threadIdx.x & 31;
     int incl = n;
@@ -348,17 +417,47 @@ __global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimCo
         narrow_item(K, ct, K.narrow_list[i]);
 }
 
-// envs [loc0, loc1) of the chunk: mrp_step_host launches it in two halves so that the first half starts as soon as
-// its actions have arrived
-__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K, int64_t loc0, int64_t loc1) {
+// k_front: every env of the chunk.  Quiet envs finish their step here; the others are listed for k_narrow / k_pre.
+__global__ void __launch_bounds__(kBlock, 4) k_front(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
+    const float* ct = load_ctab(K, smem);
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = loc < K.nloc;   // every lane of the warp stays for the warp-aggregated queue reservations
+    const int64_t env = K.env0 + loc;
+    CMask need = cm_none();
+    int code = 0;
+    if (valid) code = front_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, &need);
+    const int n = cm_count(need), lane = threadIdx.x & 31;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned act_m = __ballot_sync(0xffffffffu, code == 2);
+    int base = 0, base_a = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&K.cnt[CNT_NARROW], total);
+    if (lane == 0 && act_m) base_a = atomicAdd(&K.cnt[CNT_ACTIVE], __popc(act_m));
+    base = __shfl_sync(0xffffffffu, base, 31);
+    base_a = __shfl_sync(0xffffffffu, base_a, 0);
+    if (n) push_narrow(K, env, need, base + incl - n);
+    if (code == 2) K.active_list[base_a + __popc(act_m & ((1u << lane) - 1u))] = (int32_t)env;
+}
+
+// by_list == 0: envs [loc0, loc1) of the chunk (mrp_step_host launches it in two halves so that the first half starts as
+// soon as its actions have arrived).  by_list == 1: the envs k_front listed as active (loc0 / loc1 unused).
+__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K, int64_t loc0, int64_t loc1, int by_list) {
+    extern __shared__ float smem[];
+    if (by_list) { loc0 = 0; loc1 = K.cnt[CNT_ACTIVE]; }
+    if (loc0 + (int64_t)blockIdx.x * kBlock >= loc1) return;
     const float* ct = load_ctab(K, smem);
     const int64_t loc = loc0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = loc < loc1;   // every lane of the warp stays for the warp-aggregated list reservation
-    const int64_t env = K.env0 + loc;
+    const int64_t env = !valid ? 0 : (by_list ? (int64_t)K.active_list[loc] : K.env0 + loc);
     int T = -1;
     uint32_t m12[2] = {0u, 0u};
-    if (valid) T = pre_lane(K, smem + kCtPad + threadIdx.x, ct, env, m12);
+    if (valid) T = pre_lane(K, lane_sm(smem + kCtPad, 13 * K.nb + 24), ct, env, m12);
     stat_add_warp(K.stats, MRP_STAT_M1, m12[0]);
     stat_add_warp(K.stats, MRP_STAT_M2, m12[1]);
     // envs without solver tasks are final already: k_post handles them while the solver kernels run (post_list)
@@ -435,11 +534,11 @@ __device__ __forceinline__ void solve_vel_class(const SimConst& K, Sim& s, uint3
 
 __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
-    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 6);
+    Sim s(K, lane_sm(smem, 6 * (K.nb + 4)), K.ctab, 0, nullptr, 6);
     // every warp serves one class at a time (uniform instruction stream); multi-contact islands first, they run longest
     uint32_t flops = 0u;
     TP(tp_begin(0); tp_begin(4); tp_begin(5); tp_begin(6); tp_begin(7);)
-    solve_vel_class<3>(K, s, flops);
+    if (!K.big_split) solve_vel_class<3>(K, s, flops);
     solve_vel_class<2>(K, s, flops);
     solve_vel_class<1>(K, s, flops);
     solve_vel_class<0>(K, s, flops);
@@ -447,9 +546,30 @@ __global__ void __launch_bounds__(kBlock) k_solve_vel(const __grid_constant__ Si
     TP(tp_end(0);)
 }
 
+// lane per big island, one task at a time; the lanes of a warp walk through velocity solve, then position solve together
+__global__ void __launch_bounds__(kBigLanes) k_solve_big(const __grid_constant__ SimConst K) {
+    extern __shared__ float smem[];
+    const int bw = 9 * K.nb + 24;
+    Sim s(K, lane_sm(smem, bw), K.ctab, 0, nullptr, 9);
+    float* rec = smem + (kBigLanes >> 5) * bw * 32 + threadIdx.x * kBigRecWords;
+    const int ntasks = task_count(K, 3);
+    uint32_t flops = 0u;
+    TP(tp_begin(7);)
+    for (;;) {
+        const int task = atomicAdd(&K.cnt[CNT_HEAD_V + 3], 1);
+        if (task >= ntasks) break;
+        TP(const unsigned long long tp_t0 = tp_now();)
+        big_task_lane(K, s, task_slot(K, 3, task), rec, flops);
+        TP(tp_task(7, tp_t0, (uint32_t)K.task_T[task_slot(K, 3, task)] << 16);)
+    }
+    TP(tp_end(7);)
+    stat_add_warp(K.stats, MRP_STAT_VEL_FLOPS, flops);
+    stat_add_warp(K.stats, MRP_STAT_POS_POINTS, s.stat_pos_pts);
+}
+
 __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ SimConst K) {
     extern __shared__ float smem[];
-    Sim s(K, smem + threadIdx.x, K.ctab, 0, nullptr, 9);
+    Sim s(K, lane_sm(smem, 9 * K.nb + 24), K.ctab, 0, nullptr, 9);
     const int ntasks = task_count_all(K);
     PosTask pt;
     bool busy = false, exhausted = false;
@@ -489,7 +609,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimC
     const float* ct = load_ctab(K, smem);
     if (loc >= count) return;
     const int64_t env = which == 2 ? K.env0 + loc : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
-    post_lane(K, smem + kCtPad + threadIdx.x, ct, env, false, nullptr, which == 0);
+    post_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, false, nullptr, which == 0);
 }
 
 // rare paths, grid-stride over their queues: envs with a TOI event this step; envs to auto-reset
@@ -503,7 +623,7 @@ __global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ 
         const int64_t env = K.toi_list[free_group ? K.nloc - 1 - i : i];
         MRP_VC_SCRATCH(K, env);
         TP(const unsigned long long tp_t0 = tp_now();)
-        post_lane(K, smem + kCtPad + threadIdx.x, ct, env, true, vc_local);
+        post_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, env, true, vc_local);
         TP(tp_task(2 + (free_group ? 1 : 0), tp_t0, 0u);)
     }
     TP(tp_end(2 + (free_group ? 1 : 0));)
@@ -515,7 +635,7 @@ __global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ S
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock)
-        reset_lane(K, smem + kCtPad + threadIdx.x, ct, K.reset_list[i]);
+        reset_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, K.reset_list[i]);
 }
 
 // mrp_step_host with a pinned, device-visible obs buffer: the rows of a chunk leave by cudaMemcpyAsync as soon as its k_post
@@ -543,7 +663,7 @@ __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ S
     int64_t env = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (env >= K.N) return;
     if (K.reset_mask && !K.reset_mask[env]) return;
-    reset_lane(K, smem + kCtPad + threadIdx.x, ct, env);
+    reset_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, env);
 }
 
 __global__ void k_sample_actions(const __grid_constant__ SimConst K, float* dst, uint64_t step_index) {
@@ -575,14 +695,16 @@ struct mrp_handle {
     float* act_dev;
     uint8_t* mask_dev;  // mrp_reset_host: staging buffer of the host mask (allocated on first use)
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
-    size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post;
+    int use_front;    // MRP_FRONT=1: k_front (quiet envs finish their step in the classification kernel) instead of k_broad + k_pre over all envs
+    size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post, smem_big;
+    int big_split;    // islands with more than two contacts go to k_solve_big on a side stream (MRP_BIG, default: from 32768 envs)
     int solver_ctas;  // persistent solver CTAs per SM
     int num_sms;      // multiprocessors of the handle's device (148 on B200); persistent / queue grids are sized from it
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cact, cact0, cpre, cfree, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks];
+    cudaEvent_t cfork, cact, cact0, cpre, cfree, cbig, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks];
     cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
     int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
     cudaEvent_t tr[32];        // MRP_TRACE=1: timeline of one mrp_step_host call (created on first use)
@@ -712,6 +834,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
         cudaEventDestroy(h->cact0);
         cudaEventDestroy(h->cpre);
         cudaEventDestroy(h->cfree);
+        cudaEventDestroy(h->cbig);
     }
 #else
     free(h->emu_sm);
@@ -733,6 +856,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.task_off);
     DEV_FREE(h->K.toi_list);
     DEV_FREE(h->K.post_list);
+    DEV_FREE(h->K.active_list);
     DEV_FREE(h->K.narrow_list);
     DEV_FREE((void*)h->K.eps_env);
     DEV_FREE((void*)h->K.decay_env);
@@ -779,6 +903,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
+    h->use_front = getenv("MRP_FRONT") ? atoi(getenv("MRP_FRONT")) : 0;
     h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
     if (h->solver_ctas < 1) h->solver_ctas = 1;
     // small batches are one chunk unless the environment variables say otherwise (tests exercise chunking that way)
@@ -800,7 +925,8 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
 #endif
     const size_t N = (size_t)cfg->num_envs;
     int rc = 0;
-    rc |= DEV_ALLOC(K.S, sizeof(uint32_t) * N * K.w_total);
+    const size_t ntiles = (N + kTile - 1) / kTile;   // state tiles of 32 envs (mrp_sim.cuh)
+    rc |= DEV_ALLOC(K.S, sizeof(uint32_t) * ntiles * kTile * K.w_total);
     rc |= DEV_ALLOC(h->ctab_dev, sizeof(float) * CT_WORDS);
     rc |= DEV_ALLOC(h->act_dev, sizeof(float) * N * K.act_dim);
     rc |= DEV_ALLOC(K.obs, sizeof(float) * N * K.obs_dim);
@@ -817,6 +943,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * kTaskClasses * N * K.nb);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC(K.post_list, sizeof(int32_t) * N);
+    rc |= DEV_ALLOC(K.active_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
@@ -828,15 +955,19 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     H2D(h->ctab_dev, ctab, sizeof(ctab));
     // episode counter starts at -1 so the first reset spawns episode 0; v0 goal is fixed
     {
-        uint32_t* row = (uint32_t*)malloc(sizeof(uint32_t) * N);
-        for (size_t i = 0; i < N; ++i) row[i] = 0xffffffffu;
-        H2D(K.S + (size_t)W_EPISODE * N, row, sizeof(uint32_t) * N);
         union { double d; uint32_t u[2]; } gx, gy;
         gx.d = K.goal_x0; gy.d = K.goal_y0;
-        const uint32_t vals[4] = {gx.u[0], gx.u[1], gy.u[0], gy.u[1]};
-        for (int w = 0; w < 4; ++w) {
-            for (size_t i = 0; i < N; ++i) row[i] = vals[w];
-            H2D(K.S + (size_t)(W_GOAL + w) * N, row, sizeof(uint32_t) * N);
+        const int words[5] = {W_EPISODE, W_GOAL, W_GOAL + 1, W_GOAL + 2, W_GOAL + 3};
+        const uint32_t vals[5] = {0xffffffffu, gx.u[0], gx.u[1], gy.u[0], gy.u[1]};
+        uint32_t* row = (uint32_t*)malloc(sizeof(uint32_t) * ntiles * kTile);
+        for (int w = 0; w < 5; ++w) {   // word w of every env: one 128-byte run per tile
+            for (size_t i = 0; i < ntiles * kTile; ++i) row[i] = vals[w];
+#ifndef MRP_HOST_EMU
+            cudaMemcpy2D(K.S + (size_t)words[w] * kTile, sizeof(uint32_t) * kTile * K.w_total, row, sizeof(uint32_t) * kTile,
+                         sizeof(uint32_t) * kTile, ntiles, cudaMemcpyHostToDevice);
+#else
+            for (size_t t = 0; t < ntiles; ++t) memcpy(K.S + t * kTile * K.w_total + (size_t)words[w] * kTile, row, sizeof(uint32_t) * kTile);
+#endif
         }
         free(row);
     }
@@ -846,15 +977,27 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
+    h->smem_big = sizeof(float) * ((size_t)(9 * K.nb + 24) + kBigRecWords) * kBigLanes;
+    h->big_split = getenv("MRP_BIG") ? atoi(getenv("MRP_BIG")) : (cfg->num_envs >= 32768 ? 1 : 0);
 #ifndef MRP_HOST_EMU
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
     cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
+    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
     for (auto fn : {k_step, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_post_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    // experiment knobs: shared-memory carve-out (percent of the SM's 228 KB) of the per-env kernels — what is not carved out
+    // is L1, which backs the lanes' local arrays (contact words, island order, actions)
+    if (getenv("MRP_CARVEOUT_PRE")) cudaFuncSetAttribute(k_pre, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_PRE")));
+    if (getenv("MRP_CARVEOUT_POST")) {
+        cudaFuncSetAttribute(k_post, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_POST")));
+        cudaFuncSetAttribute(k_front, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_POST")));
+    }
+    if (getenv("MRP_CARVEOUT_BROAD")) cudaFuncSetAttribute(k_broad, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_BROAD")));
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
     cudaFuncSetAttribute(k_solve_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pos);
+    cudaFuncSetAttribute(k_solve_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_big);
     cudaFuncSetAttribute(k_reset_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     {
         // earlier chunks get higher stream priority: their CTAs are scheduled first, so they finish first and their
@@ -878,6 +1021,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaEventCreateWithFlags(&h->cact0, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cpre, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cfree, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->cbig, cudaEventDisableTiming);
     {
         // measured at 1M envs: Heavy-v0 -4 %, v0 -1.5 %, v2 with 5 robots -5 %; v2 with its default two robots +9 % (hardly
         // any env owns a solver task there, so the split only adds launches): off for that case
@@ -1023,6 +1167,7 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
     K.narrow_list = K0.narrow_list + (size_t)b * K0.maxc;
     K.reset_list = K0.reset_list + b;
     K.post_list = K0.post_list + b;
+    K.active_list = K0.active_list + b;
     (void)h;
     return K;
 }
@@ -1051,17 +1196,17 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
         cudaStream_t s2 = h->cstream[1];
         cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(st, first_half_ready, 0);
-        k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half);
+        k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half, 0);
         if (tr) cudaEventRecord(tr[21], st);
         cudaStreamWaitEvent(s2, h->cpre, 0);
         cudaStreamWaitEvent(s2, actions_ready, 0);
-        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, s2>>>(K, half, K.nloc);
+        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, s2>>>(K, half, K.nloc, 0);
         cudaEventRecord(h->cfree, s2);
         cudaStreamWaitEvent(st, h->cfree, 0);
         h->launches += 1;
     } else {
         if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
-        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
+        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc, 0);
     }
     if (tr) cudaEventRecord(tr[22], st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
@@ -1070,21 +1215,6 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
     if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
     h->launches += 6;
-}
-static void launch_front_head(mrp_handle* h, const SimConst& K, cudaStream_t st) {
-    const unsigned grid = grid_for(K.nloc, kBlock);
-    k_clear<<<1, 32, 0, st>>>(K.cnt);
-    k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
-    k_narrow<<<grid < (unsigned)h->num_sms * 16u ? grid : (unsigned)h->num_sms * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
-    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
-    h->launches += 4;
-}
-static void launch_front_solvers(mrp_handle* h, const SimConst& K, cudaStream_t st) {
-    const unsigned grid = grid_for(K.nloc, kBlock);
-    const unsigned sgrid = grid < (unsigned)h->num_sms * (unsigned)h->solver_ctas ? grid : (unsigned)h->num_sms * (unsigned)h->solver_ctas;
-    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
-    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
-    h->launches += 2;
 }
 static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool clear, cudaEvent_t after_post = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
@@ -1102,33 +1232,82 @@ static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         h->launches += 1;
     }
 }
-// Whole-batch step with k_post split by k_pre's lists: envs without solver tasks (~60 %) are final after k_pre, so their
-// k_post runs on a second, low-priority stream beside k_solve_vel / k_solve_pos — kernels whose duration is set by the
-// serial tail of the longest islands, not by throughput — and only the envs with tasks are post-processed afterwards.
-static void launch_overlapped(mrp_handle* h, const SimConst& K, cudaStream_t st) {
+// mrp_step's pipeline.  k_front classifies every env and finishes the quiet ones (no contact needs SAT) outright;
+// k_narrow / k_pre / the solver kernels / k_post only see the others.  With `side` the k_post of listed envs that turned out
+// to own no solver task, and the TOI-event pass of the task-free group, run on a second stream beside the solver kernels.
+static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool side_ok) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
-    const unsigned pgrid = grid < (unsigned)h->num_sms * 8u ? grid : (unsigned)h->num_sms * 8u;
+    const unsigned nsm = (unsigned)h->num_sms;
+    const unsigned pgrid = grid < nsm * 8u ? grid : nsm * 8u;
+    const unsigned sgrid = grid < nsm * (unsigned)h->solver_ctas ? grid : nsm * (unsigned)h->solver_ctas;
+    const bool side_on = side_ok && h->overlap_post && !timed;
     cudaStream_t side = h->cstream[kMaxChunks - 1];
-    launch_front_head(h, K, st);
-    cudaEventRecord(h->cpre, st);
-    cudaStreamWaitEvent(side, h->cpre, 0);
-    k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
+    k_clear<<<1, 32, 0, st>>>(K.cnt);
+    if (timed) {
+        if (h->ev_n == 64) drain_timing(h);
+        cudaEventRecord(h->ev0[h->ev_n], st);
+    }
+    if (h->use_front) k_front<<<grid, kBlock, h->smem_post, st>>>(K);
+    else k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
+    k_narrow<<<grid < nsm * 16u ? grid : nsm * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
+    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc, h->use_front ? 1 : 0);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
+    if (side_on) {
+        cudaEventRecord(h->cpre, st);
+        cudaStreamWaitEvent(side, h->cpre, 0);
+        k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
 #ifndef MRP_WIDE
-    k_post_events<<<pgrid, kBlock, h->smem_bytes, side>>>(K, 1);
+        k_post_events<<<pgrid, kBlock, h->smem_bytes, side>>>(K, 1);
 #endif
-    cudaEventRecord(h->cfree, side);
-    launch_front_solvers(h, K, st);
+        cudaEventRecord(h->cfree, side);
+    }
+    // big islands: velocity + position solve in one small kernel on the high-priority stream, beside the bulk solver kernels
+    // (its CTAs are placed first, one per SM; the bulk kernels fill the rest of the SMs)
+    const bool big_on = h->big_split && !timed;
+    SimConst Ks = K;
+    Ks.big_split = big_on ? 1 : 0;
+    if (big_on) {
+        cudaStream_t sb = h->cstream[0];
+        if (!side_on) cudaEventRecord(h->cpre, st);
+        cudaStreamWaitEvent(sb, h->cpre, 0);
+        k_solve_big<<<nsm, kBigLanes, h->smem_big, sb>>>(Ks);
+        cudaEventRecord(h->cbig, sb);
+        h->launches += 1;
+    }
+    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(Ks);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
+    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(Ks);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
+    if (big_on) cudaStreamWaitEvent(st, h->cbig, 0);
+    if (!side_on && !h->use_front) {
+        // one stream: every env in order (coalesced rows instead of the gathers of the two lists)
+        k_post<<<grid, kBlock, h->smem_post, st>>>(K, 2);
+        if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
+        k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
+        if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+        h->launches += 8;
+        if (K.auto_reset) {
+            k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+            h->launches += 1;
+        }
+        return;
+    }
+    if (!side_on) k_post<<<grid, kBlock, h->smem_post, st>>>(K, 0);
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 1);
+    if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
     k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
-    cudaStreamWaitEvent(st, h->cfree, 0);
+    if (side_on) cudaStreamWaitEvent(st, h->cfree, 0);
 #ifdef MRP_WIDE
-    // wide build: the event pass borrows the env's slice of the task pool as constraint scratch (MRP_VC_SCRATCH), and
-    // k_pre bump-allocates the solver records of ALL envs from the start of that pool — so the task-free group's event
-    // pass may only run once the solver kernels have finished with the records (beside them it corrupted live records)
+    // wide build: the event pass borrows the env's slice of the task pool as constraint scratch (MRP_VC_SCRATCH), and k_pre
+    // bump-allocates the solver records of ALL envs from the start of that pool — so the task-free group's event pass runs
+    // here, after the solver kernels, never beside them
     k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 1);
+#else
+    if (!side_on) k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 1);
 #endif
-    h->launches += 4;
+    if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
+    h->launches += 10;
     if (K.auto_reset) {
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
@@ -1150,10 +1329,23 @@ static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, b
         h->launches += 3;
         return;
     }
-    launch_front(h, K, st, timed, nullptr);
-    launch_back(h, K, st, timed, false);
+    launch_step(h, K, st, timed, false);
 }
 #else
+static void emu_narrow(mrp_handle* h, const SimConst& K) {
+    const int nnarrow = K.cnt[CNT_NARROW];
+    K.stats[MRP_STAT_PAIRS] += nnarrow;
+    for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
+}
+static void emu_pre(mrp_handle* h, const SimConst& K, int64_t e) {
+    uint32_t m12[2] = {0u, 0u};
+    const int T = pre_lane(K, h->emu_sm, h->ctab_dev, e, m12);
+    K.stats[MRP_STAT_M1] += m12[0]; K.stats[MRP_STAT_M2] += m12[1];
+    if (T == 0) K.post_list[K.cnt[CNT_FREE]++] = (int32_t)e;
+    else K.post_list[K.nloc - 1 - K.cnt[CNT_BUSY]++] = (int32_t)e;
+}
+static void emu_solvers(mrp_handle* h, const SimConst& K);
+// mrp_step_host's front half (collide, setup, solvers over contiguous envs: k_broad, k_narrow, k_pre, solver kernels)
 static void run_front_emu(mrp_handle* h, const SimConst& K) {
     for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
     const int64_t e0 = K.env0, e1 = K.env0 + K.nloc;
@@ -1163,17 +1355,35 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
         const int n = cm_count(need);
         if (n) push_narrow(K, e, need, atomic_add_i32(&K.cnt[CNT_NARROW], n));
     }
-    const int nnarrow = K.cnt[CNT_NARROW];
-    K.stats[MRP_STAT_PAIRS] += nnarrow;
-    for (int i = 0; i < nnarrow; ++i) narrow_item(K, h->ctab_dev, K.narrow_list[i]);
-    for (int64_t e = e0; e < e1; ++e) {
-        uint32_t m12[2] = {0u, 0u};
-        const int T = pre_lane(K, h->emu_sm, h->ctab_dev, e, m12);
-        K.stats[MRP_STAT_M1] += m12[0]; K.stats[MRP_STAT_M2] += m12[1];
-        if (T == 0) K.post_list[K.cnt[CNT_FREE]++] = (int32_t)e;
-        else K.post_list[K.nloc - 1 - K.cnt[CNT_BUSY]++] = (int32_t)e;
+    emu_narrow(h, K);
+    for (int64_t e = e0; e < e1; ++e) emu_pre(h, K, e);
+    emu_solvers(h, K);
+}
+// mrp_step's front: k_front (quiet envs finish here), k_narrow, k_pre over the active list, solver kernels
+static void run_step_front_emu(mrp_handle* h, const SimConst& K) {
+    for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
+    for (int64_t e = K.env0; e < K.env0 + K.nloc; ++e) {
+        CMask need = cm_none();
+        if (front_lane(K, h->emu_sm, h->ctab_dev, e, &need) != 2) continue;
+        const int n = cm_count(need);
+        push_narrow(K, e, need, atomic_add_i32(&K.cnt[CNT_NARROW], n));
+        K.active_list[K.cnt[CNT_ACTIVE]++] = (int32_t)e;
     }
-    for (int cls = kTaskClasses - 1; cls >= 0; --cls) {
+    emu_narrow(h, K);
+    for (int i = 0; i < K.cnt[CNT_ACTIVE]; ++i) emu_pre(h, K, K.active_list[i]);
+    emu_solvers(h, K);
+}
+static void emu_solvers(mrp_handle* h, const SimConst& K0) {
+    SimConst K = K0;
+    K.big_split = h->big_split;
+    if (K.big_split) {   // k_solve_big: velocity + position solve of the islands with more than two contacts
+        static float rec[kBigRecWords];
+        uint32_t flops = 0u;
+        Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 9);
+        const int ntasks = task_count(K, 3);
+        for (int i = 0; i < ntasks; ++i) big_task_lane(K, s, task_slot(K, 3, i), rec, flops);
+    }
+    for (int cls = kTaskClasses - 1 - (K.big_split ? 1 : 0); cls >= 0; --cls) {
         const int ntasks = task_count(K, cls);
         for (int i = 0; i < ntasks; ++i) {
             Sim s(K, h->emu_sm, h->ctab_dev, 0, nullptr, 6);
@@ -1231,7 +1441,7 @@ static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
         }
         return;
     }
-    run_front_emu(h, K);
+    if (h->use_front) run_step_front_emu(h, K); else run_front_emu(h, K);
     run_back_emu(h, K, false, true);
 }
 #endif
@@ -1260,8 +1470,8 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (nch == 1 && h->overlap_post && !h->timing && !h->fused) {
-        launch_overlapped(h, chunk_const(h, K, 0, 1), st);
+    if (nch == 1 && !h->fused) {
+        launch_step(h, chunk_const(h, K, 0, 1), st, h->timing != 0, true);
     } else if (nch == 1) {
         launch_pipeline(h, chunk_const(h, K, 0, 1), st, h->timing != 0);
     } else {
@@ -1450,32 +1660,58 @@ int MRP_API(mrp_sample_actions)(mrp_handle* h, uint64_t step_index, float* dst_d
 }
 
 // ---- canonical state records <-> internal [word][env] layout (host side) --------------
+// buf is [word][count] (word-major over the requested envs); the device state is tiled [tile][word][32] (mrp_sim.cuh): whole
+// tiles covering the range travel as one contiguous copy and are re-ordered on the host
 static int fetch_internal(mrp_handle* h, int64_t begin, int64_t count, uint32_t* buf) {
     const SimConst& K = h->K;
+    if (count == 0) return 0;
+    const int64_t t0 = begin / kTile, t1 = (begin + count - 1) / kTile + 1;
+    const size_t tw = (size_t)kTile * K.w_total;
+    uint32_t* tiles = (uint32_t*)malloc(sizeof(uint32_t) * tw * (size_t)(t1 - t0));
+    if (!tiles) return -1;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpy2D(buf, sizeof(uint32_t) * count, K.S + begin, sizeof(uint32_t) * K.N, sizeof(uint32_t) * count, K.w_total,
-                     cudaMemcpyDeviceToHost) != cudaSuccess)
-        return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(tiles, K.S + tw * t0, sizeof(uint32_t) * tw * (size_t)(t1 - t0), cudaMemcpyDeviceToHost) != cudaSuccess) { free(tiles); return -1; }
 #else
-    for (int w = 0; w < K.w_total; ++w) memcpy(buf + (size_t)w * count, K.S + (size_t)w * K.N + begin, sizeof(uint32_t) * count);
+    memcpy(tiles, K.S + tw * t0, sizeof(uint32_t) * tw * (size_t)(t1 - t0));
 #endif
+    for (int64_t e = 0; e < count; ++e) {
+        const int64_t env = begin + e;
+        const uint32_t* src = tiles + (size_t)(env / kTile - t0) * tw + (env % kTile);
+        for (int w = 0; w < K.w_total; ++w) buf[(size_t)w * count + e] = src[(size_t)w * kTile];
+    }
+    free(tiles);
     return 0;
 }
 static int push_internal(mrp_handle* h, int64_t begin, int64_t count, const uint32_t* buf) {
     const SimConst& K = h->K;
+    if (count == 0) return 0;
+    const int64_t t0 = begin / kTile, t1 = (begin + count - 1) / kTile + 1;
+    const size_t tw = (size_t)kTile * K.w_total, bytes = sizeof(uint32_t) * tw * (size_t)(t1 - t0);
+    uint32_t* tiles = (uint32_t*)malloc(bytes);
+    if (!tiles) return -1;
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;   // steps queued on any stream finish before the state is replaced
-    if (cudaMemcpy2D(K.S + begin, sizeof(uint32_t) * K.N, buf, sizeof(uint32_t) * count, sizeof(uint32_t) * count, K.w_total,
-                     cudaMemcpyHostToDevice) != cudaSuccess)
-        return -1;
+    // steps queued on any stream finish before the state is replaced; envs of the edge tiles outside the range keep their words
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(tiles, K.S + tw * t0, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { free(tiles); return -1; }
+#else
+    memcpy(tiles, K.S + tw * t0, bytes);
+#endif
+    for (int64_t e = 0; e < count; ++e) {
+        const int64_t env = begin + e;
+        uint32_t* dst = tiles + (size_t)(env / kTile - t0) * tw + (env % kTile);
+        for (int w = 0; w < K.w_total; ++w) dst[(size_t)w * kTile] = buf[(size_t)w * count + e];
+    }
+#ifndef MRP_HOST_EMU
+    if (cudaMemcpy(K.S + tw * t0, tiles, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { free(tiles); return -1; }
+    free(tiles);
     k_fix_rot<<<grid_for(count, 128), 128>>>(K, begin, count);
     h->launches += 1;
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
 #else
-    for (int w = 0; w < K.w_total; ++w) memcpy(K.S + (size_t)w * K.N + begin, buf + (size_t)w * count, sizeof(uint32_t) * count);
+    memcpy(K.S + tw * t0, tiles, bytes);
+    free(tiles);
     for (int64_t e = 0; e < count; ++e) fix_rot_lane(K, begin + e);
 #endif
     return 0;

@@ -2,7 +2,7 @@
 // (reference mrp00:413-521 / mrp02:444-584 incl. b2World::Step(1/50, 180, 60)) for the
 // sm_100a kernels.  A warp advances a tile of 32 envs; every per-env array that is
 // indexed dynamically (bodies, fat AABBs) sits in shared memory in a lane-major layout
-// (word k of lane t at smem[k*blockDim + t]) so any divergent index is bank-conflict
+// (word k of lane t at warp_block[k*32 + t]) so any divergent index is bank-conflict
 // free; the contact cache stays in HBM in a coalesced [word][env] layout.
 //
 // Box2D semantics followed: SURVEY.md Appendix A (Collide / Solve / SolveTOI ordering,
@@ -18,7 +18,7 @@
 namespace mrp {
 
 #if defined(__CUDA_ARCH__)
-#define MRP_SS 128  // lanes per CTA == shared-memory lane stride
+#define MRP_SS 32   // shared-memory lane stride: every warp owns a block of words_per_lane x 32 floats (word k of lane t at k * 32 + t)
 #else
 #define MRP_SS 1
 #endif
@@ -96,7 +96,12 @@ constexpr int CT_SHAPEX = CT_SHAPES + 8 * kShapeWords;  // [8][6] bounding data 
 constexpr int CT_WALLBOX = CT_SHAPEX + 8 * 6;          // [4][4] wall polygons in world space (lo.x, lo.y, hi.x, hi.y), no radius
 constexpr int CT_WORDS = CT_WALLBOX + 16;
 
-// ---- internal per-env state words in HBM: S[word * N + env] ------------------------
+// ---- internal per-env state words in HBM ---------------------------------------------
+// Tiled [tile][word][lane]: envs are grouped in tiles of kTile = 32 (one warp of the per-env kernels); inside a tile
+// word w of lane l sits at w * 32 + l.  A warp's access to one word is one 128-byte line (as with a plain [word][env]
+// array), but the whole state of a tile is ONE contiguous block of w_total * 128 bytes: consecutive words are neighbouring
+// lines of the same DRAM page / TLB entry instead of N * 4 bytes apart, and the word stride is a compile-time constant
+// (offsets fold into the load / store instructions).
 constexpr int W_ELAPSED = 0, W_EPISODE = 1, W_INPLACE = 2, W_NC = 3, W_GOALC = 4, W_EPLEN = 5;
 constexpr int W_EPRET = 6;   // f64
 constexpr int W_GOAL = 8;    // 2 x f64
@@ -105,13 +110,15 @@ constexpr int W_DIST = 13;   // (n+1) x f64: agent_dist[0..n-1], block_dist
 // then bodies[nb][11] = {cx, cy, a, vx, vy, w, q.s, q.c, c0x, c0y, a0} (c0/a0: pose at the start of the step, written by
 // k_pre for k_post's SynchronizeFixtures); fat[ndynfix][4]; contacts[maxc][14]
 constexpr int kBodyWords = 11;
+constexpr int kTile = 32;          // envs per state tile
+constexpr int kTileShift = 5;
 
 struct SimConst {
     // variant
     int32_t variant, v2, n, nb, nfix, ndynfix, per_agent, maxc, obs_dim, act_dim, max_steps, auto_reset;
     int32_t w_body, w_aabb, w_con, w_total;  // word offsets of the internal state
     int32_t smem_words;                      // per-lane shared-memory words
-    int32_t pad0;
+    int32_t big_split;                       // 1: islands of class 3 (more than two contacts) are solved by k_solve_big, not by k_solve_vel / k_solve_pos
     // body classes
     float blk_mass, blk_invMass, blk_invI, blk_lcx, blk_lcy;
     float ag_mass, ag_invMass, ag_invI, ag_lcx, ag_lcy, ag_inertia;
@@ -125,7 +132,7 @@ struct SimConst {
     uint64_t seed, env_id_base;
     // memory
     uint32_t* S;
-    int64_t N;       // envs of the handle (stride of the [word][env] state)
+    int64_t N;       // envs of the handle
     int64_t env0;    // first env of the chunk this launch works on
     int32_t nloc;    // envs in the chunk (chunks are pipelined on separate streams; queues and counters are per chunk)
     int32_t pad1;
@@ -148,6 +155,7 @@ struct SimConst {
     uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * kMaxC + slot
     int32_t* post_list;    // [N] envs without solver tasks from slot 0 up, envs with tasks from the last slot down (k_pre):
                            // k_post of the former runs beside the solver kernels
+    int32_t* active_list;  // [N] envs with a contact that needs SAT (k_front): the ones k_pre works on
     // optional per-env curriculum vectors (NULL: the scalar mrp_params apply): update_goal / update_params per env
     const double* eps_env;       // [N] scaled_epsilon   (mrp02:232-233)
     const double* decay_env;     // [N] decay**(-timestep) (mrp02:227-230)
@@ -164,18 +172,23 @@ struct SimConst {
 constexpr int kTaskClasses = 4;
 enum { CNT_RESET = 0, CNT_POOL = 1, CNT_TOI = 2, CNT_NARROW = 3, CNT_HEAD_P = 4, CNT_TASKS = 8 /*[4] heavy*/, CNT_TASKS_LIGHT = 12 /*[4]*/,
        CNT_HEAD_V = 16 /*[4]*/, CNT_FREE = 20 /* envs without solver tasks */, CNT_BUSY = 21 /* envs with tasks */,
-       CNT_TOI_F = 22 /* TOI-event queue of the task-free group (filled from the end of toi_list) */, CNT_N = 23 };
+       CNT_TOI_F = 22 /* TOI-event queue of the task-free group (filled from the end of toi_list) */,
+       CNT_ACTIVE = 23 /* envs k_front hands to k_narrow / k_pre (active_list) */, CNT_N = 24 };
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
+// address of word 0 of env `env` (local index within the handle); word w is at [w * kTile]
+MRP_HD uint32_t* env_words(const SimConst& K, int64_t env) {
+    return K.S + (env >> kTileShift) * ((int64_t)K.w_total << kTileShift) + (env & (kTile - 1));
+}
 MRP_HD int task_count(const SimConst& K, int cls) { return K.cnt[CNT_TASKS + cls] + K.cnt[CNT_TASKS_LIGHT + cls]; }
 MRP_HD int task_slot(const SimConst& K, int cls, int i) {  // i-th task of a class in consumption order -> slot
     const int cap = K.nloc * K.nb;
     const int nh = K.cnt[CNT_TASKS + cls];
     return cls * cap + (i < nh ? i : cap - 1 - (i - nh));
 }
-MRP_HD int task_slot_any(const SimConst& K, int i) {  // i-th task over all classes, heaviest class first
-    for (int cls = kTaskClasses - 1; cls > 0; --cls) {
+MRP_HD int task_slot_any(const SimConst& K, int i) {  // i-th task over all classes, heaviest class first (class 3 left out under big_split)
+    for (int cls = kTaskClasses - 1 - (K.big_split ? 1 : 0); cls > 0; --cls) {
         const int n = task_count(K, cls);
         if (i < n) return task_slot(K, cls, i);
         i -= n;
@@ -184,7 +197,7 @@ MRP_HD int task_slot_any(const SimConst& K, int i) {  // i-th task over all clas
 }
 MRP_HD int task_count_all(const SimConst& K) {
     int n = 0;
-    for (int cls = 0; cls < kTaskClasses; ++cls) n += task_count(K, cls);
+    for (int cls = 0; cls < kTaskClasses - (K.big_split ? 1 : 0); ++cls) n += task_count(K, cls);
     return n;
 }
 
@@ -213,8 +226,8 @@ struct Sim {
     const SimConst& K;
     float* sm;          // this lane's shared-memory column
     const float* ct;    // CTA constant table (shared memory)
-    uint32_t* G;        // &S[env] (re-pointed per task in the solver kernels)
-    int64_t N;
+    uint32_t* G;        // word 0 of the env's state (re-pointed per task in the solver kernels)
+    int32_t env_i;      // env index within the handle
     uint64_t gid;
     // per-lane scratch (local memory where dynamically indexed)
     uint32_t meta[kMaxC];  // fa | fb<<8 | touching<<16 | type<<17 | pc<<18 | bA<<20 | bB<<24
@@ -243,14 +256,15 @@ struct Sim {
     //   13 k_pre: 0-9, cache 10-12, walls                     10 k_broad: 0-9, fat AABBs
     //    9 position solver: 0-5, cache 6-8, walls               6 velocity solver: 0-5, walls
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
-        : K(k), sm(sm_), ct(ct_), G(k.S + env), N(k.N), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
+        : K(k), sm(sm_), ct(ct_), G(env_words(k, env)), env_i((int32_t)env), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
           qoff(fdyn_ == 17 || fdyn_ == 13 ? 10 : (fdyn_ == 9 ? 6 : -1)),
           fa_off(fdyn_ == 17 ? k.nb * 17 + 24 : (fdyn_ == 11 ? k.nb * 11 : (fdyn_ == 10 ? k.nb * 10 : -1))),
           c0f(fdyn_ == 17 ? 13 : (fdyn_ == 11 ? 8 : -1)), wall_off(fdyn_ == 11 || fdyn_ == 10 ? -1 : k.nb * fdyn_), nc(0), goalc(0),
           overflow(0), stat_m1(0), stat_m2(0), stat_pos_pts(0), stat_toi(0) {}
 
     // ------------------------------------------------------------ memory helpers
-    MRP_HD uint32_t& g(int w) { return G[(int64_t)w * N]; }
+    MRP_HD uint32_t& g(int w) { return G[w << kTileShift]; }
+    MRP_HD void set_env(int64_t env) { G = env_words(K, env); env_i = (int32_t)env; }
     MRP_HD float gf(int w) { return __uint_as_float_(g(w)); }
     MRP_HD void gsf(int w, float v) { g(w) = __float_as_uint_(v); }
     MRP_HD double gd(int w) {
@@ -359,12 +373,12 @@ struct Sim {
     // ------------------------------------------------------------ state load / store
     // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
     // before their results are consumed, so each batch costs one memory round trip instead of one per word.
-    MRP_HD void load() {
+    MRP_HD void load(bool load_c0 = true) {
         nc = (int)g(W_NC);
         goalc = g(W_GOALC);
         // words a kernel's layout has no use for are not fetched: k_broad (10) needs pose and rotation only, k_pre (13)
         // writes the pre-step pose words itself
-        const bool want_vel = fdyn != 10, want_c0 = c0f >= 0;
+        const bool want_vel = fdyn != 10, want_c0 = c0f >= 0 && load_c0;
         for (int b = 0; b < K.nb; ++b) {
             const int w = K.w_body + kBodyWords * b;
             float r[kBodyWords];
@@ -537,6 +551,26 @@ struct Sim {
                 cm_set(need, k);
             }
             g(cw(k, 0)) = m;
+        }
+        return need;
+    }
+    // k_front's form of broad_phase(): the classification stays in the lane's meta[] (transient kMetaWas / kMetaDead bits set,
+    // as load() would deliver them to k_pre); nothing is written to the state.  Returns the contacts that need SAT.
+    MRP_HD CMask broad_classify() {
+        CMask need = cm_none();
+        for (int k = nc - 1; k >= 0; --k) {
+            uint32_t m = meta[k] & 0x0fffffffu;
+            if ((m >> 16) & 1) m |= kMetaWas;
+            const int fa = m & 0xff, fb = (m >> 8) & 0xff;
+            const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+            if (!overlap(fat(fa), fat(fb))) {
+                m |= kMetaDead;
+            } else if (manifold_provably_empty(fa, fb, bA, bB, body_xf(bA), body_xf(bB))) {
+                m &= 0xfff0ffffu | kMetaWas;  // pointCount 0, not touching
+            } else {
+                cm_set(need, k);
+            }
+            meta[k] = m;
         }
         return need;
     }
@@ -1538,11 +1572,10 @@ struct Sim {
 MRP_HD void narrow_item(const SimConst& K, const float* ct, uint32_t item) {
     const int64_t env = item / (uint32_t)kMaxC;
     const int k = (int)(item % (uint32_t)kMaxC);
-    uint32_t* G = K.S + env;
-    const int64_t N = K.N;
-    auto gw = [&](int w) -> uint32_t& { return G[(int64_t)w * N]; };
-    auto gfl = [&](int w) { union { uint32_t u; float f; } c; c.u = G[(int64_t)w * N]; return c.f; };
-    auto gsf = [&](int w, float v) { union { uint32_t u; float f; } c; c.f = v; G[(int64_t)w * N] = c.u; };
+    uint32_t* G = env_words(K, env);
+    auto gw = [&](int w) -> uint32_t& { return G[w << kTileShift]; };
+    auto gfl = [&](int w) { union { uint32_t u; float f; } c; c.u = G[w << kTileShift]; return c.f; };
+    auto gsf = [&](int w, float v) { union { uint32_t u; float f; } c; c.f = v; G[w << kTileShift] = c.u; };
     const int cwk = K.w_con + k * MRP_CONTACT_WORDS;
     uint32_t m = gw(cwk);
     const int fa = m & 0xff, fb = (m >> 8) & 0xff;

@@ -13,7 +13,7 @@ from gym_puzzles_b200 import abi
 
 N = int(os.environ.get("QB_ENVS", 1048576))
 env_id = sys.argv[1] if len(sys.argv) > 1 else "MultiRobotPuzzleHeavy-v0"
-os.environ.setdefault("MRP_OVERLAP_POST", "0")   # one stream: kernel boundaries are clean
+os.environ.setdefault("MRP_OVERLAP_POST", "0")   # no side-stream k_post: kernel boundaries are clean
 h = abi.Handle(env_id, N, seed=17)
 lib = h.lib.lib
 h.reset()
@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 KW = 8192
 buf = np.zeros((8, 2 + KW), dtype=np.uint64)
 lib.mrp_debug_tailprobe.argtypes = [C.c_int, C.c_void_p]
-names = ["k_solve_vel", "k_solve_pos", "k_post_events", "k_post_events(free)", "vel class 0", "vel class 1", "vel class 2", "vel class 3"]
+names = ["k_solve_vel", "k_solve_pos", "k_post_events", "k_post_events(free)", "vel class 0", "vel class 1", "vel class 2", "vel class 3 / k_solve_big"]
 for rep in range(3):
     lib.mrp_debug_tailprobe(0, None)
     h.sample_actions(1000 + rep)
