@@ -135,22 +135,6 @@ MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, 
     return T;
 }
 
-// phase 0+ (lane per env): k_front — broad classification of every contact; quiet envs (no contact needs SAT) run their
-// whole step here.  Returns Env::front_phase's code; *need = contacts to queue for k_narrow (code 2).
-MRP_HD int front_lane(const SimConst& K, float* sm, const float* ct, int64_t env, CMask* need) {
-    Env e(K, sm, ct, env, nullptr, 11);
-    float a[3 * MRP_MAX_AGENTS];
-    const float* arow = K.act + env * K.act_dim;
-    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
-    e.load(false);
-    double r;
-    bool d;
-    const int code = e.front_phase(a, K.obs + env * K.obs_dim, &r, &d, need);
-    if (code == 0) finish_step(K, e, env, d, r);
-    else if (code == 1) K.toi_list[K.nloc - 1 - atomic_add_i32(&K.cnt[CNT_TOI_F], 1)] = (int32_t)env;
-    return code;
-}
-
 // phase 2a (lane per task): 180 velocity sweeps (early exit), StoreImpulses, position integration
 struct VelTask {
     Sim::VelReg st;
@@ -272,13 +256,31 @@ MRP_HD void big_task_lane(const SimConst& K, Sim& s, int task, float* rec, uint3
 
 // phase 3 (lane per env): transforms, broadphase, TOI, obs / reward / done, TimeLimit.  With allow_events ==
 // false an env whose TOI scan finds an event is queued for the event pass and left untouched.
+#ifdef MRP_TAILPROBE
+// per-env breakdown of the event pass: {total, inside time_of_impact, inside toi_event} cycles, TOI calls, events
+__device__ unsigned long long g_tp_evrec[65536][5];
+__device__ unsigned int g_tp_evn;
+#endif
 MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local,
                       bool free_group = false) {
     Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 11);
+#if defined(MRP_TAILPROBE) && defined(__CUDA_ARCH__)
+    const long long tp_c0 = clock64();
+#endif
     e.load();
     double r;
     bool d;
-    if (!e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events)) {
+    const bool fin = e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events);
+#if defined(MRP_TAILPROBE) && defined(__CUDA_ARCH__)
+    if (allow_events) {
+        const unsigned int i = atomicAdd(&g_tp_evn, 1u);
+        if (i < 65536u) {
+            g_tp_evrec[i][0] = (unsigned long long)(clock64() - tp_c0); g_tp_evrec[i][1] = (unsigned long long)e.tp_toi_clk;
+            g_tp_evrec[i][2] = (unsigned long long)e.tp_evt_clk; g_tp_evrec[i][3] = e.stat_toi; g_tp_evrec[i][4] = (unsigned long long)e.tp_evt_n;
+        }
+    }
+#endif
+    if (!fin) {
         // deferred to the event pass; the task-free group has its own queue (end of toi_list, downwards) so that its
         // events can be processed beside the solver kernels as well
         if (free_group) K.toi_list[K.nloc - 1 - atomic_add_i32(&K.cnt[CNT_TOI_F], 1)] = (int32_t)env;
@@ -417,44 +419,14 @@ __global__ void __launch_bounds__(kBlock) k_narrow(const __grid_constant__ SimCo
         narrow_item(K, ct, K.narrow_list[i]);
 }
 
-// k_front: every env of the chunk.  Quiet envs finish their step here; the others are listed for k_narrow / k_pre.
-__global__ void __launch_bounds__(kBlock, 4) k_front(const __grid_constant__ SimConst K) {
+// envs [loc0, loc1) of the chunk: mrp_step_host launches it in two halves so that the first half starts as soon as
+// its actions have arrived
+__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K, int64_t loc0, int64_t loc1) {
     extern __shared__ float smem[];
-    const float* ct = load_ctab(K, smem);
-    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = loc < K.nloc;   // every lane of the warp stays for the warp-aggregated queue reservations
-    const int64_t env = K.env0 + loc;
-    CMask need = cm_none();
-    int code = 0;
-    if (valid) code = front_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, &need);
-    const int n = cm_count(need), lane = threadIdx.x & 31;
-    int incl = n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned act_m = __ballot_sync(0xffffffffu, code == 2);
-    int base = 0, base_a = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(&K.cnt[CNT_NARROW], total);
-    if (lane == 0 && act_m) base_a = atomicAdd(&K.cnt[CNT_ACTIVE], __popc(act_m));
-    base = __shfl_sync(0xffffffffu, base, 31);
-    base_a = __shfl_sync(0xffffffffu, base_a, 0);
-    if (n) push_narrow(K, env, need, base + incl - n);
-    if (code == 2) K.active_list[base_a + __popc(act_m & ((1u << lane) - 1u))] = (int32_t)env;
-}
-
-// by_list == 0: envs [loc0, loc1) of the chunk (mrp_step_host launches it in two halves so that the first half starts as
-// soon as its actions have arrived).  by_list == 1: the envs k_front listed as active (loc0 / loc1 unused).
-__global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst K, int64_t loc0, int64_t loc1, int by_list) {
-    extern __shared__ float smem[];
-    if (by_list) { loc0 = 0; loc1 = K.cnt[CNT_ACTIVE]; }
-    if (loc0 + (int64_t)blockIdx.x * kBlock >= loc1) return;
     const float* ct = load_ctab(K, smem);
     const int64_t loc = loc0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = loc < loc1;   // every lane of the warp stays for the warp-aggregated list reservation
-    const int64_t env = !valid ? 0 : (by_list ? (int64_t)K.active_list[loc] : K.env0 + loc);
+    const int64_t env = K.env0 + loc;
     int T = -1;
     uint32_t m12[2] = {0u, 0u};
     if (valid) T = pre_lane(K, lane_sm(smem + kCtPad, 13 * K.nb + 24), ct, env, m12);
@@ -695,7 +667,6 @@ struct mrp_handle {
     float* act_dev;
     uint8_t* mask_dev;  // mrp_reset_host: staging buffer of the host mask (allocated on first use)
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
-    int use_front;    // MRP_FRONT=1: k_front (quiet envs finish their step in the classification kernel) instead of k_broad + k_pre over all envs
     size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post, smem_big;
     int big_split;    // islands with more than two contacts go to k_solve_big on a side stream (MRP_BIG, default: from 32768 envs)
     int solver_ctas;  // persistent solver CTAs per SM
@@ -856,7 +827,6 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.task_off);
     DEV_FREE(h->K.toi_list);
     DEV_FREE(h->K.post_list);
-    DEV_FREE(h->K.active_list);
     DEV_FREE(h->K.narrow_list);
     DEV_FREE((void*)h->K.eps_env);
     DEV_FREE((void*)h->K.decay_env);
@@ -903,7 +873,6 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
-    h->use_front = getenv("MRP_FRONT") ? atoi(getenv("MRP_FRONT")) : 0;
     h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
     if (h->solver_ctas < 1) h->solver_ctas = 1;
     // small batches are one chunk unless the environment variables say otherwise (tests exercise chunking that way)
@@ -943,7 +912,6 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.task_off, sizeof(int32_t) * kTaskClasses * N * K.nb);
     rc |= DEV_ALLOC(K.toi_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC(K.post_list, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.active_list, sizeof(int32_t) * N);
     rc |= DEV_ALLOC_RAW(K.narrow_list, sizeof(uint32_t) * N * K.maxc);
     if (rc) {
         fail(-7, "mrp_create: device allocation failed: %s", dev_err());
@@ -983,7 +951,6 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
     cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
-    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
     for (auto fn : {k_step, k_reset_list})
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_post_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
@@ -992,7 +959,6 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (getenv("MRP_CARVEOUT_PRE")) cudaFuncSetAttribute(k_pre, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_PRE")));
     if (getenv("MRP_CARVEOUT_POST")) {
         cudaFuncSetAttribute(k_post, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_POST")));
-        cudaFuncSetAttribute(k_front, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_POST")));
     }
     if (getenv("MRP_CARVEOUT_BROAD")) cudaFuncSetAttribute(k_broad, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MRP_CARVEOUT_BROAD")));
     cudaFuncSetAttribute(k_solve_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_vel);
@@ -1167,7 +1133,6 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
     K.narrow_list = K0.narrow_list + (size_t)b * K0.maxc;
     K.reset_list = K0.reset_list + b;
     K.post_list = K0.post_list + b;
-    K.active_list = K0.active_list + b;
     (void)h;
     return K;
 }
@@ -1196,17 +1161,17 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
         cudaStream_t s2 = h->cstream[1];
         cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(st, first_half_ready, 0);
-        k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half, 0);
+        k_pre<<<grid_for(half, kBlock), kBlock, h->smem_pre, st>>>(K, 0, half);
         if (tr) cudaEventRecord(tr[21], st);
         cudaStreamWaitEvent(s2, h->cpre, 0);
         cudaStreamWaitEvent(s2, actions_ready, 0);
-        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, s2>>>(K, half, K.nloc, 0);
+        k_pre<<<grid_for(K.nloc - half, kBlock), kBlock, h->smem_pre, s2>>>(K, half, K.nloc);
         cudaEventRecord(h->cfree, s2);
         cudaStreamWaitEvent(st, h->cfree, 0);
         h->launches += 1;
     } else {
         if (actions_ready) cudaStreamWaitEvent(st, actions_ready, 0);
-        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc, 0);
+        k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
     }
     if (tr) cudaEventRecord(tr[22], st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
@@ -1232,9 +1197,11 @@ static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         h->launches += 1;
     }
 }
-// mrp_step's pipeline.  k_front classifies every env and finishes the quiet ones (no contact needs SAT) outright;
-// k_narrow / k_pre / the solver kernels / k_post only see the others.  With `side` the k_post of listed envs that turned out
-// to own no solver task, and the TOI-event pass of the task-free group, run on a second stream beside the solver kernels.
+static void launch_events(mrp_handle* h, const SimConst& K, cudaStream_t st, unsigned pgrid, int free_group) {
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, free_group);
+}
+// mrp_step's pipeline.  With `side_ok` (and overlap_post) the k_post of the envs that own no solver task, and the TOI-event
+// pass of that group, run on a second, low-priority stream beside the solver kernels.
 static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool side_ok) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
@@ -1248,17 +1215,16 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
     }
-    if (h->use_front) k_front<<<grid, kBlock, h->smem_post, st>>>(K);
-    else k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
+    k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
     k_narrow<<<grid < nsm * 16u ? grid : nsm * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
-    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc, h->use_front ? 1 : 0);
+    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
     if (side_on) {
         cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(side, h->cpre, 0);
         k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
 #ifndef MRP_WIDE
-        k_post_events<<<pgrid, kBlock, h->smem_bytes, side>>>(K, 1);
+        launch_events(h, K, side, pgrid, 1);
 #endif
         cudaEventRecord(h->cfree, side);
     }
@@ -1280,11 +1246,11 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(Ks);
     if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
     if (big_on) cudaStreamWaitEvent(st, h->cbig, 0);
-    if (!side_on && !h->use_front) {
+    if (!side_on) {
         // one stream: every env in order (coalesced rows instead of the gathers of the two lists)
         k_post<<<grid, kBlock, h->smem_post, st>>>(K, 2);
         if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
-        k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
+        launch_events(h, K, st, pgrid, 0);
         if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
         h->launches += 8;
         if (K.auto_reset) {
@@ -1296,15 +1262,15 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     if (!side_on) k_post<<<grid, kBlock, h->smem_post, st>>>(K, 0);
     k_post<<<grid, kBlock, h->smem_post, st>>>(K, 1);
     if (timed) cudaEventRecord(h->evk[h->ev_n][3], st);
-    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 0);
+    launch_events(h, K, st, pgrid, 0);
     if (side_on) cudaStreamWaitEvent(st, h->cfree, 0);
 #ifdef MRP_WIDE
     // wide build: the event pass borrows the env's slice of the task pool as constraint scratch (MRP_VC_SCRATCH), and k_pre
     // bump-allocates the solver records of ALL envs from the start of that pool — so the task-free group's event pass runs
     // here, after the solver kernels, never beside them
-    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 1);
+    launch_events(h, K, st, pgrid, 1);
 #else
-    if (!side_on) k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K, 1);
+    if (!side_on) launch_events(h, K, st, pgrid, 1);
 #endif
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     h->launches += 10;
@@ -1357,20 +1323,6 @@ static void run_front_emu(mrp_handle* h, const SimConst& K) {
     }
     emu_narrow(h, K);
     for (int64_t e = e0; e < e1; ++e) emu_pre(h, K, e);
-    emu_solvers(h, K);
-}
-// mrp_step's front: k_front (quiet envs finish here), k_narrow, k_pre over the active list, solver kernels
-static void run_step_front_emu(mrp_handle* h, const SimConst& K) {
-    for (int i = 0; i < CNT_N; ++i) K.cnt[i] = 0;
-    for (int64_t e = K.env0; e < K.env0 + K.nloc; ++e) {
-        CMask need = cm_none();
-        if (front_lane(K, h->emu_sm, h->ctab_dev, e, &need) != 2) continue;
-        const int n = cm_count(need);
-        push_narrow(K, e, need, atomic_add_i32(&K.cnt[CNT_NARROW], n));
-        K.active_list[K.cnt[CNT_ACTIVE]++] = (int32_t)e;
-    }
-    emu_narrow(h, K);
-    for (int i = 0; i < K.cnt[CNT_ACTIVE]; ++i) emu_pre(h, K, K.active_list[i]);
     emu_solvers(h, K);
 }
 static void emu_solvers(mrp_handle* h, const SimConst& K0) {
@@ -1441,7 +1393,7 @@ static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
         }
         return;
     }
-    if (h->use_front) run_step_front_emu(h, K); else run_front_emu(h, K);
+    run_front_emu(h, K);
     run_back_emu(h, K, false, true);
 }
 #endif
@@ -1897,6 +1849,8 @@ int mrp_debug_tailprobe(int what, unsigned long long* out) {
         cudaMemset(p, 0, sizeof(unsigned long long) * kTpKernels * kTpWarps);
         cudaGetSymbolAddress((void**)&p, g_tp_maxtask);
         cudaMemset(p, 0, sizeof(unsigned long long) * kTpKernels);
+        unsigned int zero = 0;
+        cudaMemcpyToSymbol(g_tp_evn, &zero, sizeof(zero));
         return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
     }
     cudaDeviceSynchronize();
@@ -1910,6 +1864,19 @@ int mrp_debug_tailprobe(int what, unsigned long long* out) {
                              sizeof(unsigned long long) * kTpWarps * k);
     }
     return 0;
+}
+#endif
+
+#if defined(MRP_TAILPROBE) && !defined(MRP_WIDE) && !defined(MRP_HOST_EMU)
+// event-pass records of the last step: returns their number, copies up to cap records of 5 words
+int mrp_debug_event_records(unsigned long long* out, int cap) {
+    cudaDeviceSynchronize();
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_tp_evn, sizeof(n));
+    if (n > 65536u) n = 65536u;
+    const int m = (int)n < cap ? (int)n : cap;
+    cudaMemcpyFromSymbol(out, g_tp_evrec, sizeof(unsigned long long) * 5 * (size_t)m);
+    return (int)n;
 }
 #endif
 

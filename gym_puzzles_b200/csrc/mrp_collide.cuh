@@ -152,7 +152,10 @@ MRP_HD Xf sweep_xf(const Sweep& s, float beta) {  // b2Sweep::GetTransform
     Xf xf;
     xf.p = (1.0f - beta) * s.c0 + beta * s.c;
     float angle = (1.0f - beta) * s.a0 + beta * s.a;
-    xf.q = rot_set(angle);
+    // static bodies (the walls: a0 = a = 0) need no sincos: sin(+-0) = +-0, cos(0) = 1 exactly.  Half of the b2Rot::Set
+    // evaluations inside b2TimeOfImpact are of this kind (every TOI pair here is dynamic-vs-static).
+    if (angle == 0.0f) { xf.q.s = angle; xf.q.c = 1.0f; }
+    else xf.q = rot_set(angle);
     V2 r = rmul(xf.q, s.lc);
     xf.p = xf.p - r;
     return xf;

@@ -392,44 +392,6 @@ struct Env : Sim {
         for (int k = 0; k < nc; ++k) g(cw(k, 0)) = meta[k];
         return T;
     }
-    // k_front: Collide's broad half for every env and, for an env none of whose contacts needs SAT (no contact can be
-    // touching: ~60 % of the envs of a rollout), the WHOLE step in one go — control, contact events, integration,
-    // SynchronizeFixtures, FindNewContacts, TOI scan, observation, reward — with one state load and one store.
-    // Layout: k_post's (11 words per body).  Returns 0: step finished (caller runs finish_step with *reward / *done_env),
-    // 1: quiet env whose TOI scan needs the event pass (state handed off exactly as k_pre would have left it),
-    // 2: active env: classified contact words written for k_narrow / k_pre, *need = contacts to queue for k_narrow.
-    MRP_HD int front_phase(const float* a, float* obs, double* reward, bool* done_env, CMask* need) {
-        *need = broad_classify();
-        if (cm_any(*need)) {
-            for (int k = 0; k < nc; ++k) g(cw(k, 0)) = meta[k];
-            return 2;
-        }
-        if (K.v2) control_v2(a); else control_v0(a);
-        finish_collide();
-        for (int b = 0; b < K.nb; ++b) {   // pose at the start of the step (xf1 of SynchronizeFixtures, TOI sweeps)
-            BX(b, c0f) = B(b, 0); BX(b, c0f + 1) = B(b, 1); BX(b, c0f + 2) = B(b, 2);
-            integrate_position(b, K.h);
-        }
-        g(W_HINT) = 0;
-        const int nc_solved = nc;
-        for (int b = 0; b < K.nb; ++b) set_rot_cache(b, Rot{BX(b, 6), BX(b, 7)}, BX(b, c0f + 2));
-        if (!post_solve(false)) {
-            // hand-off for k_post_events, which redoes the tail of the step from the state k_pre would have stored: poses and
-            // velocities after integration, the pre-step pose, the contact list after Collide.  The rotation words and the fat
-            // AABBs of the state still hold their pre-step values (post_solve only touched the copies in shared memory).
-            g(W_NC) = (uint32_t)nc_solved;
-            g(W_GOALC) = goalc;
-            for (int b = 0; b < K.nb; ++b) {
-                const int w = K.w_body + kBodyWords * b;
-                for (int f = 0; f < 6; ++f) gsf(w + f, B(b, f));
-                gsf(w + 8, BX(b, c0f)); gsf(w + 9, BX(b, c0f + 1)); gsf(w + 10, BX(b, c0f + 2));
-            }
-            for (int k = 0; k < nc_solved; ++k) g(cw(k, 0)) = meta[k];
-            return 1;
-        }
-        *done_env = post_step(obs, reward);
-        return 0;
-    }
     // k_post: the step after the solver — transforms, broadphase, TOI, obs / reward / done.
     // Returns false (nothing stored) when a TOI event is needed and allow_events is false.
     MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events) {

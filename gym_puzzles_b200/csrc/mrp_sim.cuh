@@ -155,7 +155,6 @@ struct SimConst {
     uint32_t* narrow_list; // [N * maxc] contacts that need SAT + clipping this step: env * kMaxC + slot
     int32_t* post_list;    // [N] envs without solver tasks from slot 0 up, envs with tasks from the last slot down (k_pre):
                            // k_post of the former runs beside the solver kernels
-    int32_t* active_list;  // [N] envs with a contact that needs SAT (k_front): the ones k_pre works on
     // optional per-env curriculum vectors (NULL: the scalar mrp_params apply): update_goal / update_params per env
     const double* eps_env;       // [N] scaled_epsilon   (mrp02:232-233)
     const double* decay_env;     // [N] decay**(-timestep) (mrp02:227-230)
@@ -172,8 +171,7 @@ struct SimConst {
 constexpr int kTaskClasses = 4;
 enum { CNT_RESET = 0, CNT_POOL = 1, CNT_TOI = 2, CNT_NARROW = 3, CNT_HEAD_P = 4, CNT_TASKS = 8 /*[4] heavy*/, CNT_TASKS_LIGHT = 12 /*[4]*/,
        CNT_HEAD_V = 16 /*[4]*/, CNT_FREE = 20 /* envs without solver tasks */, CNT_BUSY = 21 /* envs with tasks */,
-       CNT_TOI_F = 22 /* TOI-event queue of the task-free group (filled from the end of toi_list) */,
-       CNT_ACTIVE = 23 /* envs k_front hands to k_narrow / k_pre (active_list) */, CNT_N = 24 };
+       CNT_TOI_F = 22 /* TOI-event queue of the task-free group (filled from the end of toi_list) */, CNT_N = 23 };
 // transient meta bits used between k_broad, k_narrow and k_pre (cleared again by k_pre)
 constexpr uint32_t kMetaWas = 1u << 29, kMetaDead = 1u << 30;
 constexpr uint32_t kHeavyHint = 120;
@@ -248,6 +246,17 @@ struct Sim {
     uint32_t overflow;
     // workload counters of this lane (MRP_STAT_M1 / M2 / POS_POINTS / TOI_CALLS): summed per warp by the kernels
     uint32_t stat_m1, stat_m2, stat_pos_pts, stat_toi;
+#ifdef MRP_TAILPROBE
+    long long tp_toi_clk = 0, tp_evt_clk = 0;   // cycles inside time_of_impact / toi_event of this lane
+    int tp_evt_n = 0;
+    static MRP_HD long long tp_clock() {
+#if defined(__CUDA_ARCH__)
+        return clock64();
+#else
+        return 0;
+#endif
+    }
+#endif
 
     // layouts (words per dynamic body):
     //   17 full: pose/vel 0-5, q 6-7, p 8-9, cache 10-12, c0/a0/alpha0 13-16, walls, fat AABBs   (fused step, reset, k_post_events)
@@ -373,12 +382,12 @@ struct Sim {
     // ------------------------------------------------------------ state load / store
     // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
     // before their results are consumed, so each batch costs one memory round trip instead of one per word.
-    MRP_HD void load(bool load_c0 = true) {
+    MRP_HD void load() {
         nc = (int)g(W_NC);
         goalc = g(W_GOALC);
         // words a kernel's layout has no use for are not fetched: k_broad (10) needs pose and rotation only, k_pre (13)
         // writes the pre-step pose words itself
-        const bool want_vel = fdyn != 10, want_c0 = c0f >= 0 && load_c0;
+        const bool want_vel = fdyn != 10, want_c0 = c0f >= 0;
         for (int b = 0; b < K.nb; ++b) {
             const int w = K.w_body + kBodyWords * b;
             float r[kBodyWords];
@@ -551,26 +560,6 @@ struct Sim {
                 cm_set(need, k);
             }
             g(cw(k, 0)) = m;
-        }
-        return need;
-    }
-    // k_front's form of broad_phase(): the classification stays in the lane's meta[] (transient kMetaWas / kMetaDead bits set,
-    // as load() would deliver them to k_pre); nothing is written to the state.  Returns the contacts that need SAT.
-    MRP_HD CMask broad_classify() {
-        CMask need = cm_none();
-        for (int k = nc - 1; k >= 0; --k) {
-            uint32_t m = meta[k] & 0x0fffffffu;
-            if ((m >> 16) & 1) m |= kMetaWas;
-            const int fa = m & 0xff, fb = (m >> 8) & 0xff;
-            const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
-            if (!overlap(fat(fa), fat(fb))) {
-                m |= kMetaDead;
-            } else if (manifold_provably_empty(fa, fb, bA, bB, body_xf(bA), body_xf(bB))) {
-                m &= 0xfff0ffffu | kMetaWas;  // pointCount 0, not touching
-            } else {
-                cm_set(need, k);
-            }
-            meta[k] = m;
         }
         return need;
     }
@@ -1496,46 +1485,74 @@ struct Sim {
         for (;;) {
             int minK = -1;
             float minAlpha = 1.0f;
-            for (int k = nc - 1; k >= 0; --k) {
-                if (!cm_test(enabled, k)) continue;
-                if (toiCount[k] > kMaxSubSteps) continue;
-                float alpha = 1.0f;
-                if (cm_test(toiFlag, k)) {
-                    alpha = toi[k];
-                } else {
-                    uint32_t m = meta[k];
-                    int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
-                    if (is_dyn(bA) && is_dyn(bB)) continue;
-                    // b2World::SolveTOI first aligns the two sweeps to the larger alpha0 (a side effect that later contacts
-                    // of the same bodies see, walls included), then calls b2TimeOfImpact
-                    float al0 = alpha0(bA);
-                    if (alpha0(bA) < alpha0(bB)) {
-                        al0 = alpha0(bB);
-                        sweep_advance(bA, al0);
-                    } else if (alpha0(bB) < alpha0(bA)) {
+            // The scan walks the contacts newest first, as b2World::SolveTOI does.  It is written as "walk down to the next
+            // contact that needs a b2TimeOfImpact evaluation (cheap), then evaluate it" so that the lanes of a warp make their
+            // n-th evaluation in the same trip of the outer loop: with the evaluation inside the contact loop every lane called
+            // it at its own trip count and the warp ran the (3 k instruction) calls one lane after the other.
+            int k = nc - 1;
+            for (;;) {
+                int kt = -1;
+                float al0 = 0.0f;
+#pragma unroll 1
+                for (; k >= 0; --k) {
+                    if (!cm_test(enabled, k)) continue;
+                    if (toiCount[k] > kMaxSubSteps) continue;
+                    float alpha;
+                    if (cm_test(toiFlag, k)) {
+                        alpha = toi[k];
+                    } else {
+                        const uint32_t m = meta[k];
+                        const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
+                        if (is_dyn(bA) && is_dyn(bB)) continue;
+                        // b2World::SolveTOI first aligns the two sweeps to the larger alpha0 (a side effect that later contacts
+                        // of the same bodies see, walls included), then calls b2TimeOfImpact
                         al0 = alpha0(bA);
-                        sweep_advance(bB, al0);
-                    }
-                    // fixture A is the dynamic one (walls are the last fixtures).  The culling bound covers every
-                    // intermediate pose of the sweep swept[] was computed for, hence also an advanced remainder of it
-                    if (toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) {
+                        if (alpha0(bA) < alpha0(bB)) {
+                            al0 = alpha0(bB);
+                            sweep_advance(bA, al0);
+                        } else if (alpha0(bB) < alpha0(bA)) {
+                            al0 = alpha0(bA);
+                            sweep_advance(bB, al0);
+                        }
+                        // fixture A is the dynamic one (walls are the last fixtures).  The culling bound covers every
+                        // intermediate pose of the sweep swept[] was computed for, hence also an advanced remainder of it
+                        if (!toi_provably_one((int)(m & 0xff), bA, bB - K.nb)) { kt = k; break; }
+                        alpha = 1.0f;
                         toi[k] = 1.0f;
                         cm_set(toiFlag, k);
-                        continue;
                     }
+                    if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
+                }
+                if (kt < 0) break;
+                {
+                    const uint32_t m = meta[kt];
+                    const int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
                     float t;
                     ++stat_toi;
-                    int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
-                    if (st == kToiTouching) alpha = fmin2(al0 + (1.0f - al0) * t, 1.0f);
-                    else alpha = 1.0f;
-                    toi[k] = alpha;
-                    cm_set(toiFlag, k);
+#ifdef MRP_TAILPROBE
+                    const long long tp_c0 = tp_clock();
+#endif
+                    const int st = time_of_impact(&t, fix_shape(m & 0xff), body_sweep(bA), fix_shape((m >> 8) & 0xff), body_sweep(bB));
+#ifdef MRP_TAILPROBE
+                    tp_toi_clk += tp_clock() - tp_c0;
+#endif
+                    const float alpha = st == kToiTouching ? fmin2(al0 + (1.0f - al0) * t, 1.0f) : 1.0f;
+                    toi[kt] = alpha;
+                    cm_set(toiFlag, kt);
+                    if (alpha < minAlpha) { minK = kt; minAlpha = alpha; }
                 }
-                if (alpha < minAlpha) { minK = k; minAlpha = alpha; }
+                k = kt - 1;
             }
             if (minK < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
             if (!allow_events) return false;
+#ifdef MRP_TAILPROBE
+            const long long tp_c1 = tp_clock();
+#endif
             toi_event(minK, minAlpha, toiFlag, enabled);
+#ifdef MRP_TAILPROBE
+            tp_evt_clk += tp_clock() - tp_c1;
+            ++tp_evt_n;
+#endif
         }
         return true;
     }

@@ -42,4 +42,21 @@ for rep in range(3):
         info = mx & 0xffffff
         print(f"{name:20s} warps {len(rel):5d}  finish us: p10 {q(.10):7.1f} p50 {q(.5):7.1f} p90 {q(.9):7.1f} p99 {q(.99):7.1f} max {rel[-1]:7.1f}"
               f" | longest task {(mx >> 24) / 1e3:7.1f} us (T {info >> 16}, sweeps {info & 0xffff})")
+    # event pass: per-env breakdown (SM cycles)
+    rec = np.zeros((65536, 5), dtype=np.uint64)
+    lib.mrp_debug_event_records.argtypes = [C.c_void_p, C.c_int]
+    n = lib.mrp_debug_event_records(rec.ctypes.data_as(C.c_void_p), 65536)
+    r = rec[:min(n, 65536)].astype(np.float64)
+    if len(r):
+        mhz = 1965.0
+        ev = r[:, 4] > 0
+        for name, sel in (("candidates only", ~ev), ("with events", ev)):
+            x = r[sel]
+            if len(x) == 0:
+                continue
+            order = np.argsort(x[:, 0])
+            top = x[order[-max(1, len(x) // 100):]]
+            print(f"  events pass, envs {name}: {len(x)}  mean total {x[:, 0].mean() / mhz:6.1f} us (TOI {x[:, 1].mean() / mhz:6.1f} us in {x[:, 3].mean():.1f} calls, "
+                  f"toi_event {x[:, 2].mean() / mhz:6.1f} us in {x[:, 4].mean():.1f} events) | slowest 1 %: total {top[:, 0].mean() / mhz:6.1f} us, TOI {top[:, 1].mean() / mhz:6.1f} us "
+                  f"in {top[:, 3].mean():.1f} calls, toi_event {top[:, 2].mean() / mhz:6.1f} us in {top[:, 4].mean():.1f} events")
 h.close()
