@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <new>
 
 #ifndef MRP_MAXC
@@ -1210,7 +1211,12 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     const unsigned sgrid = grid < nsm * (unsigned)h->solver_ctas ? grid : nsm * (unsigned)h->solver_ctas;
     const bool side_on = side_ok && h->overlap_post && !timed;
     cudaStream_t side = h->cstream[kMaxChunks - 1];
+    // MRP_TRACE=1: timeline of the step (events on every stream, printed after a device synchronise; debugging aid)
+    const bool trace = getenv("MRP_TRACE") != nullptr;
+    if (trace && !h->tr_init) { for (int i = 0; i < 32; ++i) cudaEventCreate(&h->tr[i]); h->tr_init = 1; }
+    auto mark = [&](int i, cudaStream_t s_) { if (trace) cudaEventRecord(h->tr[i], s_); };
     k_clear<<<1, 32, 0, st>>>(K.cnt);
+    mark(0, st);
     if (timed) {
         if (h->ev_n == 64) drain_timing(h);
         cudaEventRecord(h->ev0[h->ev_n], st);
@@ -1218,6 +1224,7 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     k_broad<<<grid, kBlock, h->smem_broad, st>>>(K);
     k_narrow<<<grid < nsm * 16u ? grid : nsm * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K);
     k_pre<<<grid, kBlock, h->smem_pre, st>>>(K, 0, K.nloc);
+    mark(1, st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
     if (side_on) {
         cudaEventRecord(h->cpre, st);
@@ -1238,12 +1245,15 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         if (!side_on) cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(sb, h->cpre, 0);
         k_solve_big<<<nsm, kBigLanes, h->smem_big, sb>>>(Ks);
+        mark(4, sb);
         cudaEventRecord(h->cbig, sb);
         h->launches += 1;
     }
     k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(Ks);
+    mark(5, st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
     k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(Ks);
+    mark(6, st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
     if (big_on) cudaStreamWaitEvent(st, h->cbig, 0);
     if (!side_on) {
@@ -1278,8 +1288,22 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
         h->launches += 1;
     }
-}
-static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
+    mark(9, st);
+    if (trace && side_on) {
+        cudaDeviceSynchronize();
+        static const char* nm[10] = {"start", "pre", "post_free", "events_free", "big", "vel", "pos", "post_busy", "events_busy", "end"};
+        int32_t c[CNT_N];
+        cudaMemcpy(c, K.cnt, sizeof(c), cudaMemcpyDeviceToHost);
+        printf("[mrp trace] ms since start:");
+        for (int i = 1; i <= 9; ++i) {
+            float ms = 0.0f;
+            if ((i == 4 && !big_on) || cudaEventElapsedTime(&ms, h->tr[0], h->tr[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+            printf(" %s %.3f", nm[i], ms);
+        }
+        printf(" | envs free %d busy %d, TOI queue %d + %d (free), big islands %d\n", c[CNT_FREE], c[CNT_BUSY], c[CNT_TOI], c[CNT_TOI_F],
+               c[CNT_TASKS + 3] + c[CNT_TASKS_LIGHT + 3]);
+    }
+}static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
     if (h->fused) {  // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
         const unsigned grid = grid_for(K.nloc, kBlock);
         if (grid == 0) return;

@@ -380,30 +380,58 @@ struct Sim {
     MRP_HD float& alpha0(int b) { return b < K.nb ? (fdyn == 11 ? alpha_none : BX(b, c0f + 3)) : wallAlpha0[b - K.nb]; }
 
     // ------------------------------------------------------------ state load / store
-    // Loads are issued in batches of independent requests (all words of a body, two fixtures, four contact heads)
-    // before their results are consumed, so each batch costs one memory round trip instead of one per word.
+    // Device: the body and fat-AABB words go from the state straight into the lane's shared-memory column with cp.async
+    // (LDGSTS, 4 bytes each): no register is tied up waiting, so ALL of them are in flight at once and the load phase costs
+    // one memory round trip (plus one for the contact heads, whose count has to arrive first) instead of one per body /
+    // fixture pair.  Host build: plain copies.
+#if defined(__CUDA_ARCH__)
+    static __device__ __forceinline__ void cp_word(float* dst_smem, const uint32_t* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+    }
+    static __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+#else
+    static void cp_word(float* dst, const uint32_t* src) { union { uint32_t u; float f; } c; c.u = *src; *dst = c.f; }
+    static void cp_wait() {}
+#endif
     MRP_HD void load() {
-        nc = (int)g(W_NC);
-        goalc = g(W_GOALC);
         // words a kernel's layout has no use for are not fetched: k_broad (10) needs pose and rotation only, k_pre (13)
         // writes the pre-step pose words itself
         const bool want_vel = fdyn != 10, want_c0 = c0f >= 0;
         for (int b = 0; b < K.nb; ++b) {
-            const int w = K.w_body + kBodyWords * b;
-            float r[kBodyWords];
-#pragma unroll
-            for (int i = 0; i < kBodyWords; ++i)
-                r[i] = ((i >= 3 && i <= 5 && !want_vel) || (i >= 8 && !want_c0)) ? 0.0f : gf(w + i);
+            const uint32_t* src = &g(K.w_body + kBodyWords * b);
             float* p = bp(b);
 #pragma unroll
-            for (int f = 0; f < 6; ++f) p[f * MRP_SS] = r[f];
-            p[6 * MRP_SS] = r[6]; p[7 * MRP_SS] = r[7];
-            if (c0f >= 0) { p[c0f * MRP_SS] = r[8]; p[(c0f + 1) * MRP_SS] = r[9]; p[(c0f + 2) * MRP_SS] = r[10]; }  // pre-step pose
-            set_rot_cache(b, Rot{r[6], r[7]}, r[2]);
+            for (int i = 0; i < 8; ++i)
+                if (i < 3 || i > 5 || want_vel) cp_word(p + i * MRP_SS, src + (i << kTileShift));
+            if (want_c0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cp_word(p + (c0f + i) * MRP_SS, src + ((8 + i) << kTileShift));  // pre-step pose
+            }
+        }
+        for (int f = 0; fa_off >= 0 && f < K.ndynfix; ++f) {
+            const uint32_t* src = &g(K.w_aabb + 4 * f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_word(&FA(f, i), src + (i << kTileShift));
+        }
+        nc = (int)g(W_NC);
+        goalc = g(W_GOALC);
+        for (int k = 0; k < nc; k += 4) {
+            uint32_t r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = k + i < nc ? g(cw(k + i, 0)) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (k + i < nc) meta[k + i] = r[i];
+        }
+        cp_wait();
+        for (int b = 0; b < K.nb; ++b) {
+            float* p = bp(b);
+            if (!want_vel) { p[3 * MRP_SS] = 0.0f; p[4 * MRP_SS] = 0.0f; p[5 * MRP_SS] = 0.0f; }
+            const Rot q{p[6 * MRP_SS], p[7 * MRP_SS]};
+            set_rot_cache(b, q, p[2 * MRP_SS]);
             if (fdyn != 11) {
-                V2 rc = rmul(Rot{r[6], r[7]}, localCenter(b));
-                p[8 * MRP_SS] = r[0] - rc.x;
-                p[9 * MRP_SS] = r[1] - rc.y;
+                V2 rc = rmul(q, localCenter(b));
+                p[8 * MRP_SS] = p[0] - rc.x;
+                p[9 * MRP_SS] = p[MRP_SS] - rc.y;
             }
         }
         for (int k = 0; wall_off >= 0 && k < 4; ++k) {
@@ -411,25 +439,6 @@ struct Sim {
             B(b, 0) = ct[CT_WALLPOS + 2 * k];
             B(b, 1) = ct[CT_WALLPOS + 2 * k + 1];
             B(b, 2) = 0.0f; B(b, 3) = 0.0f; B(b, 4) = 0.0f; B(b, 5) = 0.0f;
-        }
-        for (int f = 0; fa_off >= 0 && f < K.ndynfix; f += 2) {
-            float r[8];
-            const bool two = f + 1 < K.ndynfix;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = (i < 4 || two) ? gf(K.w_aabb + 4 * f + i) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) FA(f, i) = r[i];
-            if (two) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) FA(f + 1, i) = r[4 + i];
-            }
-        }
-        for (int k = 0; k < nc; k += 4) {
-            uint32_t r[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[i] = k + i < nc ? g(cw(k + i, 0)) : 0u;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (k + i < nc) meta[k + i] = r[i];
         }
     }
     MRP_HD void store() {
