@@ -339,8 +339,62 @@ inline int ClipSegmentToLine(ClipVertex vOut[2], const ClipVertex vIn[2], Vec2 n
     return numOut;
 }
 
+// Version fork: 0 = Box2D >= 2.3.1 (what box2d-py >= 2.3.5 tracks; the default and what the CUDA
+// kernels implement), 1 = Box2D 2.3.0: hill-climbing b2FindMaxSeparation from the edge facing the other centroid, and the
+// reference-face choice `sepB > 0.98 * sepA + 0.001`.  The switch exists to MEASURE what the unpinned choice can cost
+// (tests/test_box2d_forks.py): how many env-steps of a rollout change when the other fork is taken.
+inline int g_fork_230 = 0;
+
+// Box2D 2.3.0 b2EdgeSeparation: separation of poly2 from edge1 of poly1 along that edge's normal
+inline float EdgeSeparation230(const Polygon* p1, const Transform& xf1, int edge1, const Polygon* p2, const Transform& xf2) {
+    Vec2 normal1World = Mul(xf1.q, p1->n[edge1]);
+    Vec2 normal1 = MulT(xf2.q, normal1World);
+    int index = 0;
+    float minDot = FLT_MAX;
+    for (int i = 0; i < p2->count; ++i) {
+        float d = Dot(p2->v[i], normal1);
+        if (d < minDot) { minDot = d; index = i; }
+    }
+    Vec2 v1 = Mul(xf1, p1->v[edge1]);
+    Vec2 v2 = Mul(xf2, p2->v[index]);
+    return Dot(v2 - v1, normal1World);
+}
+// Box2D 2.3.0 b2FindMaxSeparation: start at the edge whose normal best faces the other polygon's centroid, then walk
+// in the improving direction while the separation strictly improves
+inline float FindMaxSeparation230(int* edgeIndex, const Polygon* p1, const Transform& xf1, const Polygon* p2, const Transform& xf2) {
+    int count1 = p1->count;
+    Vec2 d = Mul(xf2, p2->centroid) - Mul(xf1, p1->centroid);
+    Vec2 dLocal1 = MulT(xf1.q, d);
+    int edge = 0;
+    float maxDot = -FLT_MAX;
+    for (int i = 0; i < count1; ++i) {
+        float dt = Dot(p1->n[i], dLocal1);
+        if (dt > maxDot) { maxDot = dt; edge = i; }
+    }
+    float s = EdgeSeparation230(p1, xf1, edge, p2, xf2);
+    int prevEdge = edge - 1 >= 0 ? edge - 1 : count1 - 1;
+    float sPrev = EdgeSeparation230(p1, xf1, prevEdge, p2, xf2);
+    int nextEdge = edge + 1 < count1 ? edge + 1 : 0;
+    float sNext = EdgeSeparation230(p1, xf1, nextEdge, p2, xf2);
+    int bestEdge, increment;
+    float bestSeparation;
+    if (sPrev > s && sPrev > sNext) { increment = -1; bestEdge = prevEdge; bestSeparation = sPrev; }
+    else if (sNext > s) { increment = 1; bestEdge = nextEdge; bestSeparation = sNext; }
+    else { *edgeIndex = edge; return s; }
+    for (;;) {
+        if (increment == -1) edge = bestEdge - 1 >= 0 ? bestEdge - 1 : count1 - 1;
+        else edge = bestEdge + 1 < count1 ? bestEdge + 1 : 0;
+        s = EdgeSeparation230(p1, xf1, edge, p2, xf2);
+        if (s > bestSeparation) { bestEdge = edge; bestSeparation = s; }
+        else break;
+    }
+    *edgeIndex = bestEdge;
+    return bestSeparation;
+}
+
 // >=2.3.1 brute-force form
 inline float FindMaxSeparation(int* edgeIndex, const Polygon* p1, const Transform& xf1, const Polygon* p2, const Transform& xf2) {
+    if (g_fork_230) return FindMaxSeparation230(edgeIndex, p1, xf1, p2, xf2);
     int count1 = p1->count, count2 = p2->count;
     Transform xf = MulT(xf2, xf1);
     int bestIndex = 0;
@@ -390,7 +444,7 @@ inline void CollidePolygons(Manifold* manifold, const Polygon* polyA, const Tran
     int edge1;
     uint8_t flip;
     const float k_tol = 0.1f * kLinearSlop;
-    if (separationB > separationA + k_tol) {
+    if (g_fork_230 ? separationB > 0.98f * separationA + 0.001f : separationB > separationA + k_tol) {
         poly1 = polyB; poly2 = polyA; xf1 = xfB; xf2 = xfA; edge1 = edgeB;
         manifold->type = kFaceB; flip = 1;
     } else {

@@ -130,6 +130,21 @@ int b2s_load_state(void* h, int n_dyn, const float* bodies6, int n_dynfix, const
     w->LoadState(n_dyn, bodies6, n_dynfix, fat4, nc, contacts14);
     return 0;
 }
+// contact k of the world's contact list (head first): {fixtureA, fixtureB, touching, pointCount, then per point
+// localPoint.x, localPoint.y, normalImpulse, tangentImpulse}; returns the number of contacts.  For the known-answer tests
+// (pybox2d: world.contacts[k].manifold.points[j].normalImpulse).
+int b2s_contact_get(void* h, int k, float* out12) {
+    World* w = S(h)->w;
+    if (k >= 0 && k < (int)w->contactList.size()) {
+        const Contact* c = w->contactList[k];
+        out12[0] = (float)c->fA; out12[1] = (float)c->fB; out12[2] = c->touching ? 1.0f : 0.0f; out12[3] = (float)c->manifold.pointCount;
+        for (int j = 0; j < 2; ++j) {
+            const ManifoldPoint& p = c->manifold.points[j];
+            out12[4 + 4 * j] = p.localPoint.x; out12[5 + 4 * j] = p.localPoint.y; out12[6 + 4 * j] = p.normalImpulse; out12[7 + 4 * j] = p.tangentImpulse;
+        }
+    }
+    return (int)w->contactList.size();
+}
 long b2s_toi_events(void* h) { return S(h)->w->stat_toi_events; }
 
 // the Philox stream the oracle / product spawn from, so the harness can feed the reference's np.random.uniform and

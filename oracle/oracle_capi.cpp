@@ -179,6 +179,13 @@ int orc_probe_pos(void* h, double* out8) {
     return 0;
 }
 
+// Box2D version fork of the collision routine (b2core.hpp g_fork_230): 0 = >= 2.3.1 (default), 1 = 2.3.0.  Process-wide.
+int orc_set_box2d_fork(int fork_230) {
+    int old = b2o::g_fork_230;
+    b2o::g_fork_230 = fork_230 ? 1 : 0;
+    return old;
+}
+
 // ---- primitive-level probes for known-answer tests ---------------------------------
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
     orc::Philox4 r = orc::philox4x32_10(c0, c1, c2, c3, k0, k1);

@@ -34,6 +34,7 @@ _L.b2s_world_vector.argtypes = [_p, _i, _f, _f, _p]
 _L.b2s_step.argtypes = [_p, _f, _i, _i, _p, _i]
 _L.b2s_toi_events.argtypes = [_p]
 _L.b2s_load_state.argtypes = [_p, _i, _p, _i, _p, _i, _p]
+_L.b2s_contact_get.argtypes = [_p, _i, _p]
 _L.b2s_toi_events.restype = C.c_long
 _L.b2s_uniform53.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
 _L.b2s_uniform53.restype = C.c_double
@@ -292,6 +293,20 @@ class b2World:
     @property
     def toi_events(self):
         return int(_L.b2s_toi_events(self._h))
+
+    @property
+    def contacts(self):
+        """list of dicts, contact-list order (pybox2d: world.contacts / contact.manifold.points[j].normalImpulse)"""
+        buf = (C.c_float * 12)()
+        n = _L.b2s_contact_get(self._h, 0, buf)
+        out = []
+        for k in range(n):
+            _L.b2s_contact_get(self._h, k, buf)
+            pc = int(buf[3])
+            out.append(dict(fixtureA=int(buf[0]), fixtureB=int(buf[1]), touching=bool(buf[2]), pointCount=pc,
+                            points=[dict(localPoint=(buf[4 + 4 * j], buf[5 + 4 * j]), normalImpulse=buf[6 + 4 * j], tangentImpulse=buf[7 + 4 * j])
+                                    for j in range(pc)]))
+        return out
 
     def load_state(self, bodies6, fat4, contacts14):
         """harness only (no pybox2d counterpart): see b2s_load_state in oracle/b2shim_capi.cpp"""
