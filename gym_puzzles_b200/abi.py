@@ -26,7 +26,7 @@ EXPORTS = (
     "mrp_last_error", "mrp_backend", "mrp_create", "mrp_destroy", "mrp_get_layout", "mrp_get_buffers", "mrp_reset",
     "mrp_step", "mrp_step_host", "mrp_reset_host", "mrp_sample_actions", "mrp_get_state", "mrp_set_state",
     "mrp_set_params", "mrp_get_params", "mrp_get_stats", "mrp_set_timing", "mrp_get_timing", "mrp_get_phase_timing", "mrp_launch_count",
-    "mrp_enable_terminal_info", "mrp_enable_curriculum",
+    "mrp_enable_terminal_info", "mrp_enable_curriculum", "mrp_obs_v3",
 )
 
 
@@ -95,6 +95,7 @@ class MrpLib:
         L.mrp_get_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
         L.mrp_get_phase_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.mrp_launch_count.argtypes = [C.c_void_p]
+        L.mrp_obs_v3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mrp_launch_count.restype = C.c_int64
 
     @property
@@ -222,6 +223,10 @@ class Handle:
         e, d = C.c_void_p(), C.c_void_p()
         self.lib.check(self.lib.lib.mrp_enable_curriculum(self.h, C.byref(e), C.byref(d)), "mrp_enable_curriculum")
         return e.value, d.value
+
+    def obs_v3(self, out_ptr, stream=None):
+        """normalised MultiRobotPuzzle-v3 observation head (core.py:289-350) into f32[num_envs][4 n + 19] at out_ptr"""
+        self.lib.check(self.lib.lib.mrp_obs_v3(self.h, out_ptr, stream), "mrp_obs_v3")
 
     def stats(self, reset_after=False):
         s = np.zeros(N_STATS, dtype=np.float64)

@@ -327,6 +327,43 @@ MRP_HD void sample_actions_lane(const SimConst& K, float* dst, uint64_t step_ind
         dst[env * K.act_dim + k] = (float)(-1.0 + 2.0 * uniform53(K.seed, kStreamAction, gid, (uint32_t)step_index, (uint32_t)k));
 }
 
+// Alternative observation head: the normalised observation of the reference's experimental MultiRobotPuzzle-v3
+// (gym_puzzles/envs/core.py:289-350, _get_norm_pose / _get_obs), computed from the state of a v0-family env:
+// per robot [bx - ax, by - ay, rot mod 2pi, contact], block [gx - bx, gy - by, grot - brot], 8 block vertices; positions
+// (x - w/2) / (w/2), (y - h/2) / (w/2) with w, h the arena size in metres (core.py divides both by the WIDTH scale).
+MRP_HD void obs_v3_lane(const SimConst& K, float* out, int64_t env) {
+    const uint32_t* G = env_words(K, env);
+    auto gfl = [&](int w) { union { uint32_t u; float f; } c; c.u = G[w << kTileShift]; return c.f; };
+    auto gdb = [&](int w) { union { uint64_t u; double d; } c; c.u = (uint64_t)G[w << kTileShift] | ((uint64_t)G[(w + 1) << kTileShift] << 32); return c.d; };
+    const double ws = K.W / 2, hs = K.H / 2;
+    float* o = out + env * (4 * K.n + 19);
+    const int wb = K.w_body;
+    const double bx = ((double)gfl(wb) - ws) / ws, by = ((double)gfl(wb + 1) - hs) / ws, brot = py_mod((double)gfl(wb + 2), kTwoPiD);
+    const uint32_t goalc = G[W_GOALC << kTileShift];
+    for (int i = 0; i < K.n; ++i) {
+        const int w = wb + kBodyWords * (1 + i);
+        const double ax = ((double)gfl(w) - ws) / ws, ay = ((double)gfl(w + 1) - hs) / ws;
+        *o++ = (float)(bx - ax);
+        *o++ = (float)(by - ay);
+        *o++ = (float)py_mod((double)gfl(w + 2), kTwoPiD);
+        *o++ = ((goalc >> i) & 1) ? 1.0f : 0.0f;
+    }
+    const double sw = K.W * K.SCALE, sh = K.H * K.SCALE;            // screen size in pixels (640 x 480)
+    const double gx = (gdb(W_GOAL) - sw / 2) / (sw / 2), gy = (gdb(W_GOAL + 2) - sh / 2) / (sw / 2);
+    *o++ = (float)(gx - bx);
+    *o++ = (float)(gy - by);
+    *o++ = (float)(0.0 - brot);
+    Xf xf;
+    xf.q.s = gfl(wb + 6); xf.q.c = gfl(wb + 7);
+    const V2 r = rmul(xf.q, mk(K.blk_lcx, K.blk_lcy));
+    xf.p = mk(gfl(wb) - r.x, gfl(wb + 1) - r.y);
+    for (int k = 0; k < 8; ++k) {
+        const V2 p = xmul(xf, mk(K.blkv[k][0], K.blkv[k][1]));
+        *o++ = (float)(((double)p.x - ws) / ws);
+        *o++ = (float)(((double)p.y - hs) / ws);
+    }
+}
+
 MRP_HD void fix_rot_lane(const SimConst& K, int64_t env) {  // q = Rot(a) after a state upload
     for (int b = 0; b < K.nb; ++b) {
         uint32_t* G = env_words(K, env);
@@ -642,6 +679,11 @@ __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ S
 __global__ void k_sample_actions(const __grid_constant__ SimConst K, float* dst, uint64_t step_index) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env < K.N) sample_actions_lane(K, dst, step_index, env);
+}
+
+__global__ void k_obs_v3(const __grid_constant__ SimConst K, float* out) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < K.N) obs_v3_lane(K, out, env);
 }
 
 __global__ void k_fix_rot(const __grid_constant__ SimConst K, int64_t begin, int64_t count) {
@@ -1619,6 +1661,24 @@ int MRP_API(mrp_reset_host)(mrp_handle* h, const uint8_t* mask_host, float* obs_
     return 0;
 }
 
+int MRP_API(mrp_obs_v3)(mrp_handle* h, float* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(-1, "mrp_obs_v3: null argument");
+#ifndef MRP_WIDE
+    if (h->wide) return fail(-6, "mrp_obs_v3: holonomic (v0 / Heavy-v0) envs only");
+#endif
+    if (h->K.v2) return fail(-6, "mrp_obs_v3: holonomic (v0 / Heavy-v0) envs only");
+#ifndef MRP_HOST_EMU
+    cudaSetDevice(h->device);
+    k_obs_v3<<<grid_for(h->K.N, 128), 128, 0, (cudaStream_t)stream>>>(h->K, out_dev);
+    h->launches += 1;
+    return check_launch("mrp_obs_v3");
+#else
+    (void)stream;
+    for (int64_t e = 0; e < h->K.N; ++e) obs_v3_lane(h->K, out_dev, e);
+    return 0;
+#endif
+}
+
 int MRP_API(mrp_sample_actions)(mrp_handle* h, uint64_t step_index, float* dst_dev, void* stream) {
     FWD(mrp_sample_actions_wide(h->wide, step_index, dst_dev, stream))
     if (!h) return fail(-1, "mrp_sample_actions: null handle");
@@ -1901,6 +1961,14 @@ int mrp_debug_event_records(unsigned long long* out, int cap) {
     const int m = (int)n < cap ? (int)n : cap;
     cudaMemcpyFromSymbol(out, g_tp_evrec, sizeof(unsigned long long) * 5 * (size_t)m);
     return (int)n;
+}
+#endif
+
+#if defined(MRP_CHECK) && !defined(MRP_HOST_EMU)
+// checking build only: failed in-kernel assertions by kind (CHK_*) since the library was loaded
+int MRP_API(mrp_debug_check_counts)(unsigned int* out8) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out8, g_check_fail, sizeof(unsigned int) * 8) == cudaSuccess ? 0 : -1;
 }
 #endif
 

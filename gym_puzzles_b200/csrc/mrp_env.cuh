@@ -356,6 +356,7 @@ struct Env : Sim {
         uint32_t in_island = 0;  // dynamic bodies that belong to an island with touching contacts
         if (T > 0) {
             const int off = atomic_add_i32(&K.cnt[CNT_POOL], T);  // in records
+            MRP_ASSERT(off >= 0 && (int64_t)off + T <= (int64_t)K.nloc * K.maxc, CHK_RECORD);
             vcp = K.pool + (size_t)off * VC_WORDS;
             init_constraints(T, island_of, true);
             warm_start(T);
@@ -369,6 +370,7 @@ struct Env : Sim {
                 const int cls = end - start > 2 ? 3 : (end - start == 2 ? 2 : (int)((vmeta(start) >> 8) & 3) - 1);  // single contact: vpc is 1 or 2
                 const int task = cls * cap + (heavy ? atomic_add_i32(&K.cnt[CNT_TASKS + cls], 1)
                                                     : cap - 1 - atomic_add_i32(&K.cnt[CNT_TASKS_LIGHT + cls], 1));
+                MRP_ASSERT(task >= 0 && task < kTaskClasses * cap, CHK_QUEUE);
                 K.task_env[task] = env_i;
                 K.task_T[task] = end - start;
                 K.task_off[task] = off + start;

@@ -17,6 +17,28 @@
 
 namespace mrp {
 
+// -DMRP_CHECK (checking build, profiles/check_run.py under gpurun): in-kernel bounds assertions on everything a lane indexes
+// dynamically — body field vs. the kernel's shared-memory layout, fixture and contact slots, pool records, queue slots.
+// compute-sanitizer is not available on this pool; the host build of the kernel source has the same layout check.
+#ifdef MRP_CHECK
+#if defined(__CUDACC__)
+__device__ unsigned int g_check_fail[8];
+MRP_HD void check_fail(int code) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&g_check_fail[code], 1u);
+#else
+    (void)code;
+#endif
+}
+#define MRP_ASSERT(cond, code) do { if (!(cond)) check_fail(code); } while (0)
+#else
+#define MRP_ASSERT(cond, code) do { if (!(cond)) { fprintf(stderr, "MRP_CHECK %d failed\n", code); abort(); } } while (0)
+#endif
+#else
+#define MRP_ASSERT(cond, code) do { } while (0)
+#endif
+enum { CHK_BODY_FIELD = 0, CHK_FIXTURE = 1, CHK_CONTACT_SLOT = 2, CHK_RECORD = 3, CHK_QUEUE = 4, CHK_NC = 5 };
+
 #if defined(__CUDA_ARCH__)
 #define MRP_SS 32   // shared-memory lane stride: every warp owns a block of words_per_lane x 32 floats (word k of lane t at k * 32 + t)
 #else
@@ -289,7 +311,10 @@ struct Sim {
     static MRP_HD uint32_t __float_as_uint_(float f) { union { uint32_t u; float f; } c; c.f = f; return c.u; }
     static MRP_HD double __ull_as_double_(uint64_t u) { union { uint64_t u; double f; } c; c.u = u; return c.f; }
     static MRP_HD uint64_t __double_as_ull_(double f) { union { uint64_t u; double f; } c; c.f = f; return c.u; }
-    MRP_HD int cw(int k, int j) const { return K.w_con + k * MRP_CONTACT_WORDS + j; }
+    MRP_HD int cw(int k, int j) const {
+        MRP_ASSERT(k >= 0 && k < K.maxc && j >= 0 && j < MRP_CONTACT_WORDS, CHK_CONTACT_SLOT);
+        return K.w_con + k * MRP_CONTACT_WORDS + j;
+    }
 
     // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 qs 7 qc 8 px 9 py | 10 cache.s 11 cache.c
     // 12 cache angle (last Rot evaluated for this body and the angle it belongs to) | 13 c0x 14 c0y 15 a0 16 alpha0.
@@ -306,10 +331,16 @@ struct Sim {
     }
     float& BX(int b, int f) { return B(b, f); }
 #else
-    MRP_HD float& B(int b, int f) { return bp(b)[f * MRP_SS]; }
-    MRP_HD float& BX(int b, int f) { return bp(b)[f * MRP_SS]; }
+    MRP_HD float& B(int b, int f) {
+        MRP_ASSERT(b >= 0 && b < K.nb + 4 && (b < K.nb ? f < fdyn : (f < 6 && wall_off >= 0)), CHK_BODY_FIELD);
+        return bp(b)[f * MRP_SS];
+    }
+    MRP_HD float& BX(int b, int f) { return B(b, f); }
 #endif
-    MRP_HD float& FA(int fx, int j) { return sm[(fa_off + fx * 4 + j) * MRP_SS]; }
+    MRP_HD float& FA(int fx, int j) {
+        MRP_ASSERT(fa_off >= 0 && fx >= 0 && fx < K.ndynfix && j >= 0 && j < 4, CHK_FIXTURE);
+        return sm[(fa_off + fx * 4 + j) * MRP_SS];
+    }
 
     // b2Rot::Set(angle of body b) through a one-entry cache: sin/cos are pure functions of the float angle, so
     // reusing the last evaluation when the angle is bit-identical cannot change results (robots with invI = 0
@@ -718,7 +749,10 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ contact solver (A.8)
-    MRP_HD float& V(int t, int w) { return vcp[t * VC_WORDS + w]; }
+    MRP_HD float& V(int t, int w) {
+        MRP_ASSERT(t >= 0 && t < kMaxC && w >= 0 && w < VC_WORDS, CHK_RECORD);
+        return vcp[t * VC_WORDS + w];
+    }
     MRP_HD uint32_t vmeta(int t) { return __float_as_uint_(vcp[t * VC_WORDS + VC_META]); }
 
     // b2ContactSolver ctor + InitializeVelocityConstraints for constraints [0, T)

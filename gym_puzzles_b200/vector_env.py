@@ -112,6 +112,14 @@ class VectorEnv:
         self._step_index += 1
         return self.obs, self.reward, self.done, {"TimeLimit.truncated": self.truncated}
 
+    def obs_v3(self, out=None):
+        """The normalised observation of the reference's experimental MultiRobotPuzzle-v3 (gym_puzzles/envs/core.py:289-350)
+        for the current state of a v0 / Heavy-v0 batch: float32 CUDA tensor [N, 4 n + 19]."""
+        if out is None:
+            out = self.torch.empty((self.num_envs, 4 * self.n_agents + 19), dtype=self.torch.float32, device=self.device)
+        self.handle.obs_v3(out.data_ptr(), self._stream())
+        return out
+
     def sample_actions(self, step_index=None, out=None):
         """Synthetic U(-1,1) actions (Philox stream ACTION keyed by global env id and step) written on the device."""
         idx = self._step_index if step_index is None else step_index

@@ -140,6 +140,12 @@ int mrp_enable_terminal_info(mrp_handle* h, mrp_terminal_buffers* out);
  * (stream-ordered before mrp_step).  v2 family only (v0 uses the fixed EPSILON = 25 px, mrp00:54). */
 int mrp_enable_curriculum(mrp_handle* h, double** scaled_epsilon_dev, double** decay_pow_dev);
 
+/* Alternative observation head for the holonomic family: the normalised observation of the reference's experimental
+ * MultiRobotPuzzle-v3 (gym_puzzles/envs/core.py:289-350: _get_norm_pose, _get_obs) computed from the current state —
+ * out_dev: f32[num_envs][4 * n_agents + 19] = per robot {bx-ax, by-ay, rot mod 2pi, contact}, block {gx-bx, gy-by, -rot},
+ * 8 vertices {(x-w/2)/(w/2), (y-h/2)/(w/2)}.  Stream-ordered; call after mrp_step / mrp_reset. */
+int mrp_obs_v3(mrp_handle* h, float* out_dev, void* stream);
+
 int mrp_set_params(mrp_handle* h, const mrp_params* p);
 int mrp_get_params(mrp_handle* h, mrp_params* p);
 

@@ -1,5 +1,7 @@
-"""Small program for compute-sanitizer (memcheck) under gpurun: every kernel family once, default and wide build.
-  compute-sanitizer --tool memcheck python profiles/sanitize_run.py"""
+"""Every kernel family once, default and wide build, against the CHECKING build of the library (-DMRP_CHECK: in-kernel bounds
+assertions on body fields vs. shared-memory layout, fixture / contact slots, pool records, queue slots; compute-sanitizer is
+not available on this pool).  Under gpurun:
+  bash profiles/build_probe.sh check && MRP_LIB_PATH=$PWD/gym_puzzles_b200/csrc/libmrp_check.so python profiles/check_run.py"""
 import os
 import sys
 
@@ -44,3 +46,10 @@ venv.reset()
 for t in range(20):
     venv.step(rng.uniform(-1, 1, (256, 6)).astype(np.float32))
 print("sb3 ok")
+import ctypes as C
+counts = (C.c_uint * 8)()
+wide = (C.c_uint * 8)()
+lib = abi.load().lib
+assert lib.mrp_debug_check_counts(counts) == 0 and lib.mrp_debug_check_counts_wide(wide) == 0
+print("MRP_CHECK failed assertions (body field, fixture, contact slot, record, queue, nc):", list(counts)[:6], "wide build:", list(wide)[:6])
+assert sum(counts) == 0 and sum(wide) == 0

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "mrp_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mrp_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(mrp_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")

@@ -56,3 +56,44 @@ def test_actions_outside_the_box_are_not_clipped():
     o2 = h2.step_host(3.0 * a)[0]
     assert not np.array_equal(o1, o2) and np.isfinite(o2).all()
     h1.close(); h2.close()
+
+
+def _check_nan_guard(lib):
+    """a body whose state became NaN / inf ends its episode by force (done = trunc = 1, reward 0),
+    is respawned by the auto-reset and counted in MRP_STAT_NAN_RESETS; the other envs are untouched."""
+    kw = {} if lib is None else {"lib": lib}
+    N = 40
+    ref = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=9, **kw)
+    h = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=9, **kw)
+    ref.reset_host(); h.reset_host()
+    w = h.get_state()
+    l = h.layout
+    bad = [3, 17]
+    for i, e in enumerate(bad):
+        f = w[e, l.off_bodies:l.off_bodies + 6 * l.n_dyn_bodies].view(np.float32)
+        if i == 0:
+            f[6 * 1 + 0] = np.nan          # a robot's position (its velocity would be overwritten by the holonomic control)
+        else:
+            f[6 * 0 + 3] = np.inf          # the block's velocity
+    h.set_state(w)
+    a = np.random.default_rng(0).uniform(-1, 1, (N, h.act_dim)).astype(np.float32)
+    obs_r, rew_r, done_r, tr_r = ref.step_host(a)
+    obs, rew, done, trunc = h.step_host(a)
+    assert done[bad].all() and trunc[bad].all() and (rew[bad] == 0).all()
+    assert np.isfinite(obs).all()                               # the rows hold the respawned envs' observations
+    good = np.setdiff1d(np.arange(N), bad)
+    assert np.array_equal(obs[good], obs_r[good]) and np.array_equal(done[good], done_r[good])
+    s = h.stats()
+    assert s["nan_resets"] == 2 and s["episodes"] >= 2 and np.isfinite(s["sum_return"])
+    assert np.isfinite(h.get_state()[:, l.off_bodies:l.off_bodies + 6 * l.n_dyn_bodies].view(np.float32)).all()
+    h.close(); ref.close()
+
+
+def test_nan_guard_kernel_source():
+    from emu_lib import emu_lib
+    _check_nan_guard(emu_lib())
+
+
+@pytest.mark.gpu
+def test_nan_guard_gpu():
+    _check_nan_guard(None)

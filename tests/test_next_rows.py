@@ -151,3 +151,98 @@ def test_render_bridge_scene_and_image():
     env = gp.make("MultiRobotPuzzle-v0", _lib=_emu())
     env.reset()
     assert env.render(mode="rgb_array").shape == (480, 640, 3)
+
+
+def _obs_v3_numpy(env_id, words, layout):
+    """restatement of the reference's experimental -v3 observation (gym_puzzles/envs/core.py:289-350) from canonical state"""
+    from oracle_lib import StateView
+    sv = StateView(layout, words)
+    n = layout.n_agents
+    W, H = 640 / 30.0, 480 / 30.0
+    ws, hs = W / 2, H / 2
+    s = 1.0 if "Heavy" in env_id else 2.0
+    verts = [(-3 / s, 0.0), (3 / s, 0.0), (3 / s, 2 / s), (-3 / s, 2 / s), (-1 / s, -2 / s), (1 / s, -2 / s), (1 / s, 0.0), (-1 / s, 0.0)]  # bar, stem
+    lc = np.float32(0.5 if "Heavy" in env_id else 0.25)
+    out = np.zeros((len(sv.w), 4 * n + 19))
+    for e in range(len(sv.w)):
+        bod = sv.bodies[e].astype(np.float64)
+        bx, by, brot = (bod[0, 0] - ws) / ws, (bod[0, 1] - hs) / ws, bod[0, 2] % (2 * np.pi)
+        o = []
+        for i in range(n):
+            ax, ay = (bod[1 + i, 0] - ws) / ws, (bod[1 + i, 1] - hs) / ws
+            o += [bx - ax, by - ay, bod[1 + i, 2] % (2 * np.pi), float(sv.goal_contact[e, i])]
+        gx, gy = np.ascontiguousarray(sv.w[e, layout.off_goal:layout.off_goal + 4]).view(np.float64)
+        o += [(gx - 320) / 320 - bx, (gy - 240) / 320 - by, 0.0 - brot]
+        a = np.float32(sv.bodies[e, 0, 2])
+        c, sn = np.float32(np.cos(np.float64(a))), np.float32(np.sin(np.float64(a)))
+        px = sv.bodies[e, 0, 0] - (c * np.float32(0) - sn * lc)          # body origin = c - R * localCenter (float32, as Box2D)
+        py = sv.bodies[e, 0, 1] - (sn * np.float32(0) + c * lc)
+        for vx, vy in verts:
+            vx, vy = np.float32(vx), np.float32(vy)
+            x = (c * vx - sn * vy) + px
+            y = (sn * vx + c * vy) + py
+            o += [(np.float64(x) - ws) / ws, (np.float64(y) - hs) / ws]
+        out[e] = o
+    return out
+
+
+def _check_obs_v3(lib, device):
+    for env_id in ("MultiRobotPuzzle-v0", "MultiRobotPuzzleHeavy-v0"):
+        kw = {} if lib is None else {"lib": lib}
+        h = abi.Handle(env_id, 64, seed=5, max_episode_steps=30, **kw)
+        h.reset_host()
+        rng = np.random.default_rng(1)
+        for t in range(40):
+            h.step_host(rng.uniform(-1, 1, (64, h.act_dim)).astype(np.float32))
+        want = _obs_v3_numpy(env_id, h.get_state(), h.layout)
+        O3 = 4 * h.layout.n_agents + 19
+        if device:
+            import torch
+            out = torch.empty((64, O3), dtype=torch.float32, device="cuda")
+            h.obs_v3(out.data_ptr())
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+        else:
+            got = np.zeros((64, O3), dtype=np.float32)
+            h.obs_v3(got.ctypes.data_as(C.c_void_p))
+        assert np.allclose(got, want, rtol=1e-5, atol=2e-6), np.abs(got - want).max()
+        assert (got[:, 3::4][:, :h.layout.n_agents] >= 0).all()
+        h.close()
+    h = abi.Handle("MultiRobotPuzzle-v2", 4, **({} if lib is None else {"lib": lib}))
+    with pytest.raises(abi.MrpError):
+        h.obs_v3(np.zeros(4 * 27, dtype=np.float32).ctypes.data_as(C.c_void_p))
+    h.close()
+
+
+def test_obs_v3_head_kernel_source():
+    _check_obs_v3(_emu(), device=False)
+
+
+@pytest.mark.gpu
+def test_obs_v3_head_gpu():
+    _check_obs_v3(None, device=True)
+    env = gp.VectorEnv("MultiRobotPuzzleHeavy-v0", 128, seed=2)
+    env.reset()
+    o3 = env.obs_v3()
+    assert tuple(o3.shape) == (128, 39) and bool(o3.isfinite().all())
+    env.close()
+
+
+@pytest.mark.gpu
+def test_render_bridge_gpu():
+    """render.scene / rgb_array on a CUDA handle: the polygons drawn are the ones the observation's block vertices describe"""
+    from gym_puzzles_b200 import render
+    for env_id in ("MultiRobotPuzzleHeavy-v0", "MultiRobotPuzzle-v2"):
+        h = abi.Handle(env_id, 8, seed=3)
+        obs = h.reset_host()
+        rng = np.random.default_rng(0)
+        for t in range(5):
+            obs, *_ = h.step_host(rng.uniform(-1, 1, (8, h.act_dim)).astype(np.float32))
+        sc = render.scene(h, 5)
+        k = sc["scale"] if env_id.endswith("v0") else sc["scale"] / sc["viewport"][0]
+        verts = obs[5, -16:] if env_id.endswith("v0") else obs[5, -17:-1]
+        bar = [p for kd, p in sc["polygons"] if kd == "block"][1]
+        assert np.allclose(np.asarray(bar).ravel() * k, verts[:8], rtol=1e-4, atol=1e-3 * k)
+        img = render.rgb_array(h, 5, downsample=2)
+        assert img.shape == (sc["viewport"][1] // 2, sc["viewport"][0] // 2, 3)
+        h.close()
