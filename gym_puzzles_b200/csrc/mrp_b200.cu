@@ -86,13 +86,17 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
     uint32_t len = e.g(W_EPLEN) + 1u;
     e.gsd(W_EPRET, ret);
     e.g(W_EPLEN) = len;
-    e.store();
+    if (!e.stored) e.store();
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
     if (done) {
         if (K.term_obs) {  // keep what the auto-reset is about to overwrite
             const float* orow = K.obs + env * K.obs_dim;
             float* trow = K.term_obs + env * K.obs_dim;
+#if defined(__CUDA_ARCH__)
+            for (int i = 0; i < K.obs_dim; ++i) trow[i] = __ldcg(orow + i);   // the row may have been written by other lanes of the warp (obs_flush)
+#else
             for (int i = 0; i < K.obs_dim; ++i) trow[i] = orow[i];
+#endif
             K.term_ret[env] = (float)ret;
             K.term_len[env] = (int32_t)len;
         }
@@ -124,14 +128,20 @@ MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
 
 // phase 1 (lane per env): control + Collide events + island order + constraint setup -> solver task
 // returns the number of solver constraints of the env (0: no island task was queued for it)
-MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, uint32_t* m12) {
+// staged = the warp's action rows were copied into its wall slots (k_pre, coalesced): rows are read from there, walls set afterwards
+MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, uint32_t* m12, const float* staged = nullptr, unsigned vmask = 0u) {
     Env e(K, sm, ct, env, nullptr, 13);
-    // the action row is requested first so that it is in flight while the state words are loaded
     float a[3 * MRP_MAX_AGENTS];
-    const float* arow = K.act + env * K.act_dim;
-    for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
-    e.load();
-    const int T = e.pre_phase(a);
+    if (staged) {
+        for (int i = 0; i < K.act_dim; ++i) a[i] = staged[i];
+        e.load(false);
+    } else {
+        // the action row is requested first so that it is in flight while the state words are loaded
+        const float* arow = K.act + env * K.act_dim;
+        for (int i = 0; i < K.act_dim; ++i) a[i] = arow[i];
+        e.load();
+    }
+    const int T = e.pre_phase(a, staged ? vmask : 0u);
     m12[0] += e.stat_m1; m12[1] += e.stat_m2;
     return T;
 }
@@ -263,7 +273,7 @@ __device__ unsigned long long g_tp_evrec[65536][5];
 __device__ unsigned int g_tp_evn;
 #endif
 MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env, bool allow_events, float* vc_local,
-                      bool free_group = false) {
+                      bool free_group = false, unsigned entry = 0u) {
     Env e(K, sm, ct, env, vc_local, allow_events ? kDynFields : 11);
 #if defined(MRP_TAILPROBE) && defined(__CUDA_ARCH__)
     const long long tp_c0 = clock64();
@@ -271,7 +281,7 @@ MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env
     e.load();
     double r;
     bool d;
-    const bool fin = e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events);
+    const bool fin = e.post_phase(K.obs + env * K.obs_dim, &r, &d, allow_events, entry);
 #if defined(MRP_TAILPROBE) && defined(__CUDA_ARCH__)
     if (allow_events) {
         const unsigned int i = atomicAdd(&g_tp_evn, 1u);
@@ -467,7 +477,23 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
     const int64_t env = K.env0 + loc;
     int T = -1;
     uint32_t m12[2] = {0u, 0u};
-    if (valid) T = pre_lane(K, lane_sm(smem + kCtPad, 13 * K.nb + 24), ct, env, m12);
+    float* const lsm = lane_sm(smem + kCtPad, 13 * K.nb + 24);
+    const float* staged = nullptr;
+    if (K.stage_rows) {
+        // the 32 action rows of the warp's envs are one contiguous run of 32 x act_dim floats: consecutive lanes fetch
+        // consecutive words (coalesced) into the warp's wall slots (24 words per lane, set only after the rows have been read),
+        // then every lane picks up its own row
+        const int lane = threadIdx.x & 31;
+        float* blk = lsm - lane + (13 * K.nb) * 32;
+        const int64_t first = loc - lane;
+        const int words = (int)((loc1 - first < 32 ? loc1 - first : 32) * K.act_dim);
+        const float* src = K.act + (K.env0 + first) * K.act_dim;
+        for (int i = lane; i < words; i += 32) blk[i] = src[i];
+        __syncwarp();
+        staged = blk + lane * K.act_dim;
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) T = pre_lane(K, lsm, ct, env, m12, staged, vmask);
     stat_add_warp(K.stats, MRP_STAT_M1, m12[0]);
     stat_add_warp(K.stats, MRP_STAT_M2, m12[1]);
     // envs without solver tasks are final already: k_post handles them while the solver kernels run (post_list)
@@ -617,9 +643,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimC
     const int64_t count = which == 2 ? (int64_t)K.nloc : (int64_t)K.cnt[which == 0 ? CNT_FREE : CNT_BUSY];
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
+    const unsigned entry = K.stage_rows ? __ballot_sync(0xffffffffu, loc < count) : 0u;   // lanes of this warp that own an env
     if (loc >= count) return;
     const int64_t env = which == 2 ? K.env0 + loc : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
-    post_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, false, nullptr, which == 0);
+    post_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, false, nullptr, which == 0, entry);
 }
 
 // rare paths, grid-stride over their queues: envs with a TOI event this step; envs to auto-reset
@@ -726,6 +753,15 @@ struct mrp_handle {
     const void* zc_host;       // last obs_host pointer checked for device visibility ...
     float* zc_dev;             // ... and its device alias (nullptr: not pinned / not mapped -> rows leave after the passes)
     int overlap_post;  // mrp_step: k_post of envs without solver tasks runs beside the solver kernels
+    // Small batches are bound by the launch chain (eleven launches and up to five copies per step, each a few microseconds of
+    // host time for kernels that run as long): a step whose launches all sit on one stream is captured once into a CUDA graph
+    // and replayed with a single cudaGraphLaunch.  The kernel parameters are baked into the graph, so it is re-captured when
+    // the handle's constants (reward parameters, optional buffers) or the caller's pointers change.
+    int use_graph;               // MRP_GRAPH (default: batches below 32,768 envs, where no side stream is used)
+    cudaGraphExec_t gx_step, gx_host;
+    SimConst gk_step, gk_host;   // handle constants the graphs were captured with
+    const void* gp_host[5];      // host pointers of the captured mrp_step_host
+    int64_t gl_step, gl_host;    // launches inside one replay
 #endif
     int64_t launches;
     int64_t steps_done;  // mrp_step / mrp_step_host calls since the statistics were last reset (env_steps = steps_done * N)
@@ -839,6 +875,8 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     if (h->timing) MRP_API(mrp_set_timing)(h, 0);
+    if (h->gx_step) cudaGraphExecDestroy(h->gx_step);
+    if (h->gx_host) cudaGraphExecDestroy(h->gx_host);
     if (h->cfork) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); }
         cudaStreamDestroy(h->copy_stream);
@@ -1037,6 +1075,8 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
         const bool sparse_contacts = cfg->variant >= MRP_VARIANT_V2 && h->L.n_agents <= 2;
         h->overlap_post = getenv("MRP_OVERLAP_POST") ? atoi(getenv("MRP_OVERLAP_POST")) : (cfg->num_envs >= 65536 && !sparse_contacts ? 1 : 0);
     }
+    K.stage_rows = getenv("MRP_STAGE_ROWS") ? atoi(getenv("MRP_STAGE_ROWS")) : 1;
+    h->use_graph = getenv("MRP_GRAPH") ? atoi(getenv("MRP_GRAPH")) : (cfg->num_envs < 32768 ? 1 : 0);
     if (check_launch("mrp_create")) { MRP_API(mrp_destroy)(h); return -10; }
 #else
     h->emu_sm = (float*)calloc((size_t)K.smem_words + 8, sizeof(float));
@@ -1478,6 +1518,38 @@ static int step_chunks(const mrp_handle* h, int wanted) {
     return nch < 1 ? 1 : nch;
 }
 
+}  // extern "C"
+#ifndef MRP_HOST_EMU
+// a step qualifies for graph replay when all of its launches go to one stream and nothing is recorded between them
+static bool graph_ok(const mrp_handle* h, int nch) {
+    return h->use_graph && nch == 1 && !h->timing && !h->fused && !h->overlap_post && !h->big_split && !getenv("MRP_TRACE");
+}
+// capture `body` (launches on the capture stream) into an executable graph; returns nullptr when capture is not possible
+template <typename F>
+static cudaGraphExec_t capture_graph(mrp_handle* h, cudaStream_t cs, int64_t* launches, F body) {
+    const int64_t l0 = h->launches;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    body(cs);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cs, &g);
+    *launches = h->launches - l0;
+    h->launches = l0;   // counted per replay
+    cudaGraphExec_t x = nullptr;
+    if (e != cudaSuccess || !g || cudaGraphInstantiate(&x, g, 0) != cudaSuccess) x = nullptr;
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return x;
+}
+static bool host_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes pa;
+    const bool ok = cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return ok;
+}
+#endif
+extern "C" {
+
 int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
     FWD(mrp_step_wide(h->wide, actions_dev, stream))
     if (!h) return fail(-1, "mrp_step: null handle");
@@ -1488,7 +1560,18 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
 #ifndef MRP_HOST_EMU
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (nch == 1 && !h->fused) {
+    if (graph_ok(h, nch)) {
+        if (h->gx_step && memcmp(&h->gk_step, &K, sizeof(SimConst)) != 0) { cudaGraphExecDestroy(h->gx_step); h->gx_step = nullptr; }
+        if (!h->gx_step) {
+            h->gx_step = capture_graph(h, h->cstream[0], &h->gl_step, [&](cudaStream_t cs) { launch_step(h, chunk_const(h, K, 0, 1), cs, false, false); });
+            memcpy(&h->gk_step, &K, sizeof(SimConst));
+            if (!h->gx_step) h->use_graph = 0;   // capture unavailable: plain launches from now on
+        }
+    }
+    if (graph_ok(h, nch) && h->gx_step) {
+        h->launches += h->gl_step;
+        if (cudaGraphLaunch(h->gx_step, st) != cudaSuccess) return fail(-10, "mrp_step: graph launch failed: %s", dev_err());
+    } else if (nch == 1 && !h->fused) {
         launch_step(h, chunk_const(h, K, 0, 1), st, h->timing != 0, true);
     } else if (nch == 1) {
         launch_pipeline(h, chunk_const(h, K, 0, 1), st, h->timing != 0);
@@ -1524,6 +1607,38 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     // buffers should be pinned) run under the remaining chunks' kernels.
     const int nch = step_chunks(h, h->nchunks_host);
     const size_t N = (size_t)K0.N;
+    if (graph_ok(h, nch)) {
+        const void* hp[5] = {actions_host, obs_host, reward_host, done_host, trunc_host};
+        if (h->gx_host && (memcmp(&h->gk_host, &K0, sizeof(SimConst)) != 0 || memcmp(h->gp_host, hp, sizeof(hp)) != 0)) {
+            cudaGraphExecDestroy(h->gx_host);
+            h->gx_host = nullptr;
+        }
+        if (!h->gx_host && (memcmp(h->gp_host, hp, sizeof(hp)) != 0 || memcmp(&h->gk_host, &K0, sizeof(SimConst)) != 0)) {
+            // pageable buffers are not captured (their copies are staged by the driver at call time): plain path
+            bool pinned = true;
+            for (const void* p : hp) pinned = pinned && host_pinned(p);
+            memcpy(h->gp_host, hp, sizeof(hp));
+            memcpy(&h->gk_host, &K0, sizeof(SimConst));
+            if (pinned)
+                h->gx_host = capture_graph(h, h->cstream[0], &h->gl_host, [&](cudaStream_t cs) {
+                    cudaMemcpyAsync(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim, cudaMemcpyHostToDevice, cs);
+                    launch_step(h, chunk_const(h, K0, 0, 1), cs, false, false);
+                    if (obs_host) cudaMemcpyAsync(obs_host, K0.obs, sizeof(float) * N * K0.obs_dim, cudaMemcpyDeviceToHost, cs);
+                    if (reward_host) cudaMemcpyAsync(reward_host, K0.rew, sizeof(float) * N, cudaMemcpyDeviceToHost, cs);
+                    if (done_host) cudaMemcpyAsync(done_host, K0.done, N, cudaMemcpyDeviceToHost, cs);
+                    if (trunc_host) cudaMemcpyAsync(trunc_host, K0.trunc, N, cudaMemcpyDeviceToHost, cs);
+                });
+        }
+        if (h->gx_host) {
+            cudaStream_t cs = h->cstream[0];
+            cudaEventRecord(h->cfork, 0);  // order after whatever the caller queued on the default stream
+            cudaStreamWaitEvent(cs, h->cfork, 0);
+            h->launches += h->gl_host;
+            if (cudaGraphLaunch(h->gx_host, cs) != cudaSuccess) return fail(-10, "mrp_step_host: graph launch failed: %s", dev_err());
+            if (cudaStreamSynchronize(cs) != cudaSuccess) return fail(-9, "mrp_step_host: %s", dev_err());
+            return 0;
+        }
+    }
     cudaEvent_t* const tr = h->tr;
     const bool trace = getenv("MRP_TRACE") != nullptr;
     if (trace && !h->tr_init) { for (int i = 0; i < 32; ++i) cudaEventCreate(&tr[i]); h->tr_init = 1; }

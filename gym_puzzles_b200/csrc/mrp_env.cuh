@@ -135,32 +135,33 @@ struct Env : Sim {
         gsd(W_DIST + 2 * n, bd);
 
         Xf bxf = body_xf(0);
-        int o = 0;
+        obs_begin(obs);
         double reward = 0.0;
         bool in_place;
         int blks = (int)g(W_INPLACE);
         if (!K.v2) {
 #pragma unroll 1
             for (int i = 0; i < n; ++i) {
-                obs[o++] = (float)((double)B(1 + i, 0) * K.SCALE - (double)bc.x * K.SCALE);
-                obs[o++] = (float)((double)B(1 + i, 1) * K.SCALE - (double)bc.y * K.SCALE);
-                obs[o++] = (float)ad[i];
-                obs[o++] = ((goalc >> i) & 1) ? 1.0f : 0.0f;
+                obs_put((float)((double)B(1 + i, 0) * K.SCALE - (double)bc.x * K.SCALE));
+                obs_put((float)((double)B(1 + i, 1) * K.SCALE - (double)bc.y * K.SCALE));
+                obs_put((float)ad[i]);
+                obs_put(((goalc >> i) & 1) ? 1.0f : 0.0f);
             }
             double x = (double)bc.x * K.SCALE, y = (double)bc.y * K.SCALE;
             double angle = py_mod((double)B(0, 2), kTwoPiD);
             double a_diff = 0.0 - angle;
             in_place = !(fabs(gx - x) > 25.0) && !(fabs(gy - y) > 25.0);
-            obs[o++] = (float)(x - gx);
-            obs[o++] = (float)(y - gy);
-            obs[o++] = (float)a_diff;
-            obs[o++] = (float)py_distance(x, y, gx, gy);
+            obs_put((float)(x - gx));
+            obs_put((float)(y - gy));
+            obs_put((float)a_diff);
+            obs_put((float)py_distance(x, y, gx, gy));
 #pragma unroll 1
             for (int k = 0; k < 8; ++k) {
                 V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
-                obs[o++] = (float)((double)p.x * K.SCALE);
-                obs[o++] = (float)((double)p.y * K.SCALE);
+                obs_put((float)((double)p.x * K.SCALE));
+                obs_put((float)((double)p.y * K.SCALE));
             }
+            obs_end();
             reward += (prev_bd - bd) * K.rp.blockDelta * 1.0 / 4.;
             reward -= K.rp.blockDistance * bd * 1.0 / 4.;
 #pragma unroll 1
@@ -187,34 +188,35 @@ struct Env : Sim {
             double aX = (double)B(b, 0) * K.ratio, aY = (double)B(b, 1) * K.ratio;
             double theta = py_mod((double)B(b, 2), kTwoPiD);
             double nt = theta <= kPiD ? -theta / kPiD : (kTwoPiD - theta) / kPiD;
-            obs[o++] = (float)aX;
-            obs[o++] = (float)aY;
-            obs[o++] = (float)nt;
+            obs_put((float)aX);
+            obs_put((float)aY);
+            obs_put((float)nt);
             double bX = (double)bc.x * K.ratio, bY = (double)bc.y * K.ratio;
-            obs[o++] = (float)(aX - bX);
-            obs[o++] = (float)(aY - bY);
-            obs[o++] = B(b, 3);
-            obs[o++] = B(b, 4);
-            obs[o++] = B(b, 5);
-            obs[o++] = (float)ad[i];
+            obs_put((float)(aX - bX));
+            obs_put((float)(aY - bY));
+            obs_put(B(b, 3));
+            obs_put(B(b, 4));
+            obs_put(B(b, 5));
+            obs_put((float)ad[i]);
         }
         {
             double x = (double)bc.x * K.ratio, y = (double)bc.y * K.ratio;
             double angle = py_mod((double)B(0, 2), kTwoPiD);
             double a_diff = (0.0 - angle) / kPiD;
             in_place = !(fabs(gx - x) > eps) && !(fabs(gy - y) > eps);
-            obs[o++] = (float)(x - gx);
-            obs[o++] = (float)(y - gy);
-            obs[o++] = (float)a_diff;
-            obs[o++] = (float)py_distance(x, y, gx, gy);
+            obs_put((float)(x - gx));
+            obs_put((float)(y - gy));
+            obs_put((float)a_diff);
+            obs_put((float)py_distance(x, y, gx, gy));
 #pragma unroll 1
             for (int k = 0; k < 8; ++k) {
                 V2 p = xmul(bxf, mk(K.blkv[k][0], K.blkv[k][1]));
-                obs[o++] = (float)((double)p.x * K.ratio);
-                obs[o++] = (float)((double)p.y * K.ratio);
+                obs_put((float)((double)p.x * K.ratio));
+                obs_put((float)((double)p.y * K.ratio));
             }
         }
-        obs[o++] = (float)eps;
+        obs_put((float)eps);
+        obs_end();
         reward += (prev_bd - bd) * K.rp.blockDelta;
         reward -= K.rp.blockDistance * bd;
 #pragma unroll 1
@@ -343,7 +345,15 @@ struct Env : Sim {
     // ---------------------------------------------------------------- phase pipeline (one env.step split at the solver)
     // k_pre: control, Collide, island order; envs with touching contacts become solver tasks, the others
     // integrate their positions right away.  Returns T.
-    MRP_HD int pre_phase(const float* a) {
+    MRP_HD int pre_phase(const float* a, unsigned walls_pending = 0u) {
+        // walls_pending (lanes of the warp that run this pass): the warp's action rows were staged in the wall slots; once every
+        // lane has its row in registers the slots get their walls
+        if (walls_pending) {
+#if defined(__CUDA_ARCH__)
+            __syncwarp(walls_pending);
+#endif
+            init_walls();
+        }
         if (K.v2) control_v2(a); else control_v0(a);
         finish_collide();
         // pose at the start of the step, for k_post's SynchronizeFixtures / TOI sweeps
@@ -396,10 +406,18 @@ struct Env : Sim {
     }
     // k_post: the step after the solver — transforms, broadphase, TOI, obs / reward / done.
     // Returns false (nothing stored) when a TOI event is needed and allow_events is false.
-    MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events) {
+    // entry != 0 (k_post on the device): the lanes `entry` of the warp run this pass, and the observation rows leave through the
+    // warp's staging block (obs_stage / obs_flush) instead of row by row
+    MRP_HD bool post_phase(float* obs, double* reward, bool* done_env, bool allow_events, unsigned entry = 0u) {
         // load(): q/p are still the pre-step transform; c0/a0 from the hand-off words
         for (int b = 0; b < K.nb; ++b) set_rot_cache(b, Rot{BX(b, 6), BX(b, 7)}, BX(b, c0f + 2));
-        if (!post_solve(allow_events)) return false;
+        const bool fin = post_solve(allow_events);
+#if defined(__CUDA_ARCH__)
+        if (entry) obs_stage(entry, fin);
+#else
+        (void)entry;
+#endif
+        if (!fin) return false;
         *done_env = post_step(obs, reward);
         return true;
     }

@@ -1,6 +1,6 @@
 """Quick device-side A/B helper (not the bench contract — see bench.py): ms/step of mrp_step for a few settings.
 
-  python profiles/quickbench.py [ENV_ID ...]        env: MRP_CHUNKS, MRP_SOLVER_CTAS, QB_ENVS, QB_PHASES=1, QB_E2E=1
+  python profiles/quickbench.py [ENV_ID ...]        env: MRP_CHUNKS, MRP_SOLVER_CTAS, QB_ENVS, QB_PHASES=1, QB_E2E=1, QB_MAXSTEPS (TimeLimit)
 """
 import os
 import sys
@@ -13,7 +13,7 @@ from gym_puzzles_b200 import abi
 
 
 def run(env_id, N, settle=100, K=20, n_agents=0):
-    h = abi.Handle(env_id, N, seed=17, n_agents=n_agents)
+    h = abi.Handle(env_id, N, seed=17, n_agents=n_agents, max_episode_steps=int(os.environ.get("QB_MAXSTEPS", 0)))
     h.reset()
     torch.cuda.synchronize()
     for t in range(settle):

@@ -11,11 +11,11 @@ import torch
 from gym_puzzles_b200 import abi
 
 env_id = sys.argv[1] if len(sys.argv) > 1 else "MultiRobotPuzzle-v0"
-for N in (1, 6, 64, 1024, 16384, 65536):
+for N in [int(x) for x in os.environ.get("SB_SIZES", "1,6,64,1024,16384,65536").split(",")]:
     h = abi.Handle(env_id, N, seed=1)
     pin = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt).pin_memory().numpy()  # noqa: E731
     a = pin(N, h.act_dim)
-    a[:] = np.random.default_rng(0).uniform(-1, 1, a.shape)
+    a[:] = np.random.default_rng(0).uniform(-1, 1, a.shape)   # one action batch held for the whole run: steady pushing, a heavy case
     out = (pin(N, h.obs_dim), pin(N), pin(N, dt=torch.uint8), pin(N, dt=torch.uint8))
     h.reset_host()
     for _ in range(50):

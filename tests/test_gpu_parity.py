@@ -183,3 +183,52 @@ def test_rollout_parity_device_path(env_id):
     _assert_parity(rep)
     assert rep["dones"] >= 2 * N
     h.close()
+
+
+def test_graph_replay_is_invariant(monkeypatch):
+    """Small batches replay a captured CUDA graph (one cudaGraphLaunch per step instead of eleven launches): results are
+    those of the plain launches, also when the caller's buffers or the handle's parameters change between steps
+    (the graph is re-captured) and for pageable host buffers (never captured)."""
+    import torch
+
+    N, env_id = 700, "MultiRobotPuzzle-v2"
+    rng = np.random.default_rng(3)
+    acts = [rng.uniform(-1, 1, (N, 4)).astype(np.float32) for _ in range(4)]
+    pinned = [torch.from_numpy(a).pin_memory().numpy() for a in acts]
+
+    def run(graph, pin):
+        monkeypatch.setenv("MRP_GRAPH", "1" if graph else "0")
+        h = abi.Handle(env_id, N, seed=23, max_episode_steps=30)
+        h.reset_host()
+        out = []
+        bufs = [(torch.empty(N, h.obs_dim).pin_memory().numpy(), torch.empty(N).pin_memory().numpy(),
+                 torch.empty(N, dtype=torch.uint8).pin_memory().numpy(), torch.empty(N, dtype=torch.uint8).pin_memory().numpy())
+                for _ in range(2)] if pin else [(None, None, None, None)] * 2
+        for t in range(60):
+            if t == 20:
+                h.set_params(scaled_epsilon=30.0, puzzleComp=5000.0)   # baked into the captured kernel parameters
+            src = pinned if pin else acts
+            # same buffers for a while (replay), then alternating ones (re-capture)
+            a, b = (src[0], bufs[0]) if t < 10 else (src[t % 4], bufs[t % 2])
+            res = h.step_host(a, *b)
+            out.append([np.array(x) for x in res])
+        # device-resident calls: library action buffer, then a caller-owned one
+        d = torch.from_numpy(acts[1]).cuda()
+        for t in range(10):
+            h.sample_actions(t)
+            h.step()
+        for t in range(10):
+            h.step(d.data_ptr())
+        torch.cuda.synchronize()
+        st, n = h.get_state(), h.launch_count
+        h.close()
+        return out, st, n
+
+    ref, st_ref, n_ref = run(False, True)
+    for graph, pin in ((True, True), (True, False)):
+        got, st, n = run(graph, pin)
+        for x, y in zip(ref, got):
+            for u, v in zip(x, y):
+                assert np.array_equal(u, v)
+        assert np.array_equal(st_ref, st)
+        assert n == n_ref   # replays count the launches they contain
