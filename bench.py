@@ -3,7 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            # native arm (sm_100a kernels through the C-ABI)
   python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement on the host cores
-  python bench.py --config c3|c3-strong|c3-resets|c2|c4|c4-heavy ...   # the other BASELINE.json configs (default c3)
+  python bench.py --config c3|c3-strong|c3-resets|c2|c4|c4-heavy|c5 ...   # the other BASELINE.json configs (default c3)
 
 Default workload (config.workload): MultiRobotPuzzleHeavy-v0 (5 robots, 2x block), 1,048,576 envs per GPU, random actions
 U(-1,1) from the Philox ACTION stream, auto-reset on (BASELINE.json configs[2]; the registered TimeLimit of 3000
@@ -51,6 +51,9 @@ CONFIGS = {
                what="configs[3]: v2, 1M envs per GPU"),
     "c4-heavy": dict(env_id="MultiRobotPuzzleHeavy-v2", envs=1048576, scaling="weak", cap=0, n=2, A=4, O=39,
                      what="configs[3]: Heavy-v2, 1M envs per GPU"),
+    # configs[4] "4M envs on 8 GPUs" = 524,288 per GPU; n counts the bodies besides the first block (2 robots + 2 more blocks)
+    "c5": dict(env_id="MultiRobotPuzzleSquare-v2", envs=524288, scaling="weak", cap=0, n=4, A=4, O=72,
+               what="configs[4]: 3-block square-forming variant (extension; oracle-defined semantics), Heavy-v2 dynamics, 524,288 envs per GPU"),
 }
 
 

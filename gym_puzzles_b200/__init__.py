@@ -9,7 +9,7 @@ Public surface:
   render.scene / rgb_array       host render bridge from get_state()
 """
 from .abi import MrpError, VARIANTS  # noqa: F401
-from .envs import MultiRobotPuzzle, MultiRobotPuzzle2, MultiRobotPuzzleHeavy, MultiRobotPuzzleHeavy2  # noqa: F401
+from .envs import MultiRobotPuzzle, MultiRobotPuzzle2, MultiRobotPuzzleHeavy, MultiRobotPuzzleHeavy2, MultiRobotPuzzleSquare2  # noqa: F401
 from .registry import make, register_with_gym, registry, spec  # noqa: F401
 from .vector_env import VectorEnv, shard_range  # noqa: F401
 from .sb3_vec_env import SB3VecEnv  # noqa: F401
@@ -21,4 +21,4 @@ from . import render  # noqa: F401
 GYM_REGISTERED = register_with_gym()
 
 __all__ = ["make", "spec", "registry", "register_with_gym", "VectorEnv", "shard_range", "MultiRobotPuzzle", "MultiRobotPuzzleHeavy",
-           "MultiRobotPuzzle2", "MultiRobotPuzzleHeavy2", "MrpError", "VARIANTS", "SB3VecEnv", "VecNormalize", "render"]
+           "MultiRobotPuzzle2", "MultiRobotPuzzleHeavy2", "MultiRobotPuzzleSquare2", "MrpError", "VARIANTS", "SB3VecEnv", "VecNormalize", "render"]

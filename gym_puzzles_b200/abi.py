@@ -16,6 +16,8 @@ VARIANTS = {
     "MultiRobotPuzzleHeavy-v0": 1,
     "MultiRobotPuzzle-v2": 2,
     "MultiRobotPuzzleHeavy-v2": 3,
+    # extension (BASELINE.json configs[4]; not a reference env): three blocks T, L, I that form a square, Heavy-v2 dynamics
+    "MultiRobotPuzzleSquare-v2": 4,
 }
 
 N_STATS = 16

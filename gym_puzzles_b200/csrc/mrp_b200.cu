@@ -734,6 +734,7 @@ struct mrp_handle {
     mrp_layout L;
     int device;
     float* ctab_dev;
+    float ctab_host[CT_WORDS];   // host copy of the constant table (fixture -> body map for mrp_set_state)
     float* act_dev;
     uint8_t* mask_dev;  // mrp_reset_host: staging buffer of the host mask (allocated on first use)
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
@@ -1002,6 +1003,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     K.ctab = h->ctab_dev;
     K.act = h->act_dev;
     H2D(h->ctab_dev, ctab, sizeof(ctab));
+    memcpy(h->ctab_host, ctab, sizeof(ctab));
     // episode counter starts at -1 so the first reset spawns episode 0; v0 goal is fixed
     {
         union { double d; uint32_t u[2]; } gx, gy;
@@ -1943,8 +1945,8 @@ int MRP_API(mrp_set_state)(mrp_handle* h, int32_t env_begin, int32_t env_count, 
             uint32_t m = cwp[0] & 0x000fffffu;
             int fa = m & 0xff, fb = (m >> 8) & 0xff;
             if (fa >= K.nfix || fb >= K.nfix) { free(buf); return fail(-2, "mrp_set_state: bad fixture index"); }
-            // body ids of the two fixtures (fixture order: stem, bar, agents..., walls)
-            auto body_of = [&](int f) { return f < 2 ? 0 : (f < K.ndynfix ? 1 + (f - 2) / K.per_agent : K.nb + (f - K.ndynfix)); };
+            // body ids of the two fixtures (fixture order: the blocks' fixtures, the robots', the walls)
+            auto body_of = [&](int f) { return (int)h->ctab_host[CT_FIXBODY + f]; };
             m |= ((uint32_t)body_of(fa) << 20) | ((uint32_t)body_of(fb) << 24);
             I(K.w_con + MRP_CONTACT_WORDS * k, e) = m;
             for (int j = 1; j < MRP_CONTACT_WORDS; ++j) I(K.w_con + MRP_CONTACT_WORDS * k + j, e) = cwp[j];

@@ -41,8 +41,8 @@ struct Env : Sim {
     }
 
     // soft attraction force of agent b on the block (mrp00:421-424 / mrp02:470-474)
-    MRP_HD V2 soft_force(int b, double force) {
-        double Ax = (double)B(b, 0), Ay = (double)B(b, 1), Bx = (double)B(0, 0), By = (double)B(0, 1);
+    MRP_HD V2 soft_force(int b, double force, int gb = 0) {
+        double Ax = (double)B(b, 0), Ay = (double)B(b, 1), Bx = (double)B(gb, 0), By = (double)B(gb, 1);
         double dx = fabs(Bx - Ax), dy = fabs(By - Ay);
         double denom = dx > dy ? dx : dy;  // max(abs, abs)
         return mk((float)(force * ((Bx - Ax) / denom)), (float)(force * ((By - Ay) / denom)));
@@ -70,9 +70,10 @@ struct Env : Sim {
     MRP_HD void control_v2(const float* a) {  // mrp02:446-474
         V2 bf = mk(0.0f, 0.0f);
         float btorque = 0.0f;
-        V2 bc = mk(B(0, 0), B(0, 1));
+        const int gb = goal_block();   // 0 unless the square variant has moved on to its next block
+        V2 bc = mk(B(gb, 0), B(gb, 1));
         for (int i = 0; i < K.n; ++i) {
-            int b = 1 + i;
+            int b = K.nblk + i;
             float turn = a[2 * i], vel = a[2 * i + 1];
             Xf xf = body_xf(b);
             V2 c = mk(B(b, 0), B(b, 1));
@@ -101,16 +102,20 @@ struct Env : Sim {
             else torque += 0.0f;
             double sf = pow(10.0, -gd(W_DIST + 2 * i));
             sf /= 50;
-            V2 s = soft_force(b, sf);
+            V2 s = soft_force(b, sf, gb);
             bf = bf + s;
             btorque += cross(bc - bc, s);
             integrate_velocity(b, force, torque);
         }
-        integrate_velocity(0, bf, btorque);
+        for (int k = 0; k < K.nblk; ++k) {
+            if (k == gb) integrate_velocity(k, bf, btorque);
+            else integrate_velocity(k, mk(0.0f, 0.0f), 0.0f);   // the other blocks only feel damping and contacts
+        }
     }
 
     // distances, observation, reward, done after world.Step; returns env "done"
     MRP_HD bool post_step(float* obs, double* reward_out) {
+        if (K.nblk > 1) return post_step_square(obs, reward_out);
         const int n = K.n;
         double prev_ad[MRP_MAX_AGENTS];
         for (int i = 0; i < n; ++i) prev_ad[i] = gd(W_DIST + 2 * i);
@@ -260,6 +265,121 @@ struct Env : Sim {
         return done;
     }
 
+    // Square variant (BASELINE.json configs[4]; semantics: DESIGN.md "Square variant", modelled on mrp02:491-584):
+    // per robot the 9 values of v2 relative to the goal block; per block (x - tx, y - ty, (ta - angle) / pi, distance to its
+    // target, vertices); epsilon, goal-block index, blocks in place, robots touching the goal block.  When the goal block reaches
+    // its target the next block of the queue T, L, I becomes the goal; done when all three are placed.
+    MRP_HD bool post_step_square(float* obs, double* reward_out) {
+        const int n = K.n, nbk = K.nblk;
+        const int placed = (int)g(W_INPLACE);
+        const int gb = placed < nbk - 1 ? placed : nbk - 1;
+        double prev_ad[MRP_MAX_AGENTS], ad[MRP_MAX_AGENTS];
+        for (int i = 0; i < n; ++i) prev_ad[i] = gd(W_DIST + 2 * i);
+        const double prev_bd = gd(W_DIST + 2 * n);
+        const double gx = gd(W_GOAL), gy = gd(W_GOAL + 2);
+        const V2 bc = mk(B(gb, 0), B(gb, 1));
+        const double bd = py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, gx + K.sq_target[gb][0] * K.ratio, gy + K.sq_target[gb][1] * K.ratio);
+#pragma unroll 1
+        for (int i = 0; i < n; ++i)
+            ad[i] = py_distance((double)B(nbk + i, 0) * K.ratio, (double)B(nbk + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio);
+        const double eps = K.eps_env ? K.eps_env[env_i] : K.rp.scaled_epsilon;
+        const double decay_pow = K.decay_env ? K.decay_env[env_i] : K.rp.decay_pow;
+        obs_begin(obs);
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const int b = nbk + i;
+            const double aX = (double)B(b, 0) * K.ratio, aY = (double)B(b, 1) * K.ratio;
+            const double theta = py_mod((double)B(b, 2), kTwoPiD);
+            const double nt = theta <= kPiD ? -theta / kPiD : (kTwoPiD - theta) / kPiD;
+            obs_put((float)aX);
+            obs_put((float)aY);
+            obs_put((float)nt);
+            const double bX = (double)bc.x * K.ratio, bY = (double)bc.y * K.ratio;
+            obs_put((float)(aX - bX));
+            obs_put((float)(aY - bY));
+            obs_put(B(b, 3));
+            obs_put(B(b, 4));
+            obs_put(B(b, 5));
+            obs_put((float)ad[i]);
+        }
+        bool in_place = false;
+#pragma unroll 1
+        for (int k = 0; k < nbk; ++k) {
+            const Xf bxf = body_xf(k);
+            const double x = (double)B(k, 0) * K.ratio, y = (double)B(k, 1) * K.ratio;
+            const double angle = py_mod((double)B(k, 2), kTwoPiD);
+            const double fx = gx + K.sq_target[k][0] * K.ratio, fy = gy + K.sq_target[k][1] * K.ratio;
+            const double a_diff = (K.sq_target[k][2] - angle) / kPiD;
+            if (k == gb) in_place = !(fabs(fx - x) > eps) && !(fabs(fy - y) > eps);
+            obs_put((float)(x - fx));
+            obs_put((float)(y - fy));
+            obs_put((float)a_diff);
+            obs_put((float)py_distance(x, y, fx, fy));
+#pragma unroll 1
+            for (int v = K.blkv_off[k]; v < K.blkv_off[k + 1]; ++v) {
+                const V2 p = xmul(bxf, mk(K.blkv[v][0], K.blkv[v][1]));
+                obs_put((float)((double)p.x * K.ratio));
+                obs_put((float)((double)p.y * K.ratio));
+            }
+        }
+        int touching = 0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) touching += (goalc >> i) & 1;
+        obs_put((float)eps);
+        obs_put((float)gb);
+        obs_put((float)placed);
+        obs_put((float)touching);
+        obs_end();
+        double reward = 0.0;
+        reward += (prev_bd - bd) * K.rp.blockDelta;
+        reward -= K.rp.blockDistance * bd;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            reward += (prev_ad[i] - ad[i]) * K.rp.agentDelta;
+            reward -= K.rp.agentDistance * ad[i];
+        }
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) gsd(W_DIST + 2 * i, ad[i]);
+        gsd(W_DIST + 2 * n, bd);
+        const double BOUNDS = 0.1;
+#pragma unroll 1
+        for (int b = nbk; b < K.nb; ++b) {   // robots first, then the blocks (the order decides which penalty applies)
+            const double x = (double)B(b, 0), y = (double)B(b, 1);
+            if ((x < BOUNDS || x > (K.W - BOUNDS)) || (y < BOUNDS || y > (K.H - BOUNDS))) {
+                *reward_out = reward - K.rp.outOfBounds * decay_pow;
+                return true;
+            }
+        }
+#pragma unroll 1
+        for (int b = 0; b < nbk; ++b) {
+            const double x = (double)B(b, 0), y = (double)B(b, 1);
+            if ((x < BOUNDS || x > (K.W - BOUNDS)) || (y < BOUNDS || y > (K.H - BOUNDS))) {
+                *reward_out = reward - K.rp.blkOutOfBounds * decay_pow;
+                return true;
+            }
+        }
+        bool done = false;
+        if (in_place) {
+            reward += K.rp.puzzleComp * decay_pow * ((double)touching / (double)n);
+            g(W_INPLACE) = (uint32_t)(placed + 1);
+            if (placed + 1 == nbk) done = true;
+            else {   // the next block of the queue becomes the goal: distances re-based on it, contact flags start over
+                const int g2 = placed + 1;
+                goalc = 0;
+                g(W_GOALC) = 0;   // store() may already have run (staged observation rows)
+                const V2 c2 = mk(B(g2, 0), B(g2, 1));
+                gsd(W_DIST + 2 * n, py_distance((double)c2.x * K.ratio, (double)c2.y * K.ratio, gx + K.sq_target[g2][0] * K.ratio,
+                                                gy + K.sq_target[g2][1] * K.ratio));
+#pragma unroll 1
+                for (int i = 0; i < n; ++i)
+                    gsd(W_DIST + 2 * i, py_distance((double)B(nbk + i, 0) * K.ratio, (double)B(nbk + i, 1) * K.ratio, (double)c2.x * K.ratio,
+                                                    (double)c2.y * K.ratio));
+            }
+        }
+        *reward_out = reward;
+        return done;
+    }
+
     // one env.step body: control -> world.Step -> post
     MRP_HD bool env_step(const float* a, float* obs, double* reward, bool new_fixtures) {
         if (K.v2) control_v2(a); else control_v0(a);
@@ -271,19 +391,30 @@ struct Env : Sim {
     MRP_HD void spawn(uint32_t episode) {
         uint32_t d = 0;
         const double W = K.W, H = K.H;
-        double bx, by, ba;
+        double blk[3][3];   // pose of every block
         double ag[2 * MRP_MAX_AGENTS];
-        if (!K.v2) {
-            bx = 1.0 + ((W - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
-            by = 1.0 + ((H - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
-            ba = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+        if (K.nblk > 1) {
+            // square variant: the blocks start on the vertical centre line, each with its own random angle; robots and goal as v2
+            g(W_INPLACE) = 0;   // the block queue starts over
+            for (int k = 0; k < K.nblk; ++k) {
+                blk[k][0] = W / 2; blk[k][1] = H * (k + 1) / 4;
+                blk[k][2] = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            }
+            for (int i = 0; i < K.n; ++i) {
+                ag[2 * i] = 0.3 + ((W / 3 - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+                ag[2 * i + 1] = 0.3 + ((H - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            }
+        } else if (!K.v2) {
+            blk[0][0] = 1.0 + ((W - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            blk[0][1] = 1.0 + ((H - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            blk[0][2] = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
             for (int i = 0; i < K.n; ++i) {
                 ag[2 * i] = 1.0 + ((W - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
                 ag[2 * i + 1] = 1.0 + ((H - 1.0) - 1.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
             }
         } else {
-            bx = W / 2; by = H / 2;
-            ba = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
+            blk[0][0] = W / 2; blk[0][1] = H / 2;
+            blk[0][2] = 0.0 + (kTwoPiD - 0.0) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
             for (int i = 0; i < K.n; ++i) {
                 ag[2 * i] = 0.3 + ((W / 3 - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
                 ag[2 * i + 1] = 0.3 + ((H - 0.3) - 0.3) * uniform53(K.seed, kStreamSpawn, gid, episode, d++);
@@ -291,9 +422,10 @@ struct Env : Sim {
         }
         // bodies: xf.p = position, sweep.c = Mul(xf, localCenter) (b2Body ctor + ResetMassData)
         for (int b = 0; b < K.nb; ++b) {
-            float px = (float)(b == 0 ? bx : ag[2 * (b - 1)]);
-            float py = (float)(b == 0 ? by : ag[2 * (b - 1) + 1]);
-            float ang = b == 0 ? (float)ba : (K.v2 ? (float)(3.0 / 2 * kPiD) : 0.0f);
+            const bool isb = b < K.nblk;
+            float px = (float)(isb ? blk[b][0] : ag[2 * (b - K.nblk)]);
+            float py = (float)(isb ? blk[b][1] : ag[2 * (b - K.nblk) + 1]);
+            float ang = isb ? (float)blk[b][2] : (K.v2 ? (float)(3.0 / 2 * kPiD) : 0.0f);
             Xf xf;
             xf.p = mk(px, py);
             xf.q = rot_set(ang);
@@ -303,8 +435,8 @@ struct Env : Sim {
             BX(b, 6) = xf.q.s; BX(b, 7) = xf.q.c; BX(b, 8) = px; BX(b, 9) = py;
             set_rot_cache(b, xf.q, ang);
             // proxies: fat AABB = tight AABB at creation +- 0.1 (b2DynamicTree::CreateProxy)
-            int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
-            int f1 = b == 0 ? 2 : f0 + K.per_agent;
+            int f0, f1;
+            fix_range(b, f0, f1);
             for (int f = f0; f < f1; ++f) {
                 Box t = shape_aabb(fix_shape(f), xf);
                 FA(f, 0) = t.lx - kAabbExtension; FA(f, 1) = t.ly - kAabbExtension;
@@ -336,9 +468,11 @@ struct Env : Sim {
             for (int i = 0; i < K.n; ++i)
                 gsd(W_DIST + 2 * i, py_distance((double)(B(1 + i, 0) * s), (double)(B(1 + i, 1) * s), (double)(bc.x * s), (double)(bc.y * s)));
         } else {
-            gsd(W_DIST + 2 * K.n, py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, gx, gy));
+            // square variant: the goal block is block 0 and its target sits at an offset from the goal centre
+            const double tx = K.nblk > 1 ? gx + K.sq_target[0][0] * K.ratio : gx, ty = K.nblk > 1 ? gy + K.sq_target[0][1] * K.ratio : gy;
+            gsd(W_DIST + 2 * K.n, py_distance((double)bc.x * K.ratio, (double)bc.y * K.ratio, tx, ty));
             for (int i = 0; i < K.n; ++i)
-                gsd(W_DIST + 2 * i, py_distance((double)B(1 + i, 0) * K.ratio, (double)B(1 + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio));
+                gsd(W_DIST + 2 * i, py_distance((double)B(K.nblk + i, 0) * K.ratio, (double)B(K.nblk + i, 1) * K.ratio, (double)bc.x * K.ratio, (double)bc.y * K.ratio));
         }
     }
 

@@ -113,9 +113,10 @@ constexpr int CT_FIXSHAPE = 32;   // [32] shape index of fixture
 constexpr int CT_FIXFRIC = 64;    // [32] friction of fixture
 constexpr int CT_WALLFAT = 96;    // [4][4] fat AABB of wall fixtures
 constexpr int CT_WALLPOS = 112;   // [4][2] wall body positions
-constexpr int CT_SHAPES = 120;    // [8][33]
-constexpr int CT_SHAPEX = CT_SHAPES + 8 * kShapeWords;  // [8][6] bounding data per shape: centre x,y, half extents hx,hy, radius, is_box
-constexpr int CT_WALLBOX = CT_SHAPEX + 8 * 6;          // [4][4] wall polygons in world space (lo.x, lo.y, hi.x, hi.y), no radius
+constexpr int kMaxShapes = 10;    // stem, bar, octagon, two wheels, two wall boxes; square variant: + L small, L tall, I
+constexpr int CT_SHAPES = 120;    // [kMaxShapes][33]
+constexpr int CT_SHAPEX = CT_SHAPES + kMaxShapes * kShapeWords;  // [kMaxShapes][6] bounding data per shape: centre x,y, half extents hx,hy, radius, is_box
+constexpr int CT_WALLBOX = CT_SHAPEX + kMaxShapes * 6;          // [4][4] wall polygons in world space (lo.x, lo.y, hi.x, hi.y), no radius
 constexpr int CT_WORDS = CT_WALLBOX + 16;
 
 // ---- internal per-env state words in HBM ---------------------------------------------
@@ -138,6 +139,9 @@ constexpr int kTileShift = 5;
 struct SimConst {
     // variant
     int32_t variant, v2, n, nb, nfix, ndynfix, per_agent, maxc, obs_dim, act_dim, max_steps, auto_reset;
+    // blocks: bodies 0 .. nblk-1 (1; 3 = T, L, I in the square variant), robots are bodies nblk .. nb-1; the blocks' fixtures come
+    // first (nbf of them: 2, or 2 + 2 + 1), then per_agent per robot, then the four walls
+    int32_t nblk, nbf;
     int32_t w_body, w_aabb, w_con, w_total;  // word offsets of the internal state
     int32_t smem_words;                      // per-lane shared-memory words
     int32_t stage_rows;                      // 1 (device default): action rows in / observation rows out move through shared memory as coalesced runs (k_pre, k_post)
@@ -147,7 +151,12 @@ struct SimConst {
     float ag_mass, ag_invMass, ag_invI, ag_lcx, ag_lcy, ag_inertia;
     float lin_k, ang_k;  // 1/(1+h*damping)
     float h;
-    float blkv[8][2];  // observation vertex list (bar verts, then stem verts)
+    float blkv[19][2]; // observation vertex list (bar verts, then stem verts; square variant: T 8, L 7, I 4 — blkv_off)
+    int32_t blkv_off[4];
+    // square variant: mass data of blocks 1, 2 (block 0 is blk_*), target COM of block k relative to the goal centre (obs units)
+    // and target angle
+    float blkx_invMass[3], blkx_invI[3], blkx_lcx[3], blkx_lcy[3];
+    double sq_target[3][3];
     // env constants (float64, as the reference's Python arithmetic)
     double SCALE, W, H, ratio, SPEED;
     double goal_x0, goal_y0;
@@ -373,10 +382,23 @@ struct Sim {
     }
 
     MRP_HD bool is_dyn(int b) const { return b < K.nb; }
-    MRP_HD float invMass(int b) const { return b == 0 ? K.blk_invMass : (b < K.nb ? K.ag_invMass : 0.0f); }
-    MRP_HD float invI(int b) const { return b == 0 ? K.blk_invI : (b < K.nb ? K.ag_invI : 0.0f); }
+    MRP_HD float invMass(int b) const { return b == 0 ? K.blk_invMass : (b < K.nblk ? K.blkx_invMass[b] : (b < K.nb ? K.ag_invMass : 0.0f)); }
+    MRP_HD float invI(int b) const { return b == 0 ? K.blk_invI : (b < K.nblk ? K.blkx_invI[b] : (b < K.nb ? K.ag_invI : 0.0f)); }
     MRP_HD V2 localCenter(int b) const {
-        return b == 0 ? mk(K.blk_lcx, K.blk_lcy) : (b < K.nb ? mk(K.ag_lcx, K.ag_lcy) : mk(0.0f, 0.0f));
+        return b == 0 ? mk(K.blk_lcx, K.blk_lcy)
+                      : (b < K.nblk ? mk(K.blkx_lcx[b], K.blkx_lcy[b]) : (b < K.nb ? mk(K.ag_lcx, K.ag_lcy) : mk(0.0f, 0.0f)));
+    }
+    // fixtures [f0, f1) of dynamic body b (creation order: the blocks' fixtures, then the robots')
+    MRP_HD void fix_range(int b, int& f0, int& f1) const {
+        if (b >= K.nblk) { f0 = K.nbf + K.per_agent * (b - K.nblk); f1 = f0 + K.per_agent; }
+        else if (K.nblk == 1) { f0 = 0; f1 = 2; }
+        else { f0 = 2 * b; f1 = b == 2 ? 5 : f0 + 2; }   // T 0-1, L 2-3, I 4
+    }
+    // body of the current goal block: the block queue is T, L, I, so its head is the number of blocks already in place
+    MRP_HD int goal_block() {
+        if (K.nblk == 1) return 0;
+        const int placed = (int)g(W_INPLACE);
+        return placed < K.nblk - 1 ? placed : K.nblk - 1;
     }
     MRP_HD Xf body_xf(int b) {
         Xf x;
@@ -570,9 +592,10 @@ struct Sim {
     // ------------------------------------------------------------ contact events (ContactDetector, mrp00:92-111)
     MRP_HD void contact_event(uint32_t m, bool begin) {
         int bA = (m >> 20) & 15, bB = (m >> 24) & 15;
-        int ag = bA == 0 ? bB : (bB == 0 ? bA : -1);
-        if (ag >= 1 && ag < K.nb) {
-            uint32_t bit = 1u << (ag - 1);
+        const int gb = goal_block();
+        int ag = bA == gb ? bB : (bB == gb ? bA : -1);
+        if (ag >= K.nblk && ag < K.nb) {
+            uint32_t bit = 1u << (ag - K.nblk);
             goalc = begin ? (goalc | bit) : (goalc & ~bit);
         }
     }
@@ -748,8 +771,8 @@ struct Sim {
         uint32_t moved = 0;
         Xf xf2 = body_xf(b);
         V2 disp = xf2.p - xf1.p;
-        int f0 = b == 0 ? 0 : 2 + K.per_agent * (b - 1);
-        int f1 = b == 0 ? 2 : f0 + K.per_agent;
+        int f0, f1;
+        fix_range(b, f0, f1);
         for (int f = f0; f < f1; ++f) {
             const float* sh = fix_shape(f);
             // both b2PolygonShape::ComputeAABB evaluations (at xf1 and xf2) in one rolled vertex loop: same values as two
@@ -1727,7 +1750,7 @@ MRP_HD void narrow_item(const SimConst& K, const float* ct, uint32_t item) {
         if (b < K.nb) {
             const int w = K.w_body + kBodyWords * b;
             x.q.s = gfl(w + 6); x.q.c = gfl(w + 7);
-            const V2 lc = b == 0 ? mk(K.blk_lcx, K.blk_lcy) : mk(K.ag_lcx, K.ag_lcy);
+            const V2 lc = b == 0 ? mk(K.blk_lcx, K.blk_lcy) : (b < K.nblk ? mk(K.blkx_lcx[b], K.blkx_lcy[b]) : mk(K.ag_lcx, K.ag_lcy));
             const V2 r = rmul(x.q, lc);
             x.p = mk(gfl(w + 0) - r.x, gfl(w + 1) - r.y);
         } else {

@@ -170,9 +170,11 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
     // whose fat-AABB pair count averages 20 (n=3) .. 60 (n=5).  See DESIGN.md "Limits".
     if (L->max_contacts > kMaxC || L->n_dyn_fixtures > kMaxDynFix) return -3;  // needs the wide-capacity compilation (mrp_b200.cu)
     memset(ctab, 0, sizeof(float) * CT_WORDS);
-    const bool v2 = variant >= 2, heavy = (variant & 1) != 0;
+    const bool square = variant == MRP_VARIANT_SQUARE_V2;   // three blocks, Heavy-v2 dynamics (extension, include/mrp_state.h)
+    const bool v2 = variant >= 2, heavy = square || (variant & 1) != 0;
     const int n = L->n_agents;
-    K->variant = variant; K->v2 = v2 ? 1 : 0; K->n = n; K->nb = n + 1;
+    K->nblk = square ? MRP_SQUARE_BLOCKS : 1; K->nbf = square ? 5 : 2;
+    K->variant = variant; K->v2 = v2 ? 1 : 0; K->n = n; K->nb = n + K->nblk;
     K->nfix = L->n_fixtures; K->ndynfix = L->n_dyn_fixtures; K->per_agent = v2 ? 3 : 1;
     K->maxc = L->max_contacts; K->obs_dim = L->obs_dim; K->act_dim = L->act_dim; K->max_steps = L->max_episode_steps;
     K->w_body = W_DIST + 2 * (n + 1);
@@ -252,19 +254,59 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
         K->blkv[i][0] = bar.vx[i]; K->blkv[i][1] = bar.vy[i];
         K->blkv[4 + i][0] = stem.vx[i]; K->blkv[4 + i][1] = stem.vy[i];
     }
-    // shapes: 0 stem, 1 bar, 2 octagon, 3 wheel1, 4 wheel2, 5 wall L/R, 6 wall B/T
+    K->blkv_off[0] = 0; K->blkv_off[1] = 8; K->blkv_off[2] = 8; K->blkv_off[3] = 8;
+    K->blkx_invMass[0] = K->blk_invMass; K->blkx_invI[0] = K->blk_invI; K->blkx_lcx[0] = K->blk_lcx; K->blkx_lcy[0] = K->blk_lcy;
+    // shapes: 0 stem, 1 bar, 2 octagon, 3 wheel1, 4 wheel2, 5 wall L/R, 6 wall B/T; square variant: 7 L small, 8 L tall, 9 I
     put_shape(ctab, 0, &stem); put_shape(ctab, 1, &bar); put_shape(ctab, 2, &oct);
     if (v2) { put_shape(ctab, 3, &wheel1); put_shape(ctab, 4, &wheel2); }
     put_shape(ctab, 5, &wallLR); put_shape(ctab, 6, &wallBT);
+    if (square) {
+        // L and I blocks (mrp00:334-351, blocks.py:92-109) at the v2 T-block's unit u = 0.1; creation order small box, tall box
+        const float u = 0.1f;
+        HostPoly lsmall, ltall, ibox;
+        poly_box(&lsmall, 1 * u, 1 * u, 1 * u, 0.5f * u);
+        poly_box(&ltall, 1 * u, 2 * u, -1 * u, -0.5f * u);
+        poly_box_plain(&ibox, 1 * u, 2 * u);
+        put_shape(ctab, 7, &lsmall); put_shape(ctab, 8, &ltall); put_shape(ctab, 9, &ibox);
+        {   // fixture lists newest first
+            const HostPoly* ps[2] = {&ltall, &lsmall};
+            float ds[2] = {blk_density, blk_density};
+            HostBodyMass bm;
+            body_mass(ps, ds, 2, &bm);
+            K->blkx_invMass[1] = bm.invMass; K->blkx_invI[1] = bm.invI; K->blkx_lcx[1] = bm.lcx; K->blkx_lcy[1] = bm.lcy;
+            const HostPoly* pi[1] = {&ibox};
+            body_mass(pi, ds, 1, &bm);
+            K->blkx_invMass[2] = bm.invMass; K->blkx_invI[2] = bm.invI; K->blkx_lcx[2] = bm.lcx; K->blkx_lcy[2] = bm.lcy;
+        }
+        // observation vertices per block: fixtures newest first, vertices not listed before (mrp00:356-361): L has 7
+        int nv = 8;
+        const HostPoly* lists[2][2] = {{&ltall, &lsmall}, {&ibox, nullptr}};
+        for (int k = 0; k < 2; ++k) {
+            const int first = nv;
+            for (int fi = 0; fi < 2 && lists[k][fi]; ++fi)
+                for (int i = 0; i < 4; ++i) {
+                    const float x = lists[k][fi]->vx[i], y = lists[k][fi]->vy[i];
+                    bool seen = false;
+                    for (int q = first; q < nv; ++q) if (K->blkv[q][0] == x && K->blkv[q][1] == y) seen = true;
+                    if (!seen) { K->blkv[nv][0] = x; K->blkv[nv][1] = y; ++nv; }
+                }
+            K->blkv_off[2 + k] = nv;
+        }
+        // target poses of mrp00:83-88 (given there for a block unit of 0.5 m) at u = 0.1: the COMs of T, L (turned by pi/2) and I
+        // that tile the square [-3u, 3u]^2 around the goal centre
+        const double rel[3][3] = {{0.0, 0.75 / 0.5, 0.0}, {-2. / 3. / 0.5, -2. / 3. / 0.5, 0.5 * 3.14159265358979323846}, {1.0 / 0.5, -0.5 / 0.5, 0.0}};
+        for (int k = 0; k < 3; ++k) { K->sq_target[k][0] = rel[k][0] * 0.1; K->sq_target[k][1] = rel[k][1] * 0.1; K->sq_target[k][2] = rel[k][2]; }
+    }
     int f = 0;
     auto fix = [&](int body, int shape, float fr) {
         ctab[CT_FIXBODY + f] = (float)body; ctab[CT_FIXSHAPE + f] = (float)shape; ctab[CT_FIXFRIC + f] = fr; ++f;
     };
     fix(0, 0, blk_friction);
     fix(0, 1, blk_friction);
+    if (square) { fix(1, 7, blk_friction); fix(1, 8, blk_friction); fix(2, 9, blk_friction); }
     for (int i = 0; i < n; ++i) {
-        fix(1 + i, 2, ag_friction);
-        if (v2) { fix(1 + i, 3, ag_friction); fix(1 + i, 4, ag_friction); }
+        fix(K->nblk + i, 2, ag_friction);
+        if (v2) { fix(K->nblk + i, 3, ag_friction); fix(K->nblk + i, 4, ag_friction); }
     }
     const double borders[4][2] = {{0, 0.5}, {1, 0.5}, {0.5, 0}, {0.5, 1}};
     for (int k = 0; k < 4; ++k) {

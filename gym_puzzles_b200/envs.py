@@ -141,3 +141,10 @@ class MultiRobotPuzzle2(MultiRobotPuzzle):
 
 class MultiRobotPuzzleHeavy2(MultiRobotPuzzle2):
     env_id = "MultiRobotPuzzleHeavy-v2"   # heavy = True: block density 20 (reference mrp02:162-163,711-712)
+
+
+class MultiRobotPuzzleSquare2(MultiRobotPuzzle2):
+    """Extension (BASELINE.json configs[4]), NOT a reference env: the T, L and I blocks of reference mrp00:320-351 /
+    blocks.py:70-109 with Heavy-v2 dynamics; the blocks are pushed, in the reference's block_queue order, to the poses of
+    mrp00:83-88 that tile a square around the goal (semantics: DESIGN.md "Square variant")."""
+    env_id = "MultiRobotPuzzleSquare-v2"

@@ -13,6 +13,8 @@ registry = {
     "MultiRobotPuzzleHeavy-v0": EnvSpec("MultiRobotPuzzleHeavy-v0", envs.MultiRobotPuzzleHeavy, 3000, 500),
     "MultiRobotPuzzle-v2": EnvSpec("MultiRobotPuzzle-v2", envs.MultiRobotPuzzle2, 2000, 500),
     "MultiRobotPuzzleHeavy-v2": EnvSpec("MultiRobotPuzzleHeavy-v2", envs.MultiRobotPuzzleHeavy2, 2000, 500),
+    # extension, not in the reference's registry: BASELINE.json configs[4] (three blocks forming a square, Heavy-v2 dynamics)
+    "MultiRobotPuzzleSquare-v2": EnvSpec("MultiRobotPuzzleSquare-v2", envs.MultiRobotPuzzleSquare2, 2000, 500),
 }
 
 

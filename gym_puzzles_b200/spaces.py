@@ -46,6 +46,11 @@ def observation_space(env_id, n_agents):
     inf, tp = np.inf, 2 * np.pi
     if env_id.endswith("-v0"):
         high = [inf] * 4 * n_agents + [inf, inf, tp, inf] + [inf] * 16
+    elif env_id == "MultiRobotPuzzleSquare-v2":   # extension: per block 4 values + its vertices (T 8, L 7, I 4), then 4 scalars
+        high = [inf, inf, tp, inf, inf, inf, inf, inf, inf] * n_agents
+        for nv in (8, 7, 4):
+            high += [inf, inf, tp, inf] + [inf] * (2 * nv)
+        high += [inf] * 4
     else:
         high = [inf, inf, tp, inf, inf, inf, inf, inf, inf] * n_agents + [inf, inf, tp, inf] + [inf] * 16 + [inf]
     high = np.array(high, dtype=np.float32)

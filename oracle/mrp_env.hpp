@@ -59,6 +59,15 @@ struct Env : ContactListener {
     double SCALE, VIEW_W, VIEW_H, W, H;
 
     World* world = nullptr;
+    // "square" extension (BASELINE.json configs[4], not a reference env): three blocks T, L, I with Heavy-v2 dynamics;
+    // blocks[k] are world bodies 0..2, the goal block is blocks[min(blks_in_place, 2)] (block_queue order T, L, I,
+    // mrp00:293-297) and block_body always names the current goal block.  With one block everything below reduces to the
+    // reference's v2 env.
+    bool square = false;
+    int nblk = 1;
+    int blocks[MRP_SQUARE_BLOCKS] = {0, 0, 0};
+    std::vector<Vec2> sq_vertices[MRP_SQUARE_BLOCKS];  // per block, de-duplicated the reference's way (mrp00:356-361)
+    double sq_target[MRP_SQUARE_BLOCKS][3];            // target COM offset from the goal centre (metres) and target angle
     int block_body = 0;
     std::vector<int> agent_body;
     bool goal_contact[MRP_MAX_AGENTS];
@@ -78,6 +87,16 @@ struct Env : ContactListener {
         n = L.n_agents;
         v2 = variant >= 2;
         heavy = (variant & 1) != 0;
+        square = variant == MRP_VARIANT_SQUARE_V2;
+        if (square) {
+            heavy = true;                 // Heavy-v2 dynamics
+            nblk = MRP_SQUARE_BLOCKS;
+            // target poses of mrp00:83-88 (written there for block unit 0.5 m), in units of u = 0.1 m (the v2 T-block's unit):
+            // COM of T at (0, 1.5u), of L at (-4/3 u, -4/3 u) turned by pi/2, of I at (2u, -u): together the square [-3u, 3u]^2
+            const double u = 0.1;
+            const double rel[3][3] = {{0.0, 0.75 / 0.5, 0.0}, {-2. / 3. / 0.5, -2. / 3. / 0.5, 0.5 * M_PI}, {1.0 / 0.5, -0.5 / 0.5, 0.0}};
+            for (int k = 0; k < 3; ++k) { sq_target[k][0] = rel[k][0] * u; sq_target[k][1] = rel[k][1] * u; sq_target[k][2] = rel[k][2]; }
+        }
         if (!v2) {
             SCALE = 30.0; VIEW_W = 640; VIEW_H = 480;                       // mrp00:40-42
             rp.agentDelta = 10; rp.agentDistance = 0.1; rp.blockDelta = 50; rp.blockDistance = 0.025;
@@ -114,10 +133,34 @@ struct Env : ContactListener {
         world = new World();
         world->listener = this;
         agent_body.clear();
+        float damp = 5.0f;
+        if (square) {
+            // blocks.py:70-109 / mrp00:320-351 shapes at unit u = 0.1, Heavy-v2 material (mrp02:320-342); blk: [3][3] poses
+            const float u = 0.1f;
+            for (int k = 0; k < 3; ++k) {
+                double bx = blk ? blk[3 * k] : W / 2, by = blk ? blk[3 * k + 1] : H * (k + 1) / 4, ba = blk ? blk[3 * k + 2] : 0.0;
+                blocks[k] = world->CreateBody(kDynamic, Vec2((float)bx, (float)by), (float)ba, damp, damp);
+                Polygon a, b;
+                std::vector<Polygon> fx;   // creation order
+                if (k == 0) { a.SetAsBox(1 * u, 1 * u, Vec2(0.0f, -1 * u), 0.0f); b.SetAsBox(3 * u, 1 * u, Vec2(0.0f, 1 * u), 0.0f); fx = {a, b}; }
+                else if (k == 1) { a.SetAsBox(1 * u, 1 * u, Vec2(1 * u, 0.5f * u), 0.0f); b.SetAsBox(1 * u, 2 * u, Vec2(-1 * u, -0.5f * u), 0.0f); fx = {a, b}; }
+                else { a.SetAsBox(1 * u, 2 * u); fx = {a}; }
+                for (const Polygon& p : fx) world->CreateFixture(blocks[k], p, 20.0f, 0.01f, 0.0f);
+                // vertex list: fixtures newest first, vertices not seen before (mrp00:356-361)
+                sq_vertices[k].clear();
+                for (int f = (int)fx.size() - 1; f >= 0; --f)
+                    for (int i = 0; i < fx[f].count; ++i) {
+                        bool seen = false;
+                        for (const Vec2& q : sq_vertices[k]) if (q.x == fx[f].v[i].x && q.y == fx[f].v[i].y) seen = true;
+                        if (!seen) sq_vertices[k].push_back(fx[f].v[i]);
+                    }
+            }
+            block_body = blocks[blks_in_place < 2 ? (blks_in_place < 0 ? 0 : blks_in_place) : 2];
+        } else {
         double bx = blk ? blk[0] : W / 2, by = blk ? blk[1] : H / 2, ba = blk ? blk[2] : 0.0;
         // _generate_blocks  (mrp00:299-361, mrp02:313-350)
-        float damp = 5.0f;
         block_body = world->CreateBody(kDynamic, Vec2((float)bx, (float)by), (float)ba, damp, damp);
+        blocks[0] = block_body;
         Polygon stem, bar;
         if (!v2) {
             double S = 2.0;
@@ -136,6 +179,7 @@ struct Env : ContactListener {
         }
         // blks_vertices: block.fixtures iterates newest-first => bar, then stem
         for (int i = 0; i < 4; ++i) { blk_vertices[i] = bar.v[i]; blk_vertices[4 + i] = stem.v[i]; }
+        }
         // _generate_agents  (mrp00:363-378, mrp02:352-392)
         for (int i = 0; i < n; ++i) {
             double ax = agents ? agents[2 * i] : 1.0 + i, ay = agents ? agents[2 * i + 1] : 1.0;
@@ -189,9 +233,13 @@ struct Env : ContactListener {
             block_distance = py_distance((double)px, (double)py, goal_x, goal_y);
         } else {
             double ratio = SCALE / VIEW_W;
-            block_distance = py_distance((double)c.x * ratio, (double)c.y * ratio, goal_x, goal_y);
+            block_distance = py_distance((double)c.x * ratio, (double)c.y * ratio, target_x(goal_index()), target_y(goal_index()));
         }
     }
+    // square: index of the current goal block and the target COM of block k (goal centre + offset, in obs units)
+    int goal_index() const { return square ? (blks_in_place < 2 ? blks_in_place : 2) : 0; }
+    double target_x(int k) const { return square ? goal_x + sq_target[k][0] * (SCALE / VIEW_W) : goal_x; }
+    double target_y(int k) const { return square ? goal_y + sq_target[k][1] * (SCALE / VIEW_W) : goal_y; }
     void calculate_agent_distance() {  // mrp00:285-291 / mrp02:271-277
         Vec2 b = wc(block_body);
         for (int i = 0; i < n; ++i) {
@@ -210,8 +258,14 @@ struct Env : ContactListener {
     void spawn() {
         uint32_t d = 0;
         auto U = [&](double lo, double hi) { return lo + (hi - lo) * uniform53(seed, kStreamSpawn, gid, (uint32_t)episode, d++); };
-        double blk[3], ag[2 * MRP_MAX_AGENTS];
-        if (!v2) {
+        double blk[3 * MRP_SQUARE_BLOCKS], ag[2 * MRP_MAX_AGENTS];
+        if (square) {
+            // extension: the three blocks start on the vertical centre line, each with its own random angle; robots and goal as v2
+            const double BORDER = 0.3;
+            blks_in_place = 0;   // the block queue starts over (mrp00:403-404)
+            for (int k = 0; k < 3; ++k) { blk[3 * k] = W / 2; blk[3 * k + 1] = H * (k + 1) / 4; blk[3 * k + 2] = U(0, 2 * M_PI); }
+            for (int i = 0; i < n; ++i) { ag[2 * i] = U(BORDER, W / 3 - BORDER); ag[2 * i + 1] = U(BORDER, H - BORDER); }
+        } else if (!v2) {
             const double BORDER = 1;
             blk[0] = U(BORDER, W - BORDER);
             blk[1] = U(BORDER, H - BORDER);
@@ -339,6 +393,7 @@ struct Env : ContactListener {
             *done_out = done;
             return;
         }
+        if (square) { square_post(obs, prev_agent_dist, prev_distance, reward_out, done_out); return; }
         // ---- v2 (mrp02:491-584)
         double ratio = SCALE / VIEW_W;
         for (int i = 0; i < n; ++i) {
@@ -408,6 +463,86 @@ struct Env : ContactListener {
         *done_out = done;
     }
 
+    // ---- square extension: observation / reward / termination after world.Step, modelled on mrp02:491-584.
+    // obs: per robot the 9 values of v2 (relative to the goal block); per block k = T, L, I: (x - tx, y - ty, (ta - angle) / pi,
+    // distance to its target, vertices); epsilon; goal-block index; blocks in place; robots touching the goal block.  Reward: v2's shaping on the goal block;
+    // when the goal block's COM is within epsilon of its target: + puzzleComp * decay * contacts / n, the next block of the
+    // queue becomes the goal (distances re-based on it, contact flags cleared); done when all three are placed.
+    void square_post(double* obs, const double* prev_agent_dist, double prev_distance, double* reward_out, bool* done_out) {
+        const double ratio = SCALE / VIEW_W;
+        const int g = goal_index();
+        const Body& blk = world->bodies[blocks[g]];
+        int o = 0;
+        double reward = 0;
+        for (int i = 0; i < n; ++i) {
+            const Body& ag = world->bodies[agent_body[i]];
+            double aX = (double)ag.sweep.c.x * ratio, aY = (double)ag.sweep.c.y * ratio;
+            double theta = py_mod((double)ag.sweep.a, 2 * M_PI);
+            double norm_theta = theta <= M_PI ? -theta / M_PI : (2 * M_PI - theta) / M_PI;
+            obs[o++] = aX; obs[o++] = aY; obs[o++] = norm_theta;
+            double bX = (double)blk.sweep.c.x * ratio, bY = (double)blk.sweep.c.y * ratio;
+            obs[o++] = aX - bX; obs[o++] = aY - bY;
+            obs[o++] = ag.v.x; obs[o++] = ag.v.y; obs[o++] = ag.w;
+            obs[o++] = agent_dist[i];
+        }
+        bool in_place = false;
+        for (int k = 0; k < 3; ++k) {
+            const Body& bk = world->bodies[blocks[k]];
+            double x = (double)bk.sweep.c.x * ratio, y = (double)bk.sweep.c.y * ratio;
+            double angle = py_mod((double)bk.sweep.a, 2 * M_PI);
+            double fx = target_x(k), fy = target_y(k);
+            double a_diff = (sq_target[k][2] - angle) / M_PI;
+            if (k == g) in_place = !(std::fabs(fx - x) > rp.scaled_epsilon) && !(std::fabs(fy - y) > rp.scaled_epsilon);
+            obs[o++] = x - fx; obs[o++] = y - fy; obs[o++] = a_diff;
+            obs[o++] = py_distance(x, y, fx, fy);
+            for (const Vec2& v : sq_vertices[k]) {
+                Vec2 p = bk.GetWorldPoint(v);
+                obs[o++] = (double)p.x * ratio;
+                obs[o++] = (double)p.y * ratio;
+            }
+        }
+        obs[o++] = rp.scaled_epsilon;
+        obs[o++] = (double)g;
+        obs[o++] = (double)blks_in_place;
+        {
+            int touching = 0;
+            for (int i = 0; i < n; ++i) if (goal_contact[i]) ++touching;
+            obs[o++] = (double)touching;
+        }
+        reward += (prev_distance - block_distance) * rp.blockDelta;
+        reward -= rp.blockDistance * block_distance;
+        for (int i = 0; i < n; ++i) {
+            reward += (prev_agent_dist[i] - agent_dist[i]) * rp.agentDelta;
+            reward -= rp.agentDistance * agent_dist[i];
+        }
+        const double BOUNDS = 0.1;
+        auto oob = [&](Vec2 c) {
+            double x = c.x, y = c.y;
+            return (x < BOUNDS || x > (W - BOUNDS)) || (y < BOUNDS || y > (H - BOUNDS));
+        };
+        for (int i = 0; i < n; ++i)
+            if (oob(wc(agent_body[i]))) { *reward_out = reward - rp.outOfBounds * rp.decay_pow; *done_out = true; return; }
+        for (int k = 0; k < 3; ++k)
+            if (oob(wc(blocks[k]))) { *reward_out = reward - rp.blkOutOfBounds * rp.decay_pow; *done_out = true; return; }
+        bool done = false;
+        if (in_place) {
+            int num_in_contact = 0;
+            for (int i = 0; i < n; ++i) if (goal_contact[i]) ++num_in_contact;
+            reward += rp.puzzleComp * rp.decay_pow * ((double)num_in_contact / (double)n);
+            prev_blks_in_place = blks_in_place;
+            ++blks_in_place;
+            if (blks_in_place == 3) done = true;
+            else {  // _set_next_goal_block
+                block_body = blocks[goal_index()];
+                for (int i = 0; i < n; ++i) goal_contact[i] = false;
+                calculate_distance();
+                calculate_agent_distance();
+            }
+        }
+        *reward_out = reward;
+        *done_out = done;
+    }
+
     // ---- reset(): respawn + hidden random-action step (mrp00:392-411)
     void reset(double* obs) {
         ++episode;
@@ -451,8 +586,8 @@ struct Env : ContactListener {
         w[3] = (uint32_t)world->contactList.size();
         for (int i = 0; i < n; ++i) w[L.off_goal_contact + i] = goal_contact[i] ? 1 : 0;
         float* fb = (float*)(w + L.off_bodies);
-        for (int b = 0; b <= n; ++b) {
-            const Body& B = world->bodies[b == 0 ? block_body : agent_body[b - 1]];
+        for (int b = 0; b < nblk + n; ++b) {
+            const Body& B = world->bodies[b < nblk ? blocks[b] : agent_body[b - nblk]];
             fb[6 * b + 0] = B.sweep.c.x; fb[6 * b + 1] = B.sweep.c.y; fb[6 * b + 2] = B.sweep.a;
             fb[6 * b + 3] = B.v.x; fb[6 * b + 4] = B.v.y; fb[6 * b + 5] = B.w;
         }
@@ -496,11 +631,11 @@ struct Env : ContactListener {
         blks_in_place = (int)w[2];
         int nc = (int)w[3];
         const float* fb = (const float*)(w + L.off_bodies);
-        double blk[3] = {0, 0, 0}, ag[2 * MRP_MAX_AGENTS];
+        double blk[3 * MRP_SQUARE_BLOCKS] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ag[2 * MRP_MAX_AGENTS];
         for (int i = 0; i < 2 * MRP_MAX_AGENTS; ++i) ag[i] = 0;
-        build_world(blk, ag);  // shapes/masses; poses overwritten below
-        // canonical body b is world body b (block, then the robots; walls are created last)
-        world->LoadState(n + 1, fb, L.n_dyn_fixtures, (const float*)(w + L.off_aabb), nc, w + L.off_contacts);
+        build_world(blk, ag);  // shapes/masses; poses overwritten below (blks_in_place is set: the goal block is chosen by it)
+        // canonical body b is world body b (block(s), then the robots; walls are created last)
+        world->LoadState(nblk + n, fb, L.n_dyn_fixtures, (const float*)(w + L.off_aabb), nc, w + L.off_contacts);
         for (int i = 0; i < n; ++i) goal_contact[i] = w[L.off_goal_contact + i] != 0;
         double dd[MRP_MAX_AGENTS + 1];
         std::memcpy(dd, w + L.off_dists, sizeof(double) * (n + 1));

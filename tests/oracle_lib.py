@@ -47,7 +47,8 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-VARIANTS = {"MultiRobotPuzzle-v0": 0, "MultiRobotPuzzleHeavy-v0": 1, "MultiRobotPuzzle-v2": 2, "MultiRobotPuzzleHeavy-v2": 3}
+VARIANTS = {"MultiRobotPuzzle-v0": 0, "MultiRobotPuzzleHeavy-v0": 1, "MultiRobotPuzzle-v2": 2, "MultiRobotPuzzleHeavy-v2": 3,
+            "MultiRobotPuzzleSquare-v2": 4}
 
 
 class OracleBatch:
