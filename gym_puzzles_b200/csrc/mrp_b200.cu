@@ -935,7 +935,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (!h) return fail(-5, "mrp_create: out of host memory");
     memset(h, 0, sizeof(*h));
 #ifndef MRP_WIDE
-    if (cfg->variant >= 2 && cfg->n_agents > 2) {  // MultiRobotPuzzle2(num_agents > 2): contact capacity 192 build
+    if ((cfg->variant >= 2 && cfg->n_agents > 2) || cfg->variant == MRP_VARIANT_SQUARE_V2) {  // MultiRobotPuzzle2(num_agents > 2), square variant: contact capacity 192 build
         const int rc = mrp_create_wide(cfg, &h->wide);
         if (rc) {
             snprintf(g_err, sizeof(g_err), "%s", mrp_last_error_wide());
@@ -1029,7 +1029,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
     h->smem_big = sizeof(float) * ((size_t)(9 * K.nb + 24) + kBigRecWords) * kBigLanes;
-    h->big_split = getenv("MRP_BIG") ? atoi(getenv("MRP_BIG")) : (cfg->num_envs >= 32768 ? 1 : 0);
+    // the square variant's blocks lean on each other: islands with more than two contacts are the rule there, not the 1.7 % tail the
+    // side kernel was built for (measured: 14.2 ms with the bulk kernels, 30.8 ms with k_solve_big, 524,288 envs)
+    h->big_split = getenv("MRP_BIG") ? atoi(getenv("MRP_BIG")) : (cfg->num_envs >= 32768 && cfg->variant != MRP_VARIANT_SQUARE_V2 ? 1 : 0);
 #ifndef MRP_HOST_EMU
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);

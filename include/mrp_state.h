@@ -103,7 +103,8 @@ static inline int mrp_layout_for(int variant, int n_agents, mrp_layout* L) {
     /* capacity: 32 covers every registered variant (measured maximum 21 on long rollouts; overflow is counted);
      * MultiRobotPuzzle2(num_agents > 2) puts three-fixture robots side by side and reaches > 100 live fat-AABB pairs
      * (188 possible with 5 robots), so it gets the wide capacity */
-    int cap = (v2 && n_agents > 2) ? 192 : 32;
+    /* the square variant packs three multi-fixture blocks side by side: 32 slots overflow about once per 6e4 env-steps */
+    int cap = ((v2 && n_agents > 2) || square) ? 192 : 32;
     L->max_contacts = pot < cap ? pot : cap;
     /* square: per robot 9, per block 4 + 2 * vertices (T 8, L 7 after the reference's de-duplication, I 4), epsilon,
      * goal-block index, blocks in place, robots in contact with the goal block */
