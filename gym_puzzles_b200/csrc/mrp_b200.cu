@@ -725,6 +725,7 @@ __global__ void k_fix_rot(const __grid_constant__ SimConst K, int64_t begin, int
 // handle
 // ------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 8;
+constexpr int kMaxWaves = 4;   // mrp_step_host: the env range can run as up to four front-half waves (see there)
 
 struct mrp_handle {
 #ifndef MRP_WIDE
@@ -746,7 +747,10 @@ struct mrp_handle {
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
 #ifndef MRP_HOST_EMU
     cudaStream_t cstream[kMaxChunks];
-    cudaEvent_t cfork, cact, cact0, cpre, cfree, cbig, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks];
+    cudaEvent_t cfork, cact, cact0, cpre, cfree, cbig, cjoin[kMaxChunks], cpost[kMaxChunks], cd2h[kMaxChunks], cdone[kMaxChunks];
+    cudaEvent_t wpre[kMaxWaves], wbig[kMaxWaves], wjoin[kMaxWaves];
+    int host_waves;            // MRP_HOST_WAVES: front-half waves of mrp_step_host (default: measured best per batch size)
+    int wave_bound[kMaxWaves + 1];   // wave w covers the envs of back chunks [wave_bound[w], wave_bound[w + 1]) (of nchunks_host)
     cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
     int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
     cudaEvent_t tr[32];        // MRP_TRACE=1: timeline of one mrp_step_host call (created on first use)
@@ -762,6 +766,7 @@ struct mrp_handle {
     cudaGraphExec_t gx_step, gx_host;
     SimConst gk_step, gk_host;   // handle constants the graphs were captured with
     const void* gp_host[5];      // host pointers of the captured mrp_step_host
+    const float* gp_act;         // action pointer of the captured mrp_step
     int64_t gl_step, gl_host;    // launches inside one replay
 #endif
     int64_t launches;
@@ -879,7 +884,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     if (h->gx_step) cudaGraphExecDestroy(h->gx_step);
     if (h->gx_host) cudaGraphExecDestroy(h->gx_host);
     if (h->cfork) {
-        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); }
+        for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); cudaEventDestroy(h->cdone[c]); }
         cudaStreamDestroy(h->copy_stream);
         if (h->tr_init) for (int i = 0; i < 32; ++i) cudaEventDestroy(h->tr[i]);
         cudaEventDestroy(h->cfork);
@@ -888,6 +893,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
         cudaEventDestroy(h->cpre);
         cudaEventDestroy(h->cfree);
         cudaEventDestroy(h->cbig);
+        for (int w = 0; w < kMaxWaves; ++w) { cudaEventDestroy(h->wpre[w]); cudaEventDestroy(h->wbig[w]); cudaEventDestroy(h->wjoin[w]); }
     }
 #else
     free(h->emu_sm);
@@ -986,7 +992,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     rc |= DEV_ALLOC(K.trunc, N);
     rc |= DEV_ALLOC(K.stats, sizeof(double) * MRP_N_STATS);
     rc |= DEV_ALLOC(K.reset_list, sizeof(int32_t) * N);
-    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * 32 * (kMaxChunks + 1));
+    rc |= DEV_ALLOC(K.cnt, sizeof(int32_t) * 32 * (kMaxChunks + 1 + kMaxWaves));
     // worst case: every contact slot of every env touching (never reached; pages stay untouched otherwise)
     rc |= DEV_ALLOC_RAW(K.pool, sizeof(float) * N * K.maxc * VC_WORDS);
     rc |= DEV_ALLOC(K.task_env, sizeof(int32_t) * kTaskClasses * N * K.nb);  // classes x at most one island per dynamic body
@@ -1063,6 +1069,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
             cudaEventCreateWithFlags(&h->cjoin[c], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&h->cpost[c], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&h->cd2h[c], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->cdone[c], cudaEventDisableTiming);
         }
         cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi);
         h->host_early_copy = getenv("MRP_HOST_EARLY_COPY") ? atoi(getenv("MRP_HOST_EARLY_COPY")) : 1;
@@ -1073,6 +1080,29 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaEventCreateWithFlags(&h->cpre, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cfree, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->cbig, cudaEventDisableTiming);
+    for (int w = 0; w < kMaxWaves; ++w) {
+        cudaEventCreateWithFlags(&h->wpre[w], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->wbig[w], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->wjoin[w], cudaEventDisableTiming);
+    }
+    // measured end to end (1M Heavy-v0 envs, pinned buffers): 7.09 / 6.66 / 6.25 / 6.37 ms per step with 1 / 2 / 3 / 4 waves; 524,288 envs
+    // 3.91 / 3.65 / 3.58 / 3.60; v0 4.08 / 3.75 / 3.63 / 3.67 (profiles/r2_e2e_waves.md)
+    h->host_waves = getenv("MRP_HOST_WAVES") ? atoi(getenv("MRP_HOST_WAVES")) : (cfg->num_envs >= 262144 ? 3 : 1);
+    if (h->host_waves < 1 || h->host_waves > kMaxWaves || h->nchunks_host < 2 * h->host_waves) h->host_waves = 1;
+    {
+        // wave boundaries in eighths of the chunks; every wave spans at least two chunks (its front stream and the stream of its
+        // big-island kernel are the streams of its first two chunks).  MRP_HOST_WAVE_BOUNDS="3,6" overrides the inner boundaries.
+        static const int dflt[kMaxWaves + 1][kMaxWaves + 1] = {{0, 0, 0, 0, 0}, {0, 8, 8, 8, 8}, {0, 3, 8, 8, 8}, {0, 3, 6, 8, 8}, {0, 2, 4, 6, 8}};
+        for (int w = 0; w <= kMaxWaves; ++w) h->wave_bound[w] = dflt[h->host_waves][w] * h->nchunks_host / 8;
+        if (const char* b = getenv("MRP_HOST_WAVE_BOUNDS")) {
+            int v[3] = {0, 0, 0};
+            const int got = sscanf(b, "%d,%d,%d", &v[0], &v[1], &v[2]);
+            bool ok = got == h->host_waves - 1;
+            for (int i = 0; ok && i < got; ++i) ok = v[i] >= (i ? v[i - 1] : 0) + 2 && v[i] <= h->nchunks_host - 2 * (got - i);
+            for (int i = 0; ok && i < got; ++i) h->wave_bound[i + 1] = v[i];
+        }
+        h->wave_bound[h->host_waves] = h->nchunks_host;
+    }
     {
         // measured at 1M envs: Heavy-v0 -4 %, v0 -1.5 %, v2 with 5 robots -5 %; v2 with its default two robots +9 % (hardly
         // any env owns a solver task there, so the split only adds launches): off for that case
@@ -1230,7 +1260,8 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
 // back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
 // events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
 static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready,
-                         cudaEvent_t first_half_ready = nullptr, int64_t half = 0, cudaEvent_t* tr = nullptr) {
+                         cudaEvent_t first_half_ready = nullptr, int64_t half = 0, cudaEvent_t* tr = nullptr, cudaStream_t big_stream = nullptr,
+                         cudaEvent_t big_fork = nullptr, cudaEvent_t big_join = nullptr) {
     const unsigned grid = grid_for(K.nloc, kBlock);
     if (grid == 0) return;
     const unsigned sgrid = grid < (unsigned)h->num_sms * (unsigned)h->solver_ctas ? grid : (unsigned)h->num_sms * (unsigned)h->solver_ctas;
@@ -1262,10 +1293,24 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     }
     if (tr) cudaEventRecord(tr[22], st);
     if (timed) cudaEventRecord(h->evk[h->ev_n][0], st);
-    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K);
+    // big islands beside the bulk solver kernels, as in launch_step (the third chunk stream is idle until the back half starts)
+    const bool big_on = h->big_split && !timed;
+    SimConst Ks = K;
+    Ks.big_split = big_on ? 1 : 0;
+    cudaStream_t sb = big_stream ? big_stream : h->cstream[2];
+    cudaEvent_t efork = big_fork ? big_fork : h->cpre, ejoin = big_join ? big_join : h->cbig;
+    if (big_on) {
+        cudaEventRecord(efork, st);
+        cudaStreamWaitEvent(sb, efork, 0);
+        k_solve_big<<<(unsigned)h->num_sms, kBigLanes, h->smem_big, sb>>>(Ks);
+        cudaEventRecord(ejoin, sb);
+        h->launches += 1;
+    }
+    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(Ks);
     if (timed) cudaEventRecord(h->evk[h->ev_n][1], st);
-    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K);
+    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(Ks);
     if (timed) cudaEventRecord(h->evk[h->ev_n][2], st);
+    if (big_on) cudaStreamWaitEvent(st, ejoin, 0);
     h->launches += 6;
 }
 static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, bool clear, cudaEvent_t after_post = nullptr) {
@@ -1515,6 +1560,16 @@ static SimConst back_chunk_const(const mrp_handle* h, const SimConst& K0, int c,
     return K;
 }
 
+// front-half wave w of mrp_step_host: the envs of back chunks [c0, c1), with its own counters (blocks behind those of the back
+// chunks), queues and pool slice
+static SimConst wave_const(const mrp_handle* h, const SimConst& K0, int w, int c0, int c1, int nch) {
+    const SimConst first = chunk_const(h, K0, c0, nch), last = chunk_const(h, K0, c1 - 1, nch);
+    SimConst K = first;
+    K.nloc = (int32_t)(last.env0 + last.nloc - first.env0);
+    K.cnt = K0.cnt + 32 * (kMaxChunks + 1 + w);
+    return K;
+}
+
 // chunks of one step call: 1 while the per-phase timers are on (their events live on one stream)
 static int step_chunks(const mrp_handle* h, int wanted) {
     int nch = h->timing ? 1 : wanted;
@@ -1565,10 +1620,12 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (graph_ok(h, nch)) {
-        if (h->gx_step && memcmp(&h->gk_step, &K, sizeof(SimConst)) != 0) { cudaGraphExecDestroy(h->gx_step); h->gx_step = nullptr; }
+        // compared as stored in the handle (memcpy of the same object: padding bytes included and stable)
+        if (h->gx_step && (memcmp(&h->gk_step, &h->K, sizeof(SimConst)) != 0 || h->gp_act != K.act)) { cudaGraphExecDestroy(h->gx_step); h->gx_step = nullptr; }
         if (!h->gx_step) {
             h->gx_step = capture_graph(h, h->cstream[0], &h->gl_step, [&](cudaStream_t cs) { launch_step(h, chunk_const(h, K, 0, 1), cs, false, false); });
-            memcpy(&h->gk_step, &K, sizeof(SimConst));
+            memcpy(&h->gk_step, &h->K, sizeof(SimConst));
+            h->gp_act = K.act;
             if (!h->gx_step) h->use_graph = 0;   // capture unavailable: plain launches from now on
         }
     }
@@ -1651,8 +1708,15 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     cudaStream_t s_front = h->cstream[0], s_h2d = h->cstream[kMaxChunks - 1];
     cudaStreamWaitEvent(s_front, h->cfork, 0);
     cudaStreamWaitEvent(s_h2d, h->cfork, 0);
+    // Front-half waves (from 262,144 envs): the env range is cut at back-chunk boundaries into waves that run collide / setup /
+    // solvers on streams of falling priority, beside each other (the per-env kernels leave most issue slots idle).  The first
+    // wave's rows are post-processed and on their way to the host while the later waves are still in their solver kernels, so
+    // only the copies of the last wave stay exposed.
+    const int waves = (h->host_waves > 1 && nch == h->nchunks_host && !h->fused) ? h->host_waves : 1;
+    const int* const wb = h->wave_bound;
+    auto wave_of = [&](int c) { int w = 0; while (w + 1 < waves && c >= wb[w + 1]) ++w; return w; };
     // the action rows go up in two halves: k_pre of the first half starts while the second is still in flight
-    const size_t half = nch > 1 ? (N / 2 + kBlock - 1) / kBlock * kBlock : 0;
+    const size_t half = nch > 1 ? (waves > 1 ? (size_t)chunk_const(h, K0, wb[1], nch).env0 : (N / 2 + kBlock - 1) / kBlock * kBlock) : 0;
     const size_t row = sizeof(float) * K0.act_dim;
     if (half && cudaMemcpyAsync(h->act_dev, actions_host, row * half, cudaMemcpyHostToDevice, s_h2d) != cudaSuccess)
         return fail(-8, "mrp_step_host: H2D failed: %s", dev_err());
@@ -1667,14 +1731,27 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
         if (done_host) cudaMemcpyAsync(done_host + b, K0.done + b, n, cudaMemcpyDeviceToHost, st);
         if (trunc_host) cudaMemcpyAsync(trunc_host + b, K0.trunc + b, n, cudaMemcpyDeviceToHost, st);
     };
+    unsigned zc_chunks = 0;   // back chunks on the early-copy path: their reward / done / truncation values leave at the end
     if (nch == 1 || h->fused) {
         cudaStreamWaitEvent(s_front, h->cact, 0);
         launch_pipeline(h, chunk_const(h, K0, 0, 1), s_front, h->timing != 0);
         copy_out(s_front, 0, N);
     } else {
-        launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half, trace ? tr : nullptr);
-        cudaEventRecord(h->cjoin[0], s_front);
-        if (trace) cudaEventRecord(tr[2], s_front);
+        if (waves > 1) {
+            for (int w = 0; w < waves; ++w) {
+                cudaStream_t sw = h->cstream[wb[w]];
+                if (w) cudaStreamWaitEvent(sw, h->cfork, 0);
+                launch_front(h, wave_const(h, K0, w, wb[w], wb[w + 1], nch), sw, false, w ? h->cact : h->cact0, nullptr, 0, (trace && !w) ? tr : nullptr,
+                             h->cstream[wb[w] + 1], h->wpre[w], h->wbig[w]);
+                cudaEventRecord(h->wjoin[w], sw);
+                if (trace && !w) cudaEventRecord(tr[2], sw);
+                if (trace && w == waves - 1) { cudaEventRecord(tr[21], sw); }
+            }
+        } else {
+            launch_front(h, chunk_const(h, K0, 0, 1), s_front, false, h->cact, h->cact0, (int64_t)half, trace ? tr : nullptr);
+            cudaEventRecord(h->cjoin[0], s_front);
+            if (trace) cudaEventRecord(tr[2], s_front);
+        }
         // pinned obs buffer the device can address: early bulk copy + zero-copy fix-up of the rewritten rows
         float* obs_zc = nullptr;
         if (obs_host && h->host_early_copy) {
@@ -1693,8 +1770,11 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
             const SimConst K = back_chunk_const(h, K0, c, nch);
             if (K.nloc == 0) continue;
             cudaStream_t st = h->cstream[c];
+            // front of this chunk's envs: the whole batch, or its wave
+            cudaEvent_t front_done = waves > 1 ? h->wjoin[wave_of(c)] : h->cjoin[0];
             if (obs_zc) {
-                cudaStreamWaitEvent(st, c > 0 ? h->cpost[c - 1] : h->cjoin[0], 0);
+                cudaStreamWaitEvent(st, front_done, 0);
+                if (c > 0) cudaStreamWaitEvent(st, h->cpost[c - 1], 0);
                 launch_back(h, K, st, false, true, h->cpost[c]);
                 if (trace) cudaEventRecord(tr[3 + 2 * c], st);
                 const size_t b = (size_t)K.env0, n = (size_t)K.nloc;
@@ -1707,22 +1787,34 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
                     else k_out_rows<float><<<16, 256, 0, st>>>(K, which, obs_zc);
                     h->launches += 1;
                 }
-                if (reward_host) cudaMemcpyAsync(reward_host + b, K0.rew + b, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
-                if (done_host) cudaMemcpyAsync(done_host + b, K0.done + b, n, cudaMemcpyDeviceToHost, st);
-                if (trunc_host) cudaMemcpyAsync(trunc_host + b, K0.trunc + b, n, cudaMemcpyDeviceToHost, st);
                 if (trace) cudaEventRecord(tr[4 + 2 * c], st);
+                cudaEventRecord(h->cdone[c], st);
+                zc_chunks |= 1u << c;
                 continue;
             }
             // k_post of chunk c starts when k_post of chunk c-1 has finished: at that moment the (higher-priority, large
             // shared memory) TOI-event and reset kernels of chunk c-1 get the draining SMs first, and chunk c's k_post
             // fills the rest.  Launched all at once, the k_post CTAs of later chunks would keep re-occupying the SMs and
             // starve those kernels until every k_post had drained (measured: all chunks finished together).
-            cudaStreamWaitEvent(st, c > 0 ? h->cpost[c - 1] : h->cjoin[0], 0);
+            cudaStreamWaitEvent(st, front_done, 0);
+            if (c > 0) cudaStreamWaitEvent(st, h->cpost[c - 1], 0);
             launch_back(h, K, st, false, true, h->cpost[c]);
             if (trace) cudaEventRecord(tr[3 + 2 * c], st);
             copy_out(st, (size_t)K.env0, (size_t)K.nloc);
             if (trace) cudaEventRecord(tr[4 + 2 * c], st);
         }
+    }
+    if (zc_chunks) {
+        // reward / done / truncation of the whole batch leave last, as three copies behind every chunk's passes.  Issued per chunk,
+        // between the bulk copies, they held those up: the copy engine takes its work in host issue order, so a small copy waiting
+        // for chunk c's event / reset tail (~0.4 ms) kept the rows of chunk c + 1 from starting (measured: every bulk copy ended
+        // within 0.2 ms of the last one, 0.5 ms late)
+        cudaStream_t st = h->copy_stream;
+        for (int c = 0; c < nch; ++c) if ((zc_chunks >> c) & 1u) cudaStreamWaitEvent(st, h->cdone[c], 0);
+        if (reward_host) cudaMemcpyAsync(reward_host, K0.rew, sizeof(float) * N, cudaMemcpyDeviceToHost, st);
+        if (done_host) cudaMemcpyAsync(done_host, K0.done, N, cudaMemcpyDeviceToHost, st);
+        if (trunc_host) cudaMemcpyAsync(trunc_host, K0.trunc, N, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail(-9, "mrp_step_host: %s", dev_err());
     }
     int rc = check_launch("mrp_step_host");
     for (int c = 0; c < nch; ++c)

@@ -1,0 +1,7 @@
+# round-2 evidence: GPU suite, smoke, bench lines of every config, reference arm, ncu launch list + full capture
+python -m pytest tests -m gpu -q 2>&1 | tail -2 > gpurun_out/r2b_gputest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 >> gpurun_out/r2b_gputest.log
+python bench.py > gpurun_out/r2b_bench_default.json 2> gpurun_out/r2b_bench_default.err
+python bench.py --impl reference > gpurun_out/r2b_bench_reference.json 2> gpurun_out/r2b_bench_reference.err
+bash profiles/run_configs_1gpu.sh r2b > gpurun_out/r2b_configs.log 2>&1
+BENCH_LIST=1 bash profiles/capture.sh r2b > gpurun_out/r2b_capture.log 2>&1

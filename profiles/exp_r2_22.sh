@@ -1,0 +1,6 @@
+# two front-half waves in mrp_step_host: parity, then end-to-end A/B and the timeline
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+for W in 1 2; do echo "== MRP_HOST_WAVES=$W"; MRP_HOST_WAVES=$W QB_E2E=1 python profiles/quickbench.py; done
+MRP_HOST_WAVES=2 MRP_TRACE=1 QB_E2E=1 python profiles/quickbench.py 2>&1 | grep "h2d_done" | tail -2
+for W in 1 2; do echo "== MRP_HOST_WAVES=$W 524288"; MRP_HOST_WAVES=$W QB_ENVS=524288 QB_E2E=1 python profiles/quickbench.py; done
+for W in 1 2; do echo "== MRP_HOST_WAVES=$W v0"; MRP_HOST_WAVES=$W QB_E2E=1 python profiles/quickbench.py MultiRobotPuzzle-v0 MultiRobotPuzzle-v2; done

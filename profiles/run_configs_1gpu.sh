@@ -1,7 +1,7 @@
 #!/bin/bash
 # bench.py over the BASELINE.json configs on one GPU (run under gpurun); one JSON line per config into gpurun_out/
 TAG=${1:-r2}
-for c in c3 c3-resets c2 c4 c4-heavy; do
+for c in c3 c3-resets c2 c4 c4-heavy c5; do
   python bench.py --config $c --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_${c}.json 2> gpurun_out/${TAG}_bench_${c}.err || echo "config $c failed"
   python - <<PY
 import json

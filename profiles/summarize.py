@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an ncu report (read here, no GPU needed):  python profiles/summarize.py gpurun_out/prof_X.ncu-rep [out.md] [traffic.json envs]"""
+"""Summarise an ncu report (read here, no GPU needed):
+  python profiles/summarize.py gpurun_out/prof_X.ncu-rep [out.md] [kernel_traffic.json] [envs] [kernel_issue.json]
+The two JSON files are what bench.py reads for roofline.traffic and the lane-issue roofline."""
 import csv
 import io
 import json
@@ -55,6 +57,25 @@ def main():
         print(text)
     if len(sys.argv) > 3:
         json.dump(traffic, open(sys.argv[3], "w"), indent=1)
+    if len(sys.argv) > 5:
+        col = lambda m: head.index(m)  # noqa: E731
+        num = lambda r, m: float(r[col(m)].replace(",", ""))  # noqa: E731
+        st = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio"
+        issue = {}
+        for r, n in zip(data, names):
+            issue[n.split("::")[-1]] = {
+                "issue_slot_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fma_pipe_pct": num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "alu_pipe_pct": num(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                "active_lanes_per_inst": num(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "dram_pct_of_peak": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "stall_long_scoreboard_per_issue": num(r, st % "long_scoreboard"),
+                "stall_no_instruction_per_issue": num(r, st % "no_instruction"),
+                "warp_inst_per_launch": num(r, "smsp__inst_executed.sum"),
+                "envs": envs,
+            }
+        json.dump(issue, open(sys.argv[5], "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -81,19 +81,35 @@ def test_chunked_streams_are_invariant(monkeypatch):
     ref = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25)
     monkeypatch.setenv("MRP_CHUNKS", "4")
     monkeypatch.setenv("MRP_CHUNKS_HOST", "8")
+    monkeypatch.setenv("MRP_HOST_WAVES", "1")
     chk = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25)
-    assert np.array_equal(ref.reset_host(), chk.reset_host())
+    # front-half waves + big islands on their own kernel: the large-batch flow of mrp_step_host (pinned buffers: early row copies)
+    monkeypatch.setenv("MRP_BIG", "1")
+    wavs = []
+    for w in ("2", "3", "4"):
+        monkeypatch.setenv("MRP_HOST_WAVES", w)
+        wavs.append(abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25))
+    pin = (torch.empty(N, 40).pin_memory().numpy(), torch.empty(N).pin_memory().numpy(),
+           torch.empty(N, dtype=torch.uint8).pin_memory().numpy(), torch.empty(N, dtype=torch.uint8).pin_memory().numpy())
+    r0 = ref.reset_host()
+    assert np.array_equal(r0, chk.reset_host()) and all(np.array_equal(r0, wav.reset_host()) for wav in wavs)
     rng = np.random.default_rng(2)
     for t in range(60):
         act = rng.uniform(-1, 1, (N, 15)).astype(np.float32)
         if t % 2:   # host-buffer call
-            for x, y in zip(ref.step_host(act), chk.step_host(act)):
+            out_ref = ref.step_host(act)
+            for x, y in zip(out_ref, chk.step_host(act)):
                 assert np.array_equal(x, y)
+            for wav in wavs:
+                for x, y in zip(out_ref, wav.step_host(act, *pin) if t % 4 == 1 else wav.step_host(act)):
+                    assert np.array_equal(x, y)
         else:       # device-resident call on torch's current stream
             a = torch.from_numpy(act).cuda()
             ref.step(a.data_ptr()); chk.step(a.data_ptr())
+            for wav in wavs:
+                wav.step(a.data_ptr())
             torch.cuda.synchronize()
-    assert np.array_equal(ref.get_state(), chk.get_state())
+    assert np.array_equal(ref.get_state(), chk.get_state()) and all(np.array_equal(ref.get_state(), wav.get_state()) for wav in wavs)
     sr, sc = ref.stats(), chk.stats()
     for k in ("episodes", "done_by_env", "truncated", "sum_length", "overflow"):
         assert sr[k] == sc[k]
