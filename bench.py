@@ -202,15 +202,14 @@ def run_native(args):
     env.reset()
     # settle: all envs are reset at t=0, so the first steps resolve spawn overlaps (heavier than steady state);
     # run them untimed (actions sampled on the fly) before the W warm-up steps so the timed region sees the
-    # rollout's stationary mix.  With a TimeLimit cap the episodes are de-phased first: a third of the envs is reset
-    # again at one third and at two thirds of the cap, so that resets are spread over the steps instead of arriving
-    # all at once every `cap` steps.
+    # rollout's stationary mix.  With a TimeLimit cap the episodes are de-phased first: during the first `cap` steps env i is
+    # reset again at step i mod cap, so that from then on N / cap envs reach the limit and respawn in EVERY step (a steady
+    # stream of auto-resets, as in training) instead of all at once every `cap` steps.
     settle = args.settle if not cfg["cap"] else max(args.settle, 2 * cfg["cap"] + 20)
+    phase = torch.arange(N, device=dev) % cfg["cap"] if cfg["cap"] else None
     for t in range(settle + W):
-        if cfg["cap"] and t in (cfg["cap"] // 3, 2 * cfg["cap"] // 3):
-            mask = torch.zeros(N, dtype=torch.uint8, device=dev)
-            mask[(0 if t == cfg["cap"] // 3 else 1)::3] = 1
-            env.reset(mask)
+        if cfg["cap"] and t < cfg["cap"]:
+            env.reset((phase == t).to(torch.uint8))
         env.sample_actions(step_index=t)
         env.step()
     # inputs of the timed region are resident in HBM before it starts: one distinct pre-generated U(-1,1) action

@@ -331,6 +331,28 @@ MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t en
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
 }
 
+// spare episode of env: respawn + hidden step (reset_lane's work) into the spare state / observation buffers.  K2 = K with S = S2,
+// obs = obs2.  The spare continues the env's episode counter as it stands now; nothing else of the running episode enters.
+MRP_HD void refill_lane(const SimConst& K, const SimConst& K2, float* sm, const float* ct, int64_t env) {
+    env_words(K2, env)[W_EPISODE << kTileShift] = env_words(K, env)[W_EPISODE << kTileShift];
+    reset_lane(K2, sm, ct, env);
+    K.spare_ok[env] = 1;
+}
+// auto-reset of a finished env from its spare: every state word and the observation row.  Returns false when there is no valid spare.
+MRP_HD bool reset_from_spare(const SimConst& K, int64_t env) {
+    if (!K.S2 || !K.spare_ok[env]) return false;
+    const uint32_t* src = K.S2 + (env >> kTileShift) * ((int64_t)K.w_total << kTileShift) + (env & (kTile - 1));
+    uint32_t* dst = env_words(K, env);
+    const uint32_t hint = dst[W_HINT << kTileShift];
+    for (int w = 0; w < K.w_total; ++w) dst[w << kTileShift] = src[w << kTileShift];
+    dst[W_HINT << kTileShift] = hint;   // ordering hint of the solver queues: not part of the episode
+    const float* so = K.obs2 + env * K.obs_dim;
+    float* o = K.obs + env * K.obs_dim;
+    for (int i = 0; i < K.obs_dim; ++i) o[i] = so[i];
+    K.spare_ok[env] = 0;
+    return true;
+}
+
 MRP_HD void sample_actions_lane(const SimConst& K, float* dst, uint64_t step_index, int64_t env) {
     uint64_t gid = K.env_id_base + (uint64_t)env;
     for (int k = 0; k < K.act_dim; ++k)
@@ -666,13 +688,48 @@ __global__ void __launch_bounds__(kBlock) k_post_events(const __grid_constant__ 
     TP(tp_end(2 + (free_group ? 1 : 0));)
 }
 
-__global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K) {
+// `lanes` lanes per warp take an env (a power of two), the others idle: a respawned env runs a whole fused step — its own
+// path through collide, the solver sweeps and the TOI loop — so the lanes of a warp execute their streams one after the other,
+// and the queue is short (envs whose episode ended this step)
+__global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ SimConst K, int lanes) {
     extern __shared__ float smem[];
     const int count = K.cnt[CNT_RESET];
-    if ((int64_t)blockIdx.x * kBlock >= count) return;
+    if ((int64_t)blockIdx.x * (kBlock / 32) * lanes >= count) return;
     const float* ct = load_ctab(K, smem);
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += (int64_t)gridDim.x * kBlock)
-        reset_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, K.reset_list[i]);
+    const int lane = threadIdx.x & 31, step = 32 / lanes;
+    if (lane % step) return;
+    const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5, stride = (int64_t)gridDim.x * (kBlock / 32) * lanes;
+    for (int64_t i = warp * lanes + lane / step; i < count; i += stride) {
+        const int64_t env = K.reset_list[i];
+        if (!reset_from_spare(K, env)) reset_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, env);
+    }
+}
+
+// spare episodes: list the envs whose spare is missing (one warp-aggregated atomic per warp) ...
+__global__ void k_refill_collect(const __grid_constant__ SimConst K) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool need = env < K.N && !K.spare_ok[env];
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(K.refill_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) K.refill_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)env;
+}
+// ... and compute them: reset_lane's work into the spare buffers, `lanes` lanes per warp as in k_reset_list.  Runs on a
+// low-priority stream beside the step's kernels; its serial tail (a whole fused step of a freshly spawned, often overlapping
+// configuration on one lane: up to ~3.5 ms) is what the auto-reset used to add to the END of every step.
+__global__ void __launch_bounds__(kBlock) k_refill(const __grid_constant__ SimConst K, const __grid_constant__ SimConst K2, int lanes) {
+    extern __shared__ float smem[];
+    const int count = K.refill_cnt[0];
+    if ((int64_t)blockIdx.x * (kBlock / 32) * lanes >= count) return;
+    const float* ct = load_ctab(K, smem);
+    const int lane = threadIdx.x & 31, step = 32 / lanes;
+    if (lane % step) return;
+    const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5, stride = (int64_t)gridDim.x * (kBlock / 32) * lanes;
+    for (int64_t i = warp * lanes + lane / step; i < count; i += stride)
+        refill_lane(K, K2, lane_sm(smem + kCtPad, K.smem_words), ct, K.refill_list[i]);
 }
 
 // mrp_step_host with a pinned, device-visible obs buffer: the rows of a chunk leave by cudaMemcpyAsync as soon as its k_post
@@ -701,6 +758,7 @@ __global__ void __launch_bounds__(kBlock) k_reset_mask(const __grid_constant__ S
     if (env >= K.N) return;
     if (K.reset_mask && !K.reset_mask[env]) return;
     reset_lane(K, lane_sm(smem + kCtPad, K.smem_words), ct, env);
+    if (K.spare_ok) K.spare_ok[env] = 0;   // the spare was the episode this call just started
 }
 
 __global__ void k_sample_actions(const __grid_constant__ SimConst K, float* dst, uint64_t step_index) {
@@ -742,6 +800,8 @@ struct mrp_handle {
     size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post, smem_big;
     int big_split;    // islands with more than two contacts go to k_solve_big on a side stream (MRP_BIG, default: from 32768 envs)
     int solver_ctas;  // persistent solver CTAs per SM
+    int reset_lanes;  // MRP_RESET_LANES: lanes per warp that take an env in the auto-reset / spare-episode passes
+    int use_spares;   // MRP_SPARES (default: from 32,768 envs with auto-reset, capacity-32 build): next episodes computed ahead of time
     int num_sms;      // multiprocessors of the handle's device (148 on B200); persistent / queue grids are sized from it
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
@@ -752,6 +812,8 @@ struct mrp_handle {
     int host_waves;            // MRP_HOST_WAVES: front-half waves of mrp_step_host (default: measured best per batch size)
     int wave_bound[kMaxWaves + 1];   // wave w covers the envs of back chunks [wave_bound[w], wave_bound[w + 1]) (of nchunks_host)
     cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
+    cudaStream_t rstream;      // spare episodes: k_refill_collect / k_refill beside the step's kernels (lowest priority)
+    cudaEvent_t crf0, crf1;
     int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
     cudaEvent_t tr[32];        // MRP_TRACE=1: timeline of one mrp_step_host call (created on first use)
     int tr_init;
@@ -886,6 +948,9 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     if (h->cfork) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); cudaEventDestroy(h->cdone[c]); }
         cudaStreamDestroy(h->copy_stream);
+        cudaStreamDestroy(h->rstream);
+        cudaEventDestroy(h->crf0);
+        cudaEventDestroy(h->crf1);
         if (h->tr_init) for (int i = 0; i < 32; ++i) cudaEventDestroy(h->tr[i]);
         cudaEventDestroy(h->cfork);
         cudaEventDestroy(h->cact);
@@ -908,6 +973,11 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.trunc);
     DEV_FREE(h->K.stats);
     DEV_FREE(h->K.reset_list);
+    DEV_FREE(h->K.S2);
+    DEV_FREE(h->K.obs2);
+    DEV_FREE(h->K.spare_ok);
+    DEV_FREE(h->K.refill_list);
+    DEV_FREE(h->K.refill_cnt);
     DEV_FREE(h->K.cnt);
     DEV_FREE(h->K.pool);
     DEV_FREE(h->K.task_env);
@@ -961,6 +1031,8 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     if (cfg->max_episode_steps > 0) { K.max_steps = cfg->max_episode_steps; h->L.max_episode_steps = cfg->max_episode_steps; }
     K.auto_reset = cfg->auto_reset ? 1 : 0;
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
+    h->reset_lanes = getenv("MRP_RESET_LANES") ? atoi(getenv("MRP_RESET_LANES")) : 32;
+    if (h->reset_lanes < 1 || h->reset_lanes > 32 || (h->reset_lanes & (h->reset_lanes - 1))) h->reset_lanes = 32;
     h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
     if (h->solver_ctas < 1) h->solver_ctas = 1;
     // small batches are one chunk unless the environment variables say otherwise (tests exercise chunking that way)
@@ -1028,6 +1100,31 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
         }
         free(row);
     }
+    // spare episodes (see SimConst::S2).  Not in the wide build: its fused paths borrow the env's slice of the task pool as
+    // scratch, which the solver kernels of the running step are using.
+#ifdef MRP_WIDE
+    h->use_spares = 0;
+#else
+    h->use_spares = getenv("MRP_SPARES") ? atoi(getenv("MRP_SPARES")) : 0;
+#endif
+    if (h->use_spares && K.auto_reset) {
+        const size_t sbytes = sizeof(uint32_t) * ntiles * kTile * K.w_total;
+        int rs = DEV_ALLOC_RAW(K.S2, sbytes);
+        rs |= DEV_ALLOC(K.obs2, sizeof(float) * N * K.obs_dim);
+        rs |= DEV_ALLOC(K.spare_ok, N);
+        rs |= DEV_ALLOC(K.refill_list, sizeof(int32_t) * N);
+        rs |= DEV_ALLOC(K.refill_cnt, sizeof(int32_t) * 4);
+        if (rs) {
+            fail(-7, "mrp_create: device allocation failed (spare episodes): %s", dev_err());
+            MRP_API(mrp_destroy)(h);
+            return -7;
+        }
+#ifndef MRP_HOST_EMU
+        cudaMemcpy(K.S2, K.S, sbytes, cudaMemcpyDeviceToDevice);   // the constant header words (v0 goal)
+#else
+        memcpy(K.S2, K.S, sbytes);
+#endif
+    }
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
     h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(11 * K.nb + 4 * K.ndynfix) * kBlock);
@@ -1042,8 +1139,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaFuncSetAttribute(k_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_broad);
     cudaFuncSetAttribute(k_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_pre);
     cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
-    for (auto fn : {k_step, k_reset_list})
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_reset_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_post_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     // experiment knobs: shared-memory carve-out (percent of the SM's 228 KB) of the per-env kernels — what is not carved out
     // is L1, which backs the lanes' local arrays (contact words, island order, actions)
@@ -1072,6 +1170,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
             cudaEventCreateWithFlags(&h->cdone[c], cudaEventDisableTiming);
         }
         cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&h->rstream, cudaStreamNonBlocking, lo);
+        cudaEventCreateWithFlags(&h->crf0, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->crf1, cudaEventDisableTiming);
         h->host_early_copy = getenv("MRP_HOST_EARLY_COPY") ? atoi(getenv("MRP_HOST_EARLY_COPY")) : 1;
     }
     cudaEventCreateWithFlags(&h->cfork, cudaEventDisableTiming);
@@ -1158,7 +1259,7 @@ int MRP_API(mrp_reset)(mrp_handle* h, const uint8_t* mask_dev, void* stream) {
 #else
     (void)stream;
     for (int64_t e = 0; e < K.N; ++e)
-        if (!mask_dev || mask_dev[e]) reset_lane(K, h->emu_sm, h->ctab_dev, e);
+        if (!mask_dev || mask_dev[e]) { reset_lane(K, h->emu_sm, h->ctab_dev, e); if (K.spare_ok) K.spare_ok[e] = 0; }
     return 0;
 #endif
 }
@@ -1259,6 +1360,30 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
 // (k_post, TOI events, auto-reset), which may use a different chunking (mrp_step_host: front over the whole batch,
 // back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
 // events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
+// Spare episodes: at the start of a step, list the envs without a valid spare and compute their next episode on the
+// lowest-priority stream, beside everything else of the step; join_refill orders a stream behind it (before auto-resets).
+static void launch_refill(mrp_handle* h, cudaStream_t after) {
+    if (!h->K.S2) return;
+    SimConst K2 = h->K;
+    K2.S = h->K.S2;
+    K2.obs = h->K.obs2;
+    cudaEventRecord(h->crf0, after);
+    cudaStreamWaitEvent(h->rstream, h->crf0, 0);
+    cudaMemsetAsync(h->K.refill_cnt, 0, sizeof(int32_t), h->rstream);
+    k_refill_collect<<<grid_for(h->K.N, 256), 256, 0, h->rstream>>>(h->K);
+    const unsigned full = grid_for(h->K.N, kBlock), grid = full < (unsigned)h->num_sms * 8u ? full : (unsigned)h->num_sms * 8u;
+    k_refill<<<grid, kBlock, h->smem_bytes, h->rstream>>>(h->K, K2, h->reset_lanes);
+    cudaEventRecord(h->crf1, h->rstream);
+    h->launches += 2;
+}
+static void join_refill(mrp_handle* h, cudaStream_t st) {
+    if (h->K.S2) cudaStreamWaitEvent(st, h->crf1, 0);
+}
+// auto-reset of the envs that finished in this step: a copy from their spare episode where there is one, else the fused respawn
+static void launch_reset_list(mrp_handle* h, const SimConst& K, cudaStream_t st, unsigned pgrid) {
+    join_refill(h, st);
+    k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K, h->reset_lanes);
+}
 static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed, cudaEvent_t actions_ready,
                          cudaEvent_t first_half_ready = nullptr, int64_t half = 0, cudaEvent_t* tr = nullptr, cudaStream_t big_stream = nullptr,
                          cudaEvent_t big_fork = nullptr, cudaEvent_t big_join = nullptr) {
@@ -1325,7 +1450,7 @@ static void launch_back(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     h->launches += 2;
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     if (K.auto_reset) {
-        k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        launch_reset_list(h, K, st, pgrid);
         h->launches += 1;
     }
 }
@@ -1395,7 +1520,7 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
         h->launches += 8;
         if (K.auto_reset) {
-            k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+            launch_reset_list(h, K, st, pgrid);
             h->launches += 1;
         }
         return;
@@ -1416,7 +1541,7 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
     h->launches += 10;
     if (K.auto_reset) {
-        k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        launch_reset_list(h, K, st, pgrid);
         h->launches += 1;
     }
     mark(9, st);
@@ -1446,13 +1571,26 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         }
         k_step<<<grid, kBlock, h->smem_bytes, st>>>(K);
         if (timed) { cudaEventRecord(h->ev1[h->ev_n], st); h->ev_n += 1; }
-        if (K.auto_reset) k_reset_list<<<pgrid, kBlock, h->smem_bytes, st>>>(K);
+        if (K.auto_reset) launch_reset_list(h, K, st, pgrid);
         h->launches += 3;
         return;
     }
     launch_step(h, K, st, timed, false);
 }
 #else
+// spare episodes on the host build: same order of events as the device (refill at the start of a step call, copy at the auto-reset)
+static void refill_emu(mrp_handle* h) {
+    const SimConst& K = h->K;
+    if (!K.S2) return;
+    SimConst K2 = K;
+    K2.S = K.S2;
+    K2.obs = K.obs2;
+    for (int64_t e = 0; e < K.N; ++e)
+        if (!K.spare_ok[e]) refill_lane(K, K2, h->emu_sm, h->ctab_dev, e);
+}
+static void reset_emu(mrp_handle* h, const SimConst& K, int64_t env) {
+    if (!reset_from_spare(K, env)) reset_lane(K, h->emu_sm, h->ctab_dev, env);
+}
 static void emu_narrow(mrp_handle* h, const SimConst& K) {
     const int nnarrow = K.cnt[CNT_NARROW];
     K.stats[MRP_STAT_PAIRS] += nnarrow;
@@ -1535,7 +1673,7 @@ static void run_back_emu(mrp_handle* h, const SimConst& K, bool clear, bool by_l
     }
     if (K.auto_reset) {
         const int nreset = K.cnt[CNT_RESET];
-        for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+        for (int i = 0; i < nreset; ++i) reset_emu(h, K, K.reset_list[i]);
     }
 }
 static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
@@ -1544,7 +1682,7 @@ static void run_pipeline_emu(mrp_handle* h, const SimConst& K) {
         for (int64_t e = K.env0; e < K.env0 + K.nloc; ++e) step_lane(K, h->emu_sm, h->ctab_dev, e);
         if (K.auto_reset) {
             const int nreset = K.cnt[CNT_RESET];
-            for (int i = 0; i < nreset; ++i) reset_lane(K, h->emu_sm, h->ctab_dev, K.reset_list[i]);
+            for (int i = 0; i < nreset; ++i) reset_emu(h, K, K.reset_list[i]);
         }
         return;
     }
@@ -1581,7 +1719,7 @@ static int step_chunks(const mrp_handle* h, int wanted) {
 #ifndef MRP_HOST_EMU
 // a step qualifies for graph replay when all of its launches go to one stream and nothing is recorded between them
 static bool graph_ok(const mrp_handle* h, int nch) {
-    return h->use_graph && nch == 1 && !h->timing && !h->fused && !h->overlap_post && !h->big_split && !getenv("MRP_TRACE");
+    return h->use_graph && nch == 1 && !h->timing && !h->fused && !h->overlap_post && !h->big_split && !h->K.S2 && !getenv("MRP_TRACE");
 }
 // capture `body` (launches on the capture stream) into an executable graph; returns nullptr when capture is not possible
 template <typename F>
@@ -1632,7 +1770,10 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
     if (graph_ok(h, nch) && h->gx_step) {
         h->launches += h->gl_step;
         if (cudaGraphLaunch(h->gx_step, st) != cudaSuccess) return fail(-10, "mrp_step: graph launch failed: %s", dev_err());
-    } else if (nch == 1 && !h->fused) {
+        return check_launch("mrp_step");
+    }
+    launch_refill(h, st);   // spare episodes of the envs that were reset in the previous step, beside this step's kernels
+    if (nch == 1 && !h->fused) {
         launch_step(h, chunk_const(h, K, 0, 1), st, h->timing != 0, true);
     } else if (nch == 1) {
         launch_pipeline(h, chunk_const(h, K, 0, 1), st, h->timing != 0);
@@ -1649,6 +1790,7 @@ int MRP_API(mrp_step)(mrp_handle* h, const float* actions_dev, void* stream) {
     return check_launch("mrp_step");
 #else
     (void)stream;
+    refill_emu(h);
     for (int c = 0; c < nch; ++c) run_pipeline_emu(h, chunk_const(h, K, c, nch));
     return 0;
 #endif
@@ -1708,6 +1850,7 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
     cudaStream_t s_front = h->cstream[0], s_h2d = h->cstream[kMaxChunks - 1];
     cudaStreamWaitEvent(s_front, h->cfork, 0);
     cudaStreamWaitEvent(s_h2d, h->cfork, 0);
+    launch_refill(h, s_front);   // spare episodes, beside this step's kernels
     // Front-half waves (from 262,144 envs): the env range is cut at back-chunk boundaries into waves that run collide / setup /
     // solvers on streams of falling priority, beside each other (the per-env kernels leave most issue slots idle).  The first
     // wave's rows are post-processed and on their way to the host while the later waves are still in their solver kernels, so
@@ -1834,6 +1977,7 @@ int MRP_API(mrp_step_host)(mrp_handle* h, const float* actions_host, float* obs_
 #else
     const size_t N = (size_t)K0.N;
     memcpy(h->act_dev, actions_host, sizeof(float) * N * K0.act_dim);
+    refill_emu(h);
     const int nch = step_chunks(h, h->nchunks_host);
     if (nch == 1 || h->fused) {
         run_pipeline_emu(h, chunk_const(h, K0, 0, 1));
@@ -1961,6 +2105,7 @@ static int push_internal(mrp_handle* h, int64_t begin, int64_t count, const uint
     free(tiles);
     for (int64_t e = 0; e < count; ++e) fix_rot_lane(K, begin + e);
 #endif
+    if (K.spare_ok) DEV_ZERO(K.spare_ok + begin, (size_t)count);   // the episode counters may have changed: spares are recomputed
     return 0;
 }
 
@@ -2109,6 +2254,14 @@ int MRP_API(mrp_set_params)(mrp_handle* h, const mrp_params* p) {
     FWD(mrp_set_params_wide(h->wide, p))
     if (!h || !p) return fail(-1, "mrp_set_params: null argument");
     h->K.rp = *p;
+    // a spare episode's hidden step evaluates "in place" with the epsilon of the time: recompute them with the new parameters
+    if (h->K.spare_ok) {
+#ifndef MRP_HOST_EMU
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+#endif
+        DEV_ZERO(h->K.spare_ok, (size_t)h->K.N);
+    }
     return 0;
 }
 int MRP_API(mrp_get_params)(mrp_handle* h, mrp_params* p) {

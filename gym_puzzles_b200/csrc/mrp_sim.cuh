@@ -177,6 +177,14 @@ struct SimConst {
     double* stats;
     int32_t* reset_list;
     const uint8_t* reset_mask;
+    // spare episodes (large batches): the state and first observation of every env's NEXT episode, computed ahead of time beside
+    // the step's kernels (a respawn depends on seed, env id and episode number only), so that the auto-reset of a finished env is a
+    // copy instead of a whole fused step on one lane at the end of the step
+    uint32_t* S2;          // spare states, same tiled layout as S (NULL: no spares, auto-reset runs reset_lane)
+    float* obs2;           // [N][obs_dim] observation the reset returns
+    uint8_t* spare_ok;     // [N] 1: the spare of this env is valid
+    int32_t* refill_list;  // [N] envs whose spare has to be (re)computed, [refill_cnt[0]] entries
+    int32_t* refill_cnt;
     // phase pipeline (DESIGN.md "kernels"): solver tasks produced by k_pre, consumed by k_solve_vel / k_solve_pos
     float* pool;          // constraint records, VC_WORDS floats each, allocated per task with one atomic
     int32_t* cnt;         // [CNT_*] counters, zeroed at the start of every step

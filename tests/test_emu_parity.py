@@ -164,3 +164,33 @@ def test_rollout_bit_exact_through_mrp_step(variant):
     _exact(rep)
     assert rep["dones"] >= 2 * N
     h.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_spare_episodes_bit_exact(variant, monkeypatch):
+    """Large batches compute every env's NEXT episode ahead of time (a respawn depends on seed, env id and episode number only)
+    and auto-reset by copying it; forced on here for a small batch: results are those of the fused respawn, bit for bit —
+    also across explicit masked resets, parameter changes and state uploads, which invalidate spares."""
+    monkeypatch.setenv("MRP_SPARES", "1")
+    N, T, cap = 80, 150, 30
+    h = abi.Handle(variant, N, seed=13 + variant, max_episode_steps=cap, lib=emu_lib())
+    rep = rollout_compare(h, variant, N, T, seed=13 + variant, max_episode_steps=cap, nthreads=4)
+    _exact(rep)
+    assert rep["dones"] >= 4 * N
+    # lockstep continues through a masked reset, a parameter change and a state round trip
+    o = OracleBatch(variant, N, seed=13 + variant, nthreads=4, max_episode_steps=cap)
+    o.set_state(h.get_state())
+    mask = (np.arange(N) % 3 == 0).astype(np.uint8)
+    assert np.array_equal(o.reset(mask)[mask == 1].astype(np.float32), h.reset_host(mask)[mask == 1])
+    for t in range(70):
+        if t == 20:
+            p = o.get_params(); p[0] *= 2; o.set_params(p); h.set_params(agentDelta=p[0])
+        if t == 40:
+            h.set_state(o.get_state())
+        a = o.sample_actions(1000 + t)
+        oo, hh = o.step(a), h.step_host(a)
+        assert np.array_equal(oo[0].astype(np.float32), hh[0]) and np.array_equal(oo[2], hh[2]) and np.array_equal(oo[3], hh[3])
+    from parity_util import compare_states
+    ib, tb, bb, _ = compare_states(o.layout, o.get_state(), h.get_state())
+    assert ib == 0 and bb == 0
+    h.close()

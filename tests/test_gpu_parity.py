@@ -248,3 +248,18 @@ def test_graph_replay_is_invariant(monkeypatch):
                 assert np.array_equal(u, v)
         assert np.array_equal(st_ref, st)
         assert n == n_ref   # replays count the launches they contain
+
+
+@pytest.mark.parametrize("device_path", [False, True])
+@pytest.mark.parametrize("env_id", ["MultiRobotPuzzleHeavy-v0", "MultiRobotPuzzle-v2"])
+def test_spare_episodes_gpu(env_id, device_path, monkeypatch):
+    """Spare episodes (next episodes computed beside the step's kernels on a low-priority stream, auto-reset = copy): the
+    default from 32,768 envs, forced on here; TimeLimit 20 keeps a steady stream of resets going."""
+    monkeypatch.setenv("MRP_SPARES", "1")
+    monkeypatch.setenv("MRP_OVERLAP_POST", "1")
+    N, T = 4096, 90
+    h = abi.Handle(env_id, N, seed=29, max_episode_steps=20)
+    rep = rollout_compare(h, env_id, N, T, seed=29, max_episode_steps=20, device_path=device_path, nthreads=16)
+    _assert_parity(rep)
+    assert rep["dones"] >= 4 * N
+    h.close()
