@@ -110,6 +110,13 @@ MRP_HD void finish_step(const SimConst& K, Env& e, int64_t env, bool d, double r
     }
 }
 
+// env of slot `loc` of a per-env kernel: the chunk's range, or the refill pass's list (returns -1 past the end)
+MRP_HD int64_t slot_env(const SimConst& K, int64_t loc) {
+    if (!K.idx_list) return loc < K.nloc ? K.env0 + loc : -1;
+    const int64_t n = *K.idx_count < K.nloc ? *K.idx_count : K.nloc;
+    return loc < n ? (int64_t)K.idx_list[loc] : -1;
+}
+
 // phase 0 (lane per env): broadphase half of Collide — classify every contact, queue the ones that need SAT
 // returns the contacts of this env that need SAT + clipping
 MRP_HD CMask broad_lane(const SimConst& K, float* sm, const float* ct, int64_t env) {
@@ -132,7 +139,13 @@ MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
 MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, uint32_t* m12, const float* staged = nullptr, unsigned vmask = 0u) {
     Env e(K, sm, ct, env, nullptr, 13);
     float a[3 * MRP_MAX_AGENTS];
-    if (staged) {
+    if (K.hidden) {
+        // the hidden step of reset(): action_space.sample() from the reset stream of the episode that just spawned (mrp00:411)
+        const uint32_t episode = e.g(W_EPISODE);
+        for (int i = 0; i < K.act_dim; ++i)
+            a[i] = (float)(-1.0 + 2.0 * uniform53(K.seed, kStreamResetAction, e.gid, episode, (uint32_t)i));
+        e.load();
+    } else if (staged) {
         for (int i = 0; i < K.act_dim; ++i) a[i] = staged[i];
         e.load(false);
     } else {
@@ -298,6 +311,11 @@ MRP_HD void post_lane(const SimConst& K, float* sm, const float* ct, int64_t env
         else K.toi_list[atomic_add_i32(&K.cnt[CNT_TOI], 1)] = (int32_t)env;
         return;
     }
+    if (K.hidden) {   // reset_env: the hidden step's reward and done flag are dropped, the state is the episode's first
+        if (!e.stored) e.store();
+        K.spare_ok[env] = 1;
+        return;
+    }
     finish_step(K, e, env, d, r);
 }
 
@@ -331,12 +349,24 @@ MRP_HD void reset_lane(const SimConst& K, float* sm, const float* ct, int64_t en
     if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
 }
 
-// spare episode of env: respawn + hidden step (reset_lane's work) into the spare state / observation buffers.  K2 = K with S = S2,
-// obs = obs2.  The spare continues the env's episode counter as it stands now; nothing else of the running episode enters.
-MRP_HD void refill_lane(const SimConst& K, const SimConst& K2, float* sm, const float* ct, int64_t env) {
-    env_words(K2, env)[W_EPISODE << kTileShift] = env_words(K, env)[W_EPISODE << kTileShift];
-    reset_lane(K2, sm, ct, env);
-    K.spare_ok[env] = 1;
+// first half of reset_env for the refill pass: episode counters, spawn, contacts of the fresh fixtures; the hidden step follows
+// as an ordinary pipeline pass over the same list (K2: S = S2, hidden)
+MRP_HD void spawn_spare_lane(const SimConst& K, const SimConst& K2, float* sm, const float* ct, int64_t env) {
+    Env e(K2, sm, ct, env, nullptr);
+    const uint32_t episode = env_words(K, env)[W_EPISODE << kTileShift] + 1u;
+    e.g(W_EPISODE) = episode;
+    e.g(W_ELAPSED) = 0;
+    e.g(W_EPLEN) = 0;
+    e.gsd(W_EPRET, 0.0);
+    e.spawn(episode);
+    e.find_new_contacts(0xffffffffu);
+    e.store();
+    // the body origins as spawned, for the collide half of the hidden step (Sim::load(), narrow_item)
+    for (int b = 0; b < K.nb; ++b) {
+        e.gsf(K.w_body + kBodyWords * b + 8, e.BX(b, 8));
+        e.gsf(K.w_body + kBodyWords * b + 9, e.BX(b, 9));
+    }
+    if (e.overflow) stat_add(K.stats, MRP_STAT_OVERFLOW, 1.0);
 }
 // auto-reset of a finished env from its spare: every state word and the observation row.  Returns false when there is no valid spare.
 MRP_HD bool reset_from_spare(const SimConst& K, int64_t env) {
@@ -459,8 +489,8 @@ __global__ void __launch_bounds__(kBlock) k_broad(const __grid_constant__ SimCon
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = loc < K.nloc;   // every lane of the warp stays for the warp-aggregated queue reservation
-    const int64_t env = K.env0 + loc;
+    const int64_t env = slot_env(K, loc);
+    const bool valid = env >= 0;   // every lane of the warp stays for the warp-aggregated queue reservation
     CMask need = cm_none();
     if (valid) need = broad_lane(K, lane_sm(smem + kCtPad, 10 * K.nb + 4 * K.ndynfix), ct, env);
     // one atomicAdd per warp instead of one per queued contact (they were 14 % of this kernel's stall samples)
@@ -495,13 +525,13 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
     extern __shared__ float smem[];
     const float* ct = load_ctab(K, smem);
     const int64_t loc = loc0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = loc < loc1;   // every lane of the warp stays for the warp-aggregated list reservation
-    const int64_t env = K.env0 + loc;
+    const int64_t env = loc < loc1 ? slot_env(K, loc) : -1;
+    const bool valid = env >= 0;   // every lane of the warp stays for the warp-aggregated list reservation
     int T = -1;
     uint32_t m12[2] = {0u, 0u};
     float* const lsm = lane_sm(smem + kCtPad, 13 * K.nb + 24);
     const float* staged = nullptr;
-    if (K.stage_rows) {
+    if (K.stage_rows && !K.hidden) {
         // the 32 action rows of the warp's envs are one contiguous run of 32 x act_dim floats: consecutive lanes fetch
         // consecutive words (coalesced) into the warp's wall slots (24 words per lane, set only after the rows have been read),
         // then every lane picks up its own row
@@ -662,12 +692,13 @@ __global__ void __launch_bounds__(kBlock) k_solve_pos(const __grid_constant__ Si
 __global__ void __launch_bounds__(kBlock, 4) k_post(const __grid_constant__ SimConst K, int which) {
     extern __shared__ float smem[];
     const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const int64_t count = which == 2 ? (int64_t)K.nloc : (int64_t)K.cnt[which == 0 ? CNT_FREE : CNT_BUSY];
+    int64_t count = which == 2 ? (int64_t)K.nloc : (int64_t)K.cnt[which == 0 ? CNT_FREE : CNT_BUSY];
+    if (which == 2 && K.idx_list && *K.idx_count < count) count = *K.idx_count;
     if ((int64_t)blockIdx.x * kBlock >= count) return;
     const float* ct = load_ctab(K, smem);
     const unsigned entry = K.stage_rows ? __ballot_sync(0xffffffffu, loc < count) : 0u;   // lanes of this warp that own an env
     if (loc >= count) return;
-    const int64_t env = which == 2 ? K.env0 + loc : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
+    const int64_t env = which == 2 ? slot_env(K, loc) : (int64_t)K.post_list[which == 0 ? loc : K.nloc - 1 - loc];
     post_lane(K, lane_sm(smem + kCtPad, 11 * K.nb + 4 * K.ndynfix), ct, env, false, nullptr, which == 0, entry);
 }
 
@@ -707,29 +738,39 @@ __global__ void __launch_bounds__(kBlock) k_reset_list(const __grid_constant__ S
 
 // spare episodes: list the envs whose spare is missing (one warp-aggregated atomic per warp) ...
 __global__ void k_refill_collect(const __grid_constant__ SimConst K) {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool need = env < K.N && !K.spare_ok[env];
-    const unsigned m = __ballot_sync(0xffffffffu, need);
-    if (!m) return;
+    // 16 flags per thread (one 16-byte load; nearly all are 1 in steady state)
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    uint32_t miss = 0;
+    if (first < K.N) {
+        const uint4 f = *reinterpret_cast<const uint4*>(K.spare_ok + first);
+        const uint32_t w[4] = {f.x, f.y, f.z, f.w};
+        for (int i = 0; i < 16; ++i)
+            if (first + i < K.N && !((w[i >> 2] >> (8 * (i & 3))) & 0xffu)) miss |= 1u << i;
+    }
+    const int n = __popc(miss);
+    if (!__ballot_sync(0xffffffffu, n > 0)) return;
     const int lane = threadIdx.x & 31;
+    int incl = n;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
     int base = 0;
-    if (lane == 0) base = atomicAdd(K.refill_cnt, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (need) K.refill_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)env;
+    if (lane == 31) base = atomicAdd(K.refill_cnt, incl);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    for (; miss; miss &= miss - 1u, ++base)
+        if (base < K.refill_cap) K.refill_list[base] = (int32_t)(first + __ffs((int)miss) - 1);   // the rest gets its spare in a later step
 }
-// ... and compute them: reset_lane's work into the spare buffers, `lanes` lanes per warp as in k_reset_list.  Runs on a
-// low-priority stream beside the step's kernels; its serial tail (a whole fused step of a freshly spawned, often overlapping
-// configuration on one lane: up to ~3.5 ms) is what the auto-reset used to add to the END of every step.
-__global__ void __launch_bounds__(kBlock) k_refill(const __grid_constant__ SimConst K, const __grid_constant__ SimConst K2, int lanes) {
+// ... and start their next episode in the spare buffers (spawn_spare_lane); the hidden step then runs as a pipeline pass over the
+// same list on the same low-priority stream (launch_refill)
+__global__ void __launch_bounds__(kBlock) k_spawn_list(const __grid_constant__ SimConst K, const __grid_constant__ SimConst K2) {
     extern __shared__ float smem[];
-    const int count = K.refill_cnt[0];
-    if ((int64_t)blockIdx.x * (kBlock / 32) * lanes >= count) return;
+    const int64_t loc = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t n = *K2.idx_count < K2.nloc ? *K2.idx_count : K2.nloc;
+    if ((int64_t)blockIdx.x * kBlock >= n) return;
     const float* ct = load_ctab(K, smem);
-    const int lane = threadIdx.x & 31, step = 32 / lanes;
-    if (lane % step) return;
-    const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5, stride = (int64_t)gridDim.x * (kBlock / 32) * lanes;
-    for (int64_t i = warp * lanes + lane / step; i < count; i += stride)
-        refill_lane(K, K2, lane_sm(smem + kCtPad, K.smem_words), ct, K.refill_list[i]);
+    if (loc >= n) return;
+    spawn_spare_lane(K, K2, lane_sm(smem + kCtPad, K.smem_words), ct, K2.idx_list[loc]);
 }
 
 // mrp_step_host with a pinned, device-visible obs buffer: the rows of a chunk leave by cudaMemcpyAsync as soon as its k_post
@@ -801,6 +842,11 @@ struct mrp_handle {
     int big_split;    // islands with more than two contacts go to k_solve_big on a side stream (MRP_BIG, default: from 32768 envs)
     int solver_ctas;  // persistent solver CTAs per SM
     int reset_lanes;  // MRP_RESET_LANES: lanes per warp that take an env in the auto-reset / spare-episode passes
+    // queues / pool / counters of the refill pass (a second, smaller set: at most refill_cap envs per step)
+    int32_t *r_cnt, *r_task_env, *r_task_T, *r_task_off, *r_toi, *r_post;
+    uint32_t* r_narrow;
+    float* r_pool;
+    double* r_stats;
     int use_spares;   // MRP_SPARES (default: from 32,768 envs with auto-reset, capacity-32 build): next episodes computed ahead of time
     int num_sms;      // multiprocessors of the handle's device (148 on B200); persistent / queue grids are sized from it
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
@@ -812,7 +858,9 @@ struct mrp_handle {
     int host_waves;            // MRP_HOST_WAVES: front-half waves of mrp_step_host (default: measured best per batch size)
     int wave_bound[kMaxWaves + 1];   // wave w covers the envs of back chunks [wave_bound[w], wave_bound[w + 1]) (of nchunks_host)
     cudaStream_t copy_stream;  // mrp_step_host: bulk obs copies of the chunks (early-copy path)
-    cudaStream_t rstream;      // spare episodes: k_refill_collect / k_refill beside the step's kernels (lowest priority)
+    cudaStream_t rstream;      // spare episodes: the refill pass beside the step's kernels (highest priority, small grids)
+    int refill_pending;        // a refill pass is in flight on rstream (joined before the auto-resets of the step)
+    int32_t* refill_seen;      // pinned: length of the refill list of an earlier step (sizes the pass's grids without a sync)
     cudaEvent_t crf0, crf1;
     int host_early_copy;       // MRP_HOST_EARLY_COPY (default 1): copy a chunk's rows before its event / reset passes
     cudaEvent_t tr[32];        // MRP_TRACE=1: timeline of one mrp_step_host call (created on first use)
@@ -949,6 +997,7 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
         for (int c = 0; c < kMaxChunks; ++c) { cudaStreamDestroy(h->cstream[c]); cudaEventDestroy(h->cjoin[c]); cudaEventDestroy(h->cpost[c]); cudaEventDestroy(h->cd2h[c]); cudaEventDestroy(h->cdone[c]); }
         cudaStreamDestroy(h->copy_stream);
         cudaStreamDestroy(h->rstream);
+        if (h->refill_seen) cudaFreeHost(h->refill_seen);
         cudaEventDestroy(h->crf0);
         cudaEventDestroy(h->crf1);
         if (h->tr_init) for (int i = 0; i < 32; ++i) cudaEventDestroy(h->tr[i]);
@@ -978,6 +1027,8 @@ int MRP_API(mrp_destroy)(mrp_handle* h) {
     DEV_FREE(h->K.spare_ok);
     DEV_FREE(h->K.refill_list);
     DEV_FREE(h->K.refill_cnt);
+    DEV_FREE(h->r_cnt); DEV_FREE(h->r_task_env); DEV_FREE(h->r_task_T); DEV_FREE(h->r_task_off); DEV_FREE(h->r_toi); DEV_FREE(h->r_post);
+    DEV_FREE(h->r_narrow); DEV_FREE(h->r_pool); DEV_FREE(h->r_stats);
     DEV_FREE(h->K.cnt);
     DEV_FREE(h->K.pool);
     DEV_FREE(h->K.task_env);
@@ -1105,15 +1156,31 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
 #ifdef MRP_WIDE
     h->use_spares = 0;
 #else
-    h->use_spares = getenv("MRP_SPARES") ? atoi(getenv("MRP_SPARES")) : 0;
+    h->use_spares = getenv("MRP_SPARES") ? atoi(getenv("MRP_SPARES")) : (cfg->num_envs >= 32768 ? 1 : 0);
 #endif
     if (h->use_spares && K.auto_reset) {
         const size_t sbytes = sizeof(uint32_t) * ntiles * kTile * K.w_total;
         int rs = DEV_ALLOC_RAW(K.S2, sbytes);
         rs |= DEV_ALLOC(K.obs2, sizeof(float) * N * K.obs_dim);
-        rs |= DEV_ALLOC(K.spare_ok, N);
-        rs |= DEV_ALLOC(K.refill_list, sizeof(int32_t) * N);
+        rs |= DEV_ALLOC(K.spare_ok, (N + 15) / 16 * 16);
+        // at most an eighth of the batch (4,096 at least) gets its spare per step: after a reset of everything the spares arrive
+        // over eight steps, and an env that finishes before its spare exists takes the fused respawn
+        size_t cap = ((N / 8 + kBlock - 1) / kBlock) * kBlock;
+        if (cap < 4096) cap = 4096;
+        if (cap > N) cap = N;
+        if (getenv("MRP_REFILL_CAP") && atoi(getenv("MRP_REFILL_CAP")) > 0) cap = (size_t)atoi(getenv("MRP_REFILL_CAP")) < N ? (size_t)atoi(getenv("MRP_REFILL_CAP")) : N;
+        K.refill_cap = (int32_t)cap;
+        rs |= DEV_ALLOC(K.refill_list, sizeof(int32_t) * cap);
         rs |= DEV_ALLOC(K.refill_cnt, sizeof(int32_t) * 4);
+        rs |= DEV_ALLOC(h->r_cnt, sizeof(int32_t) * 32);
+        rs |= DEV_ALLOC_RAW(h->r_pool, sizeof(float) * cap * K.maxc * VC_WORDS);
+        rs |= DEV_ALLOC(h->r_task_env, sizeof(int32_t) * kTaskClasses * cap * K.nb);
+        rs |= DEV_ALLOC(h->r_task_T, sizeof(int32_t) * kTaskClasses * cap * K.nb);
+        rs |= DEV_ALLOC(h->r_task_off, sizeof(int32_t) * kTaskClasses * cap * K.nb);
+        rs |= DEV_ALLOC(h->r_toi, sizeof(int32_t) * cap);
+        rs |= DEV_ALLOC(h->r_post, sizeof(int32_t) * cap);
+        rs |= DEV_ALLOC_RAW(h->r_narrow, sizeof(uint32_t) * cap * K.maxc);
+        rs |= DEV_ALLOC(h->r_stats, sizeof(double) * MRP_N_STATS);
         if (rs) {
             fail(-7, "mrp_create: device allocation failed (spare episodes): %s", dev_err());
             MRP_API(mrp_destroy)(h);
@@ -1141,7 +1208,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post);
     cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_reset_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-    cudaFuncSetAttribute(k_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    cudaFuncSetAttribute(k_spawn_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     cudaFuncSetAttribute(k_post_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     // experiment knobs: shared-memory carve-out (percent of the SM's 228 KB) of the per-env kernels — what is not carved out
     // is L1, which backs the lanes' local arrays (contact words, island order, actions)
@@ -1170,7 +1237,12 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
             cudaEventCreateWithFlags(&h->cdone[c], cudaEventDisableTiming);
         }
         cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi);
-        cudaStreamCreateWithPriority(&h->rstream, cudaStreamNonBlocking, lo);
+        // highest priority: the pass is a chain of a dozen small dependent kernels; at the priority of the step's own (large) grids
+        // each of them was dispatched only when one of those had drained, so the chain ended with the step and the auto-reset
+        // waited for it (+0.25 ms per step); its grids are sized to the list, so it takes little from the step
+        cudaStreamCreateWithPriority(&h->rstream, cudaStreamNonBlocking, getenv("MRP_REFILL_PRIO") ? atoi(getenv("MRP_REFILL_PRIO")) : hi);
+        if (cudaHostAlloc((void**)&h->refill_seen, sizeof(int32_t) * 2, cudaHostAllocDefault) == cudaSuccess) h->refill_seen[0] = (int32_t)cfg->num_envs;
+        else h->refill_seen = nullptr;
         cudaEventCreateWithFlags(&h->crf0, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->crf1, cudaEventDisableTiming);
         h->host_early_copy = getenv("MRP_HOST_EARLY_COPY") ? atoi(getenv("MRP_HOST_EARLY_COPY")) : 1;
@@ -1355,29 +1427,82 @@ static SimConst chunk_const(const mrp_handle* h, const SimConst& K0, int c, int 
     return K;
 }
 
+// constants of the refill pass: the handle's, re-pointed at the spare buffers and at the pass's own queues
+static SimConst refill_const(const mrp_handle* h) {
+    SimConst K2 = h->K;
+    K2.S = h->K.S2;
+    K2.obs = h->K.obs2;
+    K2.stats = h->r_stats;
+    K2.hidden = 1;
+    K2.auto_reset = 0;
+    K2.big_split = 0;
+    K2.term_obs = nullptr;
+    K2.idx_list = h->K.refill_list;
+    K2.idx_count = h->K.refill_cnt;
+    K2.env0 = 0;
+    K2.nloc = h->K.refill_cap;
+    K2.cnt = h->r_cnt;
+    K2.pool = h->r_pool;
+    K2.task_env = h->r_task_env;
+    K2.task_T = h->r_task_T;
+    K2.task_off = h->r_task_off;
+    K2.toi_list = h->r_toi;
+    K2.post_list = h->r_post;
+    K2.narrow_list = h->r_narrow;
+    return K2;
+}
 #ifndef MRP_HOST_EMU
 // One chunk's phase pipeline on one stream, in two halves: the front (collide, constraint setup, solvers) and the back
 // (k_post, TOI events, auto-reset), which may use a different chunking (mrp_step_host: front over the whole batch,
 // back in chunks so that each chunk's D2H runs under the next chunk's kernels).  `timed` records the phase-boundary
 // events (single-chunk steps only); `actions_ready` is awaited before the first kernel that reads actions (k_pre).
-// Spare episodes: at the start of a step, list the envs without a valid spare and compute their next episode on the
-// lowest-priority stream, beside everything else of the step; join_refill orders a stream behind it (before auto-resets).
+// Spare episodes: at the start of a step, list the envs without a valid spare, spawn their next episode in the spare buffers and
+// run its hidden step as a pipeline pass over that list — all on its own stream, beside everything else of the step;
+// join_refill orders a stream behind it (before auto-resets).
 static void launch_refill(mrp_handle* h, cudaStream_t after) {
     if (!h->K.S2) return;
-    SimConst K2 = h->K;
-    K2.S = h->K.S2;
-    K2.obs = h->K.obs2;
+    const SimConst K2 = refill_const(h);
+    // the list is made on the caller's stream (a few microseconds); only the pass itself forks off
+    cudaMemsetAsync(h->K.refill_cnt, 0, sizeof(int32_t), after);
+    k_refill_collect<<<grid_for((h->K.N + 15) / 16, 256), 256, 0, after>>>(h->K);
+    h->launches += 1;
+    // The pass's grids are sized from the list length an earlier step saw (copied to pinned memory without waiting for it), with a
+    // margin: run with the capacity's grids, the pass's mostly empty CTAs — the persistent solver CTAs above all, which stay for
+    // the ~1 ms tail of the slowest fresh spawn — take shared memory from the step's own kernels.  Envs beyond the grid keep their
+    // flag and are listed again in the next step.
+    const int64_t seen = h->refill_seen ? (int64_t)h->refill_seen[0] : (int64_t)K2.nloc;
+    int64_t est = 2 * seen + 512;
+    if (est > K2.nloc) est = K2.nloc;
+    if (h->refill_seen) cudaMemcpyAsync(h->refill_seen, h->K.refill_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, after);
+    // The pass runs only when enough spares are missing (64, or one per 16,384 envs): a dozen small kernels beside the step cost
+    // 0.2-0.3 ms of a 4.9 ms step however short the list, so a few missing spares are left to accumulate — an env that finishes
+    // without one takes the fused respawn, as all of them did before.
+    const int64_t threshold = getenv("MRP_REFILL_MIN") ? atoi(getenv("MRP_REFILL_MIN")) : (h->K.N / 16384 > 64 ? h->K.N / 16384 : 64);
+    h->refill_pending = seen >= threshold;
+    if (!h->refill_pending) return;
+    cudaStream_t st = h->rstream;
     cudaEventRecord(h->crf0, after);
-    cudaStreamWaitEvent(h->rstream, h->crf0, 0);
-    cudaMemsetAsync(h->K.refill_cnt, 0, sizeof(int32_t), h->rstream);
-    k_refill_collect<<<grid_for(h->K.N, 256), 256, 0, h->rstream>>>(h->K);
-    const unsigned full = grid_for(h->K.N, kBlock), grid = full < (unsigned)h->num_sms * 8u ? full : (unsigned)h->num_sms * 8u;
-    k_refill<<<grid, kBlock, h->smem_bytes, h->rstream>>>(h->K, K2, h->reset_lanes);
-    cudaEventRecord(h->crf1, h->rstream);
-    h->launches += 2;
+    cudaStreamWaitEvent(st, h->crf0, 0);
+    const bool trace = h->tr_init && getenv("MRP_TRACE") != nullptr;
+    if (trace) cudaEventRecord(h->tr[10], st);
+    const unsigned grid = grid_for(est, kBlock), nsm = (unsigned)h->num_sms;
+    const unsigned sgrid = grid < nsm * (unsigned)h->solver_ctas ? grid : nsm * (unsigned)h->solver_ctas;
+    const unsigned pgrid = grid < nsm * 8u ? grid : nsm * 8u;
+    k_clear<<<1, 32, 0, st>>>(K2.cnt);
+    k_spawn_list<<<grid, kBlock, h->smem_bytes, st>>>(h->K, K2);
+    k_broad<<<grid, kBlock, h->smem_broad, st>>>(K2);
+    k_narrow<<<grid < nsm * 16u ? grid : nsm * 16u, kBlock, sizeof(float) * kCtPad, st>>>(K2);
+    k_pre<<<grid, kBlock, h->smem_pre, st>>>(K2, 0, K2.nloc);
+    k_solve_vel<<<sgrid, kBlock, h->smem_vel, st>>>(K2);
+    k_solve_pos<<<sgrid, kBlock, h->smem_pos, st>>>(K2);
+    k_post<<<grid, kBlock, h->smem_post, st>>>(K2, 2);
+    k_post_events<<<pgrid, kBlock, h->smem_bytes, st>>>(K2, 0);
+    if (trace) cudaEventRecord(h->tr[11], st);
+    cudaEventRecord(h->crf1, st);
+    h->launches += 9;
 }
 static void join_refill(mrp_handle* h, cudaStream_t st) {
-    if (h->K.S2) cudaStreamWaitEvent(st, h->crf1, 0);
+    if (h->K.S2 && h->refill_pending) cudaStreamWaitEvent(st, h->crf1, 0);
 }
 // auto-reset of the envs that finished in this step: a copy from their spare episode where there is one, else the fused respawn
 static void launch_reset_list(mrp_handle* h, const SimConst& K, cudaStream_t st, unsigned pgrid) {
@@ -1556,8 +1681,14 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
             if ((i == 4 && !big_on) || cudaEventElapsedTime(&ms, h->tr[0], h->tr[i]) != cudaSuccess) { cudaGetLastError(); continue; }
             printf(" %s %.3f", nm[i], ms);
         }
-        printf(" | envs free %d busy %d, TOI queue %d + %d (free), big islands %d\n", c[CNT_FREE], c[CNT_BUSY], c[CNT_TOI], c[CNT_TOI_F],
-               c[CNT_TASKS + 3] + c[CNT_TASKS_LIGHT + 3]);
+        if (h->refill_pending) {
+            float a = 0.0f, b = 0.0f;
+            if (cudaEventElapsedTime(&a, h->tr[0], h->tr[10]) == cudaSuccess && cudaEventElapsedTime(&b, h->tr[0], h->tr[11]) == cudaSuccess)
+                printf(" refill pass %.3f .. %.3f", a, b);
+            cudaGetLastError();
+        }
+        printf(" | envs free %d busy %d, TOI queue %d + %d (free), big islands %d, resets %d, spares to refill %d\n", c[CNT_FREE], c[CNT_BUSY], c[CNT_TOI],
+               c[CNT_TOI_F], c[CNT_TASKS + 3] + c[CNT_TASKS_LIGHT + 3], c[CNT_RESET], h->refill_seen ? h->refill_seen[0] : -1);
     }
 }static void launch_pipeline(mrp_handle* h, const SimConst& K, cudaStream_t st, bool timed) {
     if (h->fused) {  // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
@@ -1578,15 +1709,37 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
     launch_step(h, K, st, timed, false);
 }
 #else
-// spare episodes on the host build: same order of events as the device (refill at the start of a step call, copy at the auto-reset)
+// spare episodes on the host build: same order of events as the device (refill pass at the start of a step call — spawn, then the
+// hidden step as a pipeline pass over the list — copy at the auto-reset)
+static void emu_narrow(mrp_handle* h, const SimConst& K);
+static void emu_pre(mrp_handle* h, const SimConst& K, int64_t e);
+static void emu_solvers(mrp_handle* h, const SimConst& K);
 static void refill_emu(mrp_handle* h) {
     const SimConst& K = h->K;
     if (!K.S2) return;
-    SimConst K2 = K;
-    K2.S = K.S2;
-    K2.obs = K.obs2;
-    for (int64_t e = 0; e < K.N; ++e)
-        if (!K.spare_ok[e]) refill_lane(K, K2, h->emu_sm, h->ctab_dev, e);
+    int n = 0;
+    for (int64_t e = 0; e < K.N && n < K.refill_cap; ++e)
+        if (!K.spare_ok[e]) K.refill_list[n++] = (int32_t)e;
+    K.refill_cnt[0] = n;
+    const SimConst K2 = refill_const(h);
+    for (int i = 0; i < CNT_N; ++i) K2.cnt[i] = 0;
+    for (int i = 0; i < n; ++i) spawn_spare_lane(K, K2, h->emu_sm, h->ctab_dev, K.refill_list[i]);
+    for (int i = 0; i < n; ++i) {
+        const int64_t e = slot_env(K2, i);
+        const CMask need = broad_lane(K2, h->emu_sm, h->ctab_dev, e);
+        const int c = cm_count(need);
+        if (c) push_narrow(K2, e, need, atomic_add_i32(&K2.cnt[CNT_NARROW], c));
+    }
+    emu_narrow(h, K2);
+    for (int i = 0; i < n; ++i) emu_pre(h, K2, K.refill_list[i]);
+    emu_solvers(h, K2);
+    for (int i = 0; i < n; ++i) post_lane(K2, h->emu_sm, h->ctab_dev, K.refill_list[i], false, nullptr);
+    const int ntoi = K2.cnt[CNT_TOI];
+    for (int i = 0; i < ntoi; ++i) {
+        const int64_t env = K2.toi_list[i];
+        MRP_VC_SCRATCH(K2, env);
+        post_lane(K2, h->emu_sm, h->ctab_dev, env, true, vc_local);
+    }
 }
 static void reset_emu(mrp_handle* h, const SimConst& K, int64_t env) {
     if (!reset_from_spare(K, env)) reset_lane(K, h->emu_sm, h->ctab_dev, env);

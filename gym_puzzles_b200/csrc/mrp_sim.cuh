@@ -183,8 +183,16 @@ struct SimConst {
     uint32_t* S2;          // spare states, same tiled layout as S (NULL: no spares, auto-reset runs reset_lane)
     float* obs2;           // [N][obs_dim] observation the reset returns
     uint8_t* spare_ok;     // [N] 1: the spare of this env is valid
-    int32_t* refill_list;  // [N] envs whose spare has to be (re)computed, [refill_cnt[0]] entries
+    int32_t* refill_list;  // envs whose spare has to be (re)computed, [min(refill_cnt[0], refill_cap)] entries
     int32_t* refill_cnt;
+    int32_t refill_cap;    // spares computed per step at most (the rest waits for the next step)
+    // the refill pass runs the phase pipeline over a LIST of envs (idx_list, *idx_count entries, at most nloc) with S = S2,
+    // obs = obs2 and `hidden` set: the step after a respawn — action drawn from the reset stream, no reward / done / TimeLimit
+    // accounting, the spare marked valid at the end
+    const int32_t* idx_list;
+    const int32_t* idx_count;
+    int32_t hidden;
+    int32_t pad2;
     // phase pipeline (DESIGN.md "kernels"): solver tasks produced by k_pre, consumed by k_solve_vel / k_solve_pos
     float* pool;          // constraint records, VC_WORDS floats each, allocated per task with one atomic
     int32_t* cnt;         // [CNT_*] counters, zeroed at the start of every step
@@ -508,7 +516,12 @@ struct Sim {
             if (!want_vel) { p[3 * MRP_SS] = 0.0f; p[4 * MRP_SS] = 0.0f; p[5 * MRP_SS] = 0.0f; }
             const Rot q{p[6 * MRP_SS], p[7 * MRP_SS]};
             set_rot_cache(b, q, p[2 * MRP_SS]);
-            if (fdyn != 11) {
+            if (K.hidden && (fdyn == 10 || fdyn == 13)) {
+                // first step after a spawn: the body origin is the spawn position itself (b2Body's constructor), kept in the
+                // pre-step pose words by spawn_spare_lane until k_pre overwrites them; c - R(q) * localCenter rounds differently
+                p[8 * MRP_SS] = gf(K.w_body + kBodyWords * b + 8);
+                p[9 * MRP_SS] = gf(K.w_body + kBodyWords * b + 9);
+            } else if (fdyn != 11) {
                 V2 rc = rmul(q, localCenter(b));
                 p[8 * MRP_SS] = p[0] - rc.x;
                 p[9 * MRP_SS] = p[MRP_SS] - rc.y;
@@ -1760,7 +1773,7 @@ MRP_HD void narrow_item(const SimConst& K, const float* ct, uint32_t item) {
             x.q.s = gfl(w + 6); x.q.c = gfl(w + 7);
             const V2 lc = b == 0 ? mk(K.blk_lcx, K.blk_lcy) : (b < K.nblk ? mk(K.blkx_lcx[b], K.blkx_lcy[b]) : mk(K.ag_lcx, K.ag_lcy));
             const V2 r = rmul(x.q, lc);
-            x.p = mk(gfl(w + 0) - r.x, gfl(w + 1) - r.y);
+            x.p = K.hidden ? mk(gfl(w + 8), gfl(w + 9)) : mk(gfl(w + 0) - r.x, gfl(w + 1) - r.y);   // hidden: see Sim::load()
         } else {
             x.p = mk(ct[CT_WALLPOS + 2 * (b - K.nb)], ct[CT_WALLPOS + 2 * (b - K.nb) + 1]);
             x.q.s = 0.0f; x.q.c = 1.0f;

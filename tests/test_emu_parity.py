@@ -172,6 +172,8 @@ def test_spare_episodes_bit_exact(variant, monkeypatch):
     and auto-reset by copying it; forced on here for a small batch: results are those of the fused respawn, bit for bit —
     also across explicit masked resets, parameter changes and state uploads, which invalidate spares."""
     monkeypatch.setenv("MRP_SPARES", "1")
+    if variant % 2:
+        monkeypatch.setenv("MRP_REFILL_CAP", "16")   # few spares per step: envs that finish without one take the fused respawn
     N, T, cap = 80, 150, 30
     h = abi.Handle(variant, N, seed=13 + variant, max_episode_steps=cap, lib=emu_lib())
     rep = rollout_compare(h, variant, N, T, seed=13 + variant, max_episode_steps=cap, nthreads=4)
