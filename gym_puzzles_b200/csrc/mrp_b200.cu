@@ -847,7 +847,7 @@ struct mrp_handle {
     uint32_t* r_narrow;
     float* r_pool;
     double* r_stats;
-    int use_spares;   // MRP_SPARES (default: from 32,768 envs with auto-reset, capacity-32 build): next episodes computed ahead of time
+    int use_spares;   // MRP_SPARES (default: from 131,072 envs with auto-reset, capacity-32 build): next episodes computed ahead of time
     int num_sms;      // multiprocessors of the handle's device (148 on B200); persistent / queue grids are sized from it
     int nchunks;       // mrp_step: the env range runs as nchunks independent pipelines on separate streams
     int nchunks_host;  // mrp_step_host: same, with each chunk's H2D / D2H copies on its stream
@@ -1156,7 +1156,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
 #ifdef MRP_WIDE
     h->use_spares = 0;
 #else
-    h->use_spares = getenv("MRP_SPARES") ? atoi(getenv("MRP_SPARES")) : (cfg->num_envs >= 32768 ? 1 : 0);
+    // default from 131,072 envs: below, a step is short enough (0.6 ms at 65,536 v0 envs) for the three extra stream operations of
+    // the spare list to cost 5 % (measured), and the fused respawn's tail hides less often behind nothing
+    h->use_spares = getenv("MRP_SPARES") ? atoi(getenv("MRP_SPARES")) : (cfg->num_envs >= 131072 ? 1 : 0);
 #endif
     if (h->use_spares && K.auto_reset) {
         const size_t sbytes = sizeof(uint32_t) * ntiles * kTile * K.w_total;
@@ -1260,7 +1262,9 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     }
     // measured end to end (1M Heavy-v0 envs, pinned buffers): 7.09 / 6.66 / 6.25 / 6.37 ms per step with 1 / 2 / 3 / 4 waves; 524,288 envs
     // 3.91 / 3.65 / 3.58 / 3.60; v0 4.08 / 3.75 / 3.63 / 3.67 (profiles/r2_e2e_waves.md)
-    h->host_waves = getenv("MRP_HOST_WAVES") ? atoi(getenv("MRP_HOST_WAVES")) : (cfg->num_envs >= 262144 ? 3 : 1);
+    // (the square variant's step is dominated by the velocity solve of its big islands, which concurrent waves only slow down:
+    // 16.3 ms with one wave, 19.7 with three, 524,288 envs)
+    h->host_waves = getenv("MRP_HOST_WAVES") ? atoi(getenv("MRP_HOST_WAVES")) : (cfg->num_envs >= 262144 && cfg->variant != MRP_VARIANT_SQUARE_V2 ? 3 : 1);
     if (h->host_waves < 1 || h->host_waves > kMaxWaves || h->nchunks_host < 2 * h->host_waves) h->host_waves = 1;
     {
         // wave boundaries in eighths of the chunks; every wave spans at least two chunks (its front stream and the stream of its

@@ -3,7 +3,9 @@
 # 1) launch list (gpu__time_duration per launch, last 3 steps)  2) --set full of every kernel of the last step
 set -e
 TAG=${1:-rX}
-CMD="python profiles/profile_step.py"
+# spare episodes off for the step capture: their refill pass launches the same kernels a second time during the first steps after
+# the reset, which would shift the skip counts below; the steady-state kernels of a step are the same either way
+CMD="env MRP_SPARES=0 python profiles/profile_step.py"
 # k_out_rows (row fix-up of mrp_step_host with pinned buffers, a few microseconds) is left out so that the per-step skip counts
 # below stay aligned with the 11 kernels of a device-resident step
 KERNELS='regex:^k_(broad|narrow|pre|solve_vel|solve_pos|solve_big|post|post_events|reset_list)$'
