@@ -85,6 +85,8 @@ def test_chunked_streams_are_invariant(monkeypatch):
     chk = abi.Handle("MultiRobotPuzzleHeavy-v0", N, seed=4, max_episode_steps=25)
     # front-half waves + big islands on their own kernel: the large-batch flow of mrp_step_host (pinned buffers: early row copies)
     monkeypatch.setenv("MRP_BIG", "1")
+    monkeypatch.setenv("MRP_SPARES", "1")      # ... with spare episodes: the auto-resets of the back chunks copy what the refill pass prepared
+    monkeypatch.setenv("MRP_REFILL_MIN", "1")
     wavs = []
     for w in ("2", "3", "4"):
         monkeypatch.setenv("MRP_HOST_WAVES", w)
