@@ -839,6 +839,7 @@ struct mrp_handle {
     uint8_t* mask_dev;  // mrp_reset_host: staging buffer of the host mask (allocated on first use)
     int fused;        // MRP_FUSED_STEP=1: single fused kernel per step (debug / A-B comparison)
     size_t smem_vel, smem_pos, smem_broad, smem_pre, smem_post, smem_big;
+    int big_ctas;     // CTAs of k_solve_big per SM (MRP_BIG_CTAS)
     int big_split;    // islands with more than two contacts go to k_solve_big on a side stream (MRP_BIG, default: from 32768 envs)
     int solver_ctas;  // persistent solver CTAs per SM
     int reset_lanes;  // MRP_RESET_LANES: lanes per warp that take an env in the auto-reset / spare-episode passes
@@ -1084,6 +1085,8 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     h->fused = getenv("MRP_FUSED_STEP") ? 1 : 0;
     h->reset_lanes = getenv("MRP_RESET_LANES") ? atoi(getenv("MRP_RESET_LANES")) : 32;
     if (h->reset_lanes < 1 || h->reset_lanes > 32 || (h->reset_lanes & (h->reset_lanes - 1))) h->reset_lanes = 32;
+    h->big_ctas = getenv("MRP_BIG_CTAS") ? atoi(getenv("MRP_BIG_CTAS")) : 1;
+    if (h->big_ctas < 1 || h->big_ctas > 4) h->big_ctas = 1;
     h->solver_ctas = getenv("MRP_SOLVER_CTAS") ? atoi(getenv("MRP_SOLVER_CTAS")) : 4;
     if (h->solver_ctas < 1) h->solver_ctas = 1;
     // small batches are one chunk unless the environment variables say otherwise (tests exercise chunking that way)
@@ -1556,7 +1559,7 @@ static void launch_front(mrp_handle* h, const SimConst& K, cudaStream_t st, bool
     if (big_on) {
         cudaEventRecord(efork, st);
         cudaStreamWaitEvent(sb, efork, 0);
-        k_solve_big<<<(unsigned)h->num_sms, kBigLanes, h->smem_big, sb>>>(Ks);
+        k_solve_big<<<(unsigned)h->num_sms * (unsigned)h->big_ctas, kBigLanes, h->smem_big, sb>>>(Ks);
         cudaEventRecord(ejoin, sb);
         h->launches += 1;
     }
@@ -1629,7 +1632,7 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         cudaStream_t sb = h->cstream[0];
         if (!side_on) cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(sb, h->cpre, 0);
-        k_solve_big<<<nsm, kBigLanes, h->smem_big, sb>>>(Ks);
+        k_solve_big<<<nsm * (unsigned)h->big_ctas, kBigLanes, h->smem_big, sb>>>(Ks);
         mark(4, sb);
         cudaEventRecord(h->cbig, sb);
         h->launches += 1;

@@ -15,6 +15,14 @@
  * (NULL = legacy default stream).  Stream-ordered calls never synchronise the host.
  * There is no CPU implementation behind this ABI: without a CUDA device
  * mrp_create() fails.
+ *
+ * Device memory of a handle (MultiRobotPuzzleHeavy-v0, per env): state 2.2 KB, solver task pool 4.9 KB (a worst-case
+ * reservation, touched only for touching contacts), queues 0.5 KB, action / observation / reward rows 0.23 KB; from
+ * 131,072 envs also the spare episodes (next episodes computed ahead of time, so that an
+ * auto-reset is a copy): a second state buffer and observation buffer (2.4 KB) plus the queues of the refill pass for an
+ * eighth of the batch (0.7 KB).  1,048,576 envs: ~11 GB.  Steps of batches below 32,768 envs are replayed from a CUDA
+ * graph; mrp_step_host pipelines large batches (front-half waves, chunked result copies).  None of this changes
+ * results; the environment variables that switch it are listed in INTEGRATION.md §4.
  */
 #ifndef MRP_B200_H
 #define MRP_B200_H

@@ -6,7 +6,13 @@ import os
 import sys
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-os.environ.setdefault("MRP_CHUNKS_HOST", "3")
+os.environ.setdefault("MRP_CHUNKS_HOST", "8")
+os.environ.setdefault("MRP_HOST_WAVES", "3")     # front-half waves of mrp_step_host
+os.environ.setdefault("MRP_SPARES", "1")         # spare episodes: refill pass (list mode of the pipeline kernels) + reset by copy
+os.environ.setdefault("MRP_REFILL_MIN", "1")
+os.environ.setdefault("MRP_OVERLAP_POST", "1")
+os.environ.setdefault("MRP_BIG", "1")
+os.environ.setdefault("MRP_GRAPH", "0")
 import numpy as np
 import torch
 
@@ -15,7 +21,7 @@ from gym_puzzles_b200 import abi
 
 rng = np.random.default_rng(0)
 for env_id, n_agents, N in [("MultiRobotPuzzleHeavy-v0", 0, 1500), ("MultiRobotPuzzle-v0", 0, 700), ("MultiRobotPuzzle-v2", 0, 700),
-                            ("MultiRobotPuzzleHeavy-v2", 5, 300)]:
+                            ("MultiRobotPuzzleHeavy-v2", 5, 300), ("MultiRobotPuzzleSquare-v2", 0, 400)]:
     h = abi.Handle(env_id, N, seed=1, n_agents=n_agents, max_episode_steps=12)
     h.enable_terminal_info()
     if env_id.endswith("v2"):
