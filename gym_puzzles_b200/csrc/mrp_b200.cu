@@ -137,7 +137,7 @@ MRP_HD void push_narrow(const SimConst& K, int64_t env, CMask need, int base) {
 // returns the number of solver constraints of the env (0: no island task was queued for it)
 // staged = the warp's action rows were copied into its wall slots (k_pre, coalesced): rows are read from there, walls set afterwards
 MRP_HD int pre_lane(const SimConst& K, float* sm, const float* ct, int64_t env, uint32_t* m12, const float* staged = nullptr, unsigned vmask = 0u) {
-    Env e(K, sm, ct, env, nullptr, 13);
+    Env e(K, sm, ct, env, nullptr, 8);
     float a[3 * MRP_MAX_AGENTS];
     if (K.hidden) {
         // the hidden step of reset(): action_space.sample() from the reset stream of the episode that just spawned (mrp00:411)
@@ -529,14 +529,14 @@ __global__ void __launch_bounds__(kBlock) k_pre(const __grid_constant__ SimConst
     const bool valid = env >= 0;   // every lane of the warp stays for the warp-aggregated list reservation
     int T = -1;
     uint32_t m12[2] = {0u, 0u};
-    float* const lsm = lane_sm(smem + kCtPad, 13 * K.nb + 24);
+    float* const lsm = lane_sm(smem + kCtPad, 8 * K.nb + 24);
     const float* staged = nullptr;
     if (K.stage_rows && !K.hidden) {
         // the 32 action rows of the warp's envs are one contiguous run of 32 x act_dim floats: consecutive lanes fetch
         // consecutive words (coalesced) into the warp's wall slots (24 words per lane, set only after the rows have been read),
         // then every lane picks up its own row
         const int lane = threadIdx.x & 31;
-        float* blk = lsm - lane + (13 * K.nb) * 32;
+        float* blk = lsm - lane + (8 * K.nb) * 32;
         const int64_t first = loc - lane;
         const int words = (int)((loc1 - first < 32 ? loc1 - first : 32) * K.act_dim);
         const float* src = K.act + (K.env0 + first) * K.act_dim;
@@ -1200,7 +1200,7 @@ int MRP_API(mrp_create)(const mrp_config* cfg, mrp_handle** out) {
     h->smem_bytes = sizeof(float) * ((size_t)kCtPad + (size_t)K.smem_words * kBlock);
     h->smem_broad = sizeof(float) * ((size_t)kCtPad + (size_t)(10 * K.nb + 4 * K.ndynfix) * kBlock);
     h->smem_post = sizeof(float) * ((size_t)kCtPad + (size_t)(11 * K.nb + 4 * K.ndynfix) * kBlock);
-    h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(13 * K.nb + 24) * kBlock);
+    h->smem_pre = sizeof(float) * ((size_t)kCtPad + (size_t)(8 * K.nb + 24) * kBlock);
     h->smem_vel = sizeof(float) * (size_t)(6 * (K.nb + 4)) * kBlock;
     h->smem_pos = sizeof(float) * (size_t)(9 * K.nb + 24) * kBlock;
     h->smem_big = sizeof(float) * ((size_t)(9 * K.nb + 24) + kBigRecWords) * kBigLanes;

@@ -318,7 +318,7 @@ struct Sim {
     //   17 full: pose/vel 0-5, q 6-7, p 8-9, cache 10-12, c0/a0/alpha0 13-16, walls, fat AABBs   (fused step, reset, k_post_events)
     //   11 k_post: 0-7, c0/a0 8-10, fat AABBs; no p (recomputed from c, q), no alpha0 (0: no TOI event is processed
     //      in this layout), no cache, no wall slots
-    //   13 k_pre: 0-9, cache 10-12, walls                     10 k_broad: 0-9, fat AABBs
+    //    8 k_pre: 0-7, walls (origin recomputed, rotation = q)   10 k_broad: 0-9, fat AABBs
     //    9 position solver: 0-5, cache 6-8, walls               6 velocity solver: 0-5, walls
     MRP_HD Sim(const SimConst& k, float* sm_, const float* ct_, int64_t env, float* vc_ = nullptr, int fdyn_ = kDynFields)
         : K(k), sm(sm_), ct(ct_), G(env_words(k, env)), env_i((int32_t)env), gid(k.env_id_base + (uint64_t)env), vcp(vc_), fdyn(fdyn_),
@@ -353,7 +353,7 @@ struct Sim {
 
     // body fields: 0 cx 1 cy 2 a 3 vx 4 vy 5 w (all bodies incl. walls) | 6 qs 7 qc 8 px 9 py | 10 cache.s 11 cache.c
     // 12 cache angle (last Rot evaluated for this body and the angle it belongs to) | 13 c0x 14 c0y 15 a0 16 alpha0.
-    // Kernels that do not need the tail allocate fewer words per body (fdyn): k_broad 10, k_pre 13, k_post 17;
+    // Kernels that do not need the tail allocate fewer words per body (fdyn): k_broad 10, k_pre 8, k_post 11, event / reset paths 17;
     // the solver kernels use 6 (velocities) and 9 (pose + cache at qoff = 6).
     // body-major, lane-strided: one base computation per body, then compile-time field offsets
     MRP_HD float* bp(int b) { return sm + (b < K.nb ? b * fdyn : wall_off + (b - K.nb) * 6) * MRP_SS; }
@@ -389,6 +389,7 @@ struct Sim {
     MRP_HD Rot body_rot(int b, float angle) {
         Rot q;
         if (b >= K.nb) { q.s = 0.0f; q.c = 1.0f; return q; }
+        if (fdyn == 8) return Rot{BX(b, 6), BX(b, 7)};   // k_pre: angles are the loaded ones throughout, q belongs to them
         if (qoff < 0) return INL ? rot_set_inline(angle) : rot_set(angle);
         float* const c = bp(b) + qoff * MRP_SS;
         if (c[2 * MRP_SS] == angle) { q.s = c[0]; q.c = c[MRP_SS]; return q; }
@@ -419,7 +420,9 @@ struct Sim {
     MRP_HD Xf body_xf(int b) {
         Xf x;
         if (b < K.nb) {
-            if (fdyn == 11) {  // p = c - R(q) * localCenter: the very expression sync_transform stores
+            if (fdyn == 8 && K.hidden) {   // first step after a spawn: the body origin as spawned (see load())
+                x.p = mk(gf(K.w_body + kBodyWords * b + 8), gf(K.w_body + kBodyWords * b + 9));
+            } else if (fdyn == 11 || fdyn == 8) {  // p = c - R(q) * localCenter: the very expression sync_transform stores
                 const V2 r = rmul(Rot{BX(b, 6), BX(b, 7)}, localCenter(b));
                 x.p = mk(B(b, 0) - r.x, B(b, 1) - r.y);
             } else {
@@ -439,7 +442,7 @@ struct Sim {
         V2 r = rmul(q, localCenter(b));
         BX(b, 6) = q.s;
         BX(b, 7) = q.c;
-        if (fdyn != 11) {
+        if (fdyn != 11 && fdyn != 8) {
             BX(b, 8) = B(b, 0) - r.x;
             BX(b, 9) = B(b, 1) - r.y;
         }
@@ -516,7 +519,9 @@ struct Sim {
             if (!want_vel) { p[3 * MRP_SS] = 0.0f; p[4 * MRP_SS] = 0.0f; p[5 * MRP_SS] = 0.0f; }
             const Rot q{p[6 * MRP_SS], p[7 * MRP_SS]};
             set_rot_cache(b, q, p[2 * MRP_SS]);
-            if (K.hidden && (fdyn == 10 || fdyn == 13)) {
+            if (fdyn == 8) {
+                // k_pre keeps no origin in shared memory: body_xf() recomputes it (or, for a hidden step, reads the spawn's)
+            } else if (K.hidden && fdyn == 10) {
                 // first step after a spawn: the body origin is the spawn position itself (b2Body's constructor), kept in the
                 // pre-step pose words by spawn_spare_lane until k_pre overwrites them; c - R(q) * localCenter rounds differently
                 p[8 * MRP_SS] = gf(K.w_body + kBodyWords * b + 8);
