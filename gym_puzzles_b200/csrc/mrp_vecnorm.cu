@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(kVnBlock) k_vn_apply(const __grid_constant__ V
 struct mrp_vecnorm {
     VnConst V;
     int device;
+    int num_sms;   // multiprocessors of the device (148 on B200): the persistent grids are sized from it
     int training;
     int64_t launches;
 };
@@ -307,6 +308,10 @@ int mrp_vecnorm_create(const mrp_vecnorm_config* cfg, mrp_vecnorm** out) {
     V.norm_obs = cfg->norm_obs; V.norm_reward = cfg->norm_reward;
     V.clip_obs = (float)cfg->clip_obs; V.clip_reward = (float)cfg->clip_reward; V.epsilon = cfg->epsilon; V.gamma = cfg->gamma;
     vn->device = cfg->device;
+    vn->num_sms = 148;
+#ifndef MRP_HOST_EMU
+    if (cudaDeviceGetAttribute(&vn->num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || vn->num_sms < 1) vn->num_sms = 148;
+#endif
     vn->training = cfg->training;
     const size_t C = (size_t)V.O + 1;
     int rc = VN_ALLOC(V.mean, sizeof(double) * C) | VN_ALLOC(V.var, sizeof(double) * C) | VN_ALLOC(V.count, sizeof(double) * 2) |
@@ -385,7 +390,7 @@ int mrp_vecnorm_moments(mrp_vecnorm* vn, const float* obs_dev, const float* rewa
     // count that is a multiple of O / gcd(O, 4)
     const int64_t n4 = ((int64_t)V.N * V.O) >> 2;
     int64_t grid = (n4 / 4 + kVnBlockM - 1) / kVnBlockM;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (int64_t)vn->num_sms * 8) grid = (int64_t)vn->num_sms * 8;
     if (grid < 1) grid = 1;
     int g = 4, o = V.O;
     while (o) { int t = g % o; g = o; o = t; }   // gcd(4, O)
@@ -432,7 +437,7 @@ int mrp_vecnorm_apply(mrp_vecnorm* vn, const float* obs_dev, const float* reward
     if (vn->training) { k_vn_merge<<<1, 128, 0, st>>>(V); vn->launches += 1; }
     const int64_t work = ((int64_t)V.N * V.O + 3) / 4;
     int64_t grid = (work + kVnBlock - 1) / kVnBlock;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)vn->num_sms * 16) grid = (int64_t)vn->num_sms * 16;
     k_vn_apply<<<(unsigned)grid, kVnBlock, 0, st>>>(V, obs_dev, reward_dev, done_dev, obs_out_dev, reward_out_dev, terminal_obs_dev);
     vn->launches += 1;
     if (cudaGetLastError() != cudaSuccess) return vn_fail(-10, "mrp_vecnorm_apply: launch failed");
