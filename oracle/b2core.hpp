@@ -12,8 +12,11 @@
 // SURVEY.md Appendix A/E (>=2.3.1 forks: brute-force b2FindMaxSeparation,
 // reference-face tolerance 0.1*linearSlop, Pade damping; b2_maxPolygonVertices = 16
 // as in pybox2d).  *** PARITY UNPINNED ***: the reference ships no golden vectors for
-// this path; this oracle is pinned only by hand-derived known-answer tests
-// (tests/test_oracle_kat.py).
+// this path; this oracle is pinned only by known-answer tests: hand-derived ones
+// (tests/test_oracle_kat.py) and ones whose answers come from outside this repository
+// (tests/test_b2_external_kats.py: the block solver's LCP solved by hand, a rotating-rod
+// time of impact in closed form, and the printed output of the Box2D manual's
+// "Hello Box2D" program, which this file reproduces digit for digit).
 //
 // One deliberate, documented deviation: b2Rot::Set uses correctly-rounded
 // sinf/cosf ((float)sin((double)a)); glibc 2.39 sinf differs from that by 1 ulp in

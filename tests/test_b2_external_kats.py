@@ -115,3 +115,34 @@ def test_toi_of_a_rotating_rod_matches_closed_form_geometry():
     # a swing that stops short of the wall: separated, t = 1
     sR2 = np.asarray((0, 0, 0, 0, 0, -0.3), dtype=np.float32)
     assert lib().orc_toi(4, _p(wall), _p(sW), 4, _p(rod), _p(sR2), C.byref(t)) == 4 and t.value == 1.0
+
+
+def test_hello_box2d_listing_of_the_box2d_manual():
+    """The one worked example Box2D itself publishes with numbers: "Hello Box2D" (Box2D v2.x manual, chapter 2; the program
+    is HelloWorld.cpp of the distribution).  A static ground box (half extents 50 x 10 at (0, -10)), a dynamic unit box
+    (half extents 1 x 1, density 1, friction 0.3) dropped from (0, 4) under gravity (0, -10), stepped 60 times with
+    timeStep = 1/60, 6 velocity and 2 position iterations, printing position and angle with "%4.2f %4.2f %4.2f".  The manual
+    lists the output as
+        0.00 4.00 0.00 / 0.00 3.99 0.00 / 0.00 3.98 0.00 / ... / 0.00 1.25 0.00 / 0.00 1.13 0.00 / 0.00 1.01 0.00
+    i.e. free fall through step 45 (1.13 is 1.1250004 in float32: the accumulated rounding decides the digit) and, in step 46,
+    the continuous-collision path: the fall would end at 0.997, b2TimeOfImpact stops the box linearSlop above the ground's
+    skin and the TOI sub-step leaves it at 1.0146 — "1.01", where it stays.  Exercises the integrator, fat-AABB pair creation,
+    b2TimeOfImpact / SolveTOI against a static body, the contact solver and the position correction on numbers that come from
+    Box2D's own documentation.  The oracle's world has no gravity term (the reference uses gravity (0, 0)); gravity is applied
+    as the force m g, which is the same arithmetic: v += h * (invMass * force) with invMass * (m g) = g exactly for m = 4."""
+    w = Box2D.b2World(gravity=(0, 0), doSleep=False)
+    w.CreateStaticBody(position=(0.0, -10.0), fixtures=Box2D.fixtureDef(shape=Box2D.polygonShape(box=(50.0, 10.0))))
+    box = w.CreateDynamicBody(position=(0.0, 4.0), angle=0.0, linearDamping=0.0, angularDamping=0.0,
+                              fixtures=Box2D.fixtureDef(shape=Box2D.polygonShape(box=(1.0, 1.0)), density=1.0, friction=0.3))
+    assert box.mass == 4.0
+    lines = []
+    for _ in range(60):
+        box.ApplyForce((0.0, -10.0 * box.mass), box.worldCenter, True)
+        w.Step(1.0 / 60.0, 6, 2)
+        lines.append("%4.2f %4.2f %4.2f" % (box.position[0], box.position[1], box.angle))
+    assert lines[:3] == ["0.00 4.00 0.00", "0.00 3.99 0.00", "0.00 3.98 0.00"]
+    assert lines[43:46] == ["0.00 1.25 0.00", "0.00 1.13 0.00", "0.00 1.01 0.00"]
+    assert all(ln == "0.00 1.01 0.00" for ln in lines[45:])           # "the box lands on the ground box and comes to rest"
+    # free fall of the semi-implicit Euler integrator: y_n = 4 - n (n + 1) / 720 while nothing touches
+    ys = [float(ln.split()[1]) for ln in lines[:45]]
+    assert all(abs(y - (4.0 - n * (n + 1) / 720.0)) <= 0.00501 for n, y in enumerate(ys, start=1))
