@@ -1618,8 +1618,10 @@ static void launch_step(mrp_handle* h, const SimConst& K, cudaStream_t st, bool 
         cudaEventRecord(h->cpre, st);
         cudaStreamWaitEvent(side, h->cpre, 0);
         k_post<<<grid, kBlock, h->smem_post, side>>>(K, 0);
+        mark(2, side);
 #ifndef MRP_WIDE
         launch_events(h, K, side, pgrid, 1);
+        mark(3, side);
 #endif
         cudaEventRecord(h->cfree, side);
     }
