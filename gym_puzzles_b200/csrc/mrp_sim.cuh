@@ -117,7 +117,8 @@ constexpr int kMaxShapes = 10;    // stem, bar, octagon, two wheels, two wall bo
 constexpr int CT_SHAPES = 120;    // [kMaxShapes][33]
 constexpr int CT_SHAPEX = CT_SHAPES + kMaxShapes * kShapeWords;  // [kMaxShapes][6] bounding data per shape: centre x,y, half extents hx,hy, radius, is_box
 constexpr int CT_WALLBOX = CT_SHAPEX + kMaxShapes * 6;          // [4][4] wall polygons in world space (lo.x, lo.y, hi.x, hi.y), no radius
-constexpr int CT_WORDS = CT_WALLBOX + 16;
+constexpr int CT_BODYP = CT_WALLBOX + 16;                        // [20][4] per body (dynamic bodies, then the four walls: zeros): invMass, invI, local centre x, y
+constexpr int CT_WORDS = CT_BODYP + 80;
 
 // ---- internal per-env state words in HBM ---------------------------------------------
 // Tiled [tile][word][lane]: envs are grouped in tiles of kTile = 32 (one warp of the per-env kernels); inside a tile
@@ -399,12 +400,10 @@ struct Sim {
     }
 
     MRP_HD bool is_dyn(int b) const { return b < K.nb; }
-    MRP_HD float invMass(int b) const { return b == 0 ? K.blk_invMass : (b < K.nblk ? K.blkx_invMass[b] : (b < K.nb ? K.ag_invMass : 0.0f)); }
-    MRP_HD float invI(int b) const { return b == 0 ? K.blk_invI : (b < K.nblk ? K.blkx_invI[b] : (b < K.nb ? K.ag_invI : 0.0f)); }
-    MRP_HD V2 localCenter(int b) const {
-        return b == 0 ? mk(K.blk_lcx, K.blk_lcy)
-                      : (b < K.nblk ? mk(K.blkx_lcx[b], K.blkx_lcy[b]) : (b < K.nb ? mk(K.ag_lcx, K.ag_lcy) : mk(0.0f, 0.0f)));
-    }
+    // one table read each (CT_BODYP, filled by fill_variant from blk_* / blkx_* / ag_*) instead of a chain of selects over kernel parameters
+    MRP_HD float invMass(int b) const { return ct[CT_BODYP + 4 * b]; }
+    MRP_HD float invI(int b) const { return ct[CT_BODYP + 4 * b + 1]; }
+    MRP_HD V2 localCenter(int b) const { return mk(ct[CT_BODYP + 4 * b + 2], ct[CT_BODYP + 4 * b + 3]); }
     // fixtures [f0, f1) of dynamic body b (creation order: the blocks' fixtures, then the robots')
     MRP_HD void fix_range(int b, int& f0, int& f1) const {
         if (b >= K.nblk) { f0 = K.nbf + K.per_agent * (b - K.nblk); f1 = f0 + K.per_agent; }

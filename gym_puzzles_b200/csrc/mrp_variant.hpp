@@ -328,6 +328,13 @@ inline int build_variant(int variant, int n_agents, SimConst* K, float* ctab, mr
         wf[2] = (hx + kPolygonRadius) + kAabbExtension; wf[3] = (hy + kPolygonRadius) + kAabbExtension;
         fix(K->nb + k, k < 2 ? 5 : 6, 0.2f);
     }
+    for (int b = 0; b < K->nb; ++b) {   // walls (bodies nb .. nb + 3) keep the zeros of the memset
+        float* bp = ctab + CT_BODYP + 4 * b;
+        bp[0] = b == 0 ? K->blk_invMass : (b < K->nblk ? K->blkx_invMass[b] : K->ag_invMass);
+        bp[1] = b == 0 ? K->blk_invI : (b < K->nblk ? K->blkx_invI[b] : K->ag_invI);
+        bp[2] = b == 0 ? K->blk_lcx : (b < K->nblk ? K->blkx_lcx[b] : K->ag_lcx);
+        bp[3] = b == 0 ? K->blk_lcy : (b < K->nblk ? K->blkx_lcy[b] : K->ag_lcy);
+    }
     return 0;
 }
 
