@@ -1,4 +1,5 @@
 # main chain of mrp_step on a library stream of middle priority (MRP_MAIN_PRIO=1) vs on the caller's stream
+# (the code under test was measured and NOT kept: DESIGN.md §8, "Measured dead ends"; this script is the record of the A/B)
 for i in 1 2; do echo "== MRP_MAIN_PRIO=0"; python profiles/quickbench.py; echo "== MRP_MAIN_PRIO=1"; MRP_MAIN_PRIO=1 python profiles/quickbench.py; done
 echo "== trace 0 / 1"
 MRP_TRACE=1 python profiles/quickbench.py | grep "mrp trace" | tail -2

@@ -1,4 +1,5 @@
 # fifth solver queue: two-1-point-contact islands of envs whose position solve ran all 60 sweeps on the previous step, taken first
+# (the code under test was measured and NOT kept: DESIGN.md §8, "Measured dead ends"; this script is the record of the A/B)
 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_square_variant.py -m gpu -x -q 2>&1 | tail -2
 OLD=gym_puzzles_b200/csrc/build/var/libmrp_old.so
 for i in 1 2 3; do echo "== old"; MRP_LIB_PATH=$OLD python profiles/quickbench.py; echo "== new"; python profiles/quickbench.py; done
