@@ -146,6 +146,9 @@ int b2s_contact_get(void* h, int k, float* out12) {
     return (int)w->contactList.size();
 }
 long b2s_toi_events(void* h) { return S(h)->w->stat_toi_events; }
+// Box2D version fork of the collision routine for the worlds of this library (b2core.hpp g_fork_230; no pybox2d counterpart:
+// it stands for which box2d-py wheel is installed).  Returns the previous setting.
+int b2s_set_box2d_fork(int fork_230) { int old = g_fork_230; g_fork_230 = fork_230 ? 1 : 0; return old; }
 
 // the Philox stream the oracle / product spawn from, so the harness can feed the reference's np.random.uniform and
 // action_space.sample() the very same draws (oracle/philox.hpp)

@@ -117,7 +117,8 @@ def test_toi_of_a_rotating_rod_matches_closed_form_geometry():
     assert lib().orc_toi(4, _p(wall), _p(sW), 4, _p(rod), _p(sR2), C.byref(t)) == 4 and t.value == 1.0
 
 
-def test_hello_box2d_listing_of_the_box2d_manual():
+@pytest.mark.parametrize("fork_230", [0, 1])
+def test_hello_box2d_listing_of_the_box2d_manual(fork_230):
     """The one worked example Box2D itself publishes with numbers: "Hello Box2D" (Box2D v2.x manual, chapter 2; the program
     is HelloWorld.cpp of the distribution).  A static ground box (half extents 50 x 10 at (0, -10)), a dynamic unit box
     (half extents 1 x 1, density 1, friction 0.3) dropped from (0, 4) under gravity (0, -10), stepped 60 times with
@@ -130,6 +131,17 @@ def test_hello_box2d_listing_of_the_box2d_manual():
     b2TimeOfImpact / SolveTOI against a static body, the contact solver and the position correction on numbers that come from
     Box2D's own documentation.  The oracle's world has no gravity term (the reference uses gravity (0, 0)); gravity is applied
     as the force m g, which is the same arithmetic: v += h * (invMass * force) with invMass * (m g) = g exactly for m = 4."""
+    # both collision forks (Box2D 2.3.0 / >= 2.3.1, oracle/b2core.hpp g_fork_230) have to print the same listing: the manual's output did not
+    # change between those releases
+    shim = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "libb2shim.so"))
+    old = shim.b2s_set_box2d_fork(fork_230)
+    try:
+        _hello_box2d()
+    finally:
+        shim.b2s_set_box2d_fork(old)
+
+
+def _hello_box2d():
     w = Box2D.b2World(gravity=(0, 0), doSleep=False)
     w.CreateStaticBody(position=(0.0, -10.0), fixtures=Box2D.fixtureDef(shape=Box2D.polygonShape(box=(50.0, 10.0))))
     box = w.CreateDynamicBody(position=(0.0, 4.0), angle=0.0, linearDamping=0.0, angularDamping=0.0,
