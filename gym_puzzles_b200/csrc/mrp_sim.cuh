@@ -1204,19 +1204,25 @@ struct Sim {
         if (r.vpc == 2) { vr_op_1d<1>(r); vr_op_block(r); }
         else vr_op_1d<2>(r);
     }
+    // the velocities of the bodies contact d shares with contact s, straight from s's registers: what a store of s's velocities to the
+    // lane's body slots followed by a load of d's would deliver (a body d does not share with s still holds what d left there)
+    MRP_HD void vr_forward(const VelReg& s, VelReg& d) {
+        if (d.bA == s.bA) { d.vA = s.vA; d.wA = s.wA; } else if (d.bA == s.bB) { d.vA = s.vB; d.wA = s.wB; }
+        if (d.bB == s.bA) { d.vB = s.vA; d.wB = s.wA; } else if (d.bB == s.bB) { d.vB = s.vB; d.wB = s.wB; }
+    }
     MRP_HD bool vr_sweep_pair(VelReg& r0, VelReg& r1, int iters) {
-        vr_load_vel(r0);
+        // r0 holds current velocities on entry (vr_begin_pair, or the forward at the end of the previous sweep): the shared-memory
+        // round trip between the two contacts (12 stores + 12 loads on the dependent chain of every sweep) is replaced by selects
         vr_contact_ops(r0);
-        vr_store_vel(r0);
-        vr_load_vel(r1);
+        vr_forward(r0, r1);
         vr_contact_ops(r1);
-        vr_store_vel(r1);
         ++r0.sweep;
         if (!(r0.changed || r1.changed) || r0.sweep == iters) {
             vr_store(r0);
             vr_store(r1);   // contact 1 ran last: its velocities are the final ones for shared bodies
             return true;
         }
+        vr_forward(r1, r0);
         r0.changed = false;
         r1.changed = false;
         return false;
