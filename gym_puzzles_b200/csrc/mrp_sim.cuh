@@ -1191,8 +1191,8 @@ struct Sim {
         }
         return false;
     }
-    // two-contact islands: both constraint records stay in registers; only the body velocities travel through the
-    // lane's shared-memory slots between the two contacts (they may share one or both bodies)
+    // two-contact islands: both constraint records and the velocities of their bodies stay in registers; the bodies the two
+    // contacts share (one or both) are handed from one contact to the other by vr_forward
     MRP_HD void vr_begin_pair(VelReg& r0, VelReg& r1) {
         r0.T = 2; r0.t = 0; r0.j = 0; r0.sweep = 0; r0.changed = false;
         vr_load(r0);
